@@ -1,0 +1,119 @@
+// HOST EMULATION (test infrastructure only, never loaded by the product path).
+// Straight-loop restatement of the conv / wgrad *contracts* of include/mmhand_sm100.h so that the host
+// logic (layouts, tap tables, engine sequencing, elementwise index math) can be exercised on a CPU-only
+// box. Built into libmmhand_hostemu.so by tests/hostemu.py with -DMMH_HOST_EMU.
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/mmhand_sm100.h"
+#include "ew_common.h"
+#include "host_common.h"
+
+struct MmhConvPlan { MmhConvDesc d; };
+struct MmhWgradPlan { MmhWgradDesc d; };
+
+extern "C" int mmh_conv_plan_create(const MmhConvDesc* d, MmhConvPlan** plan) {
+  MMH_CHECK(d && plan, "null argument");
+  MMH_CHECK(d->T >= 1 && d->T <= MMH_MAX_TAPS, "T=%d out of range", d->T);
+  MMH_CHECK(d->C == 16 || d->C == 32 || d->C == 48 || (d->C % 64) == 0, "C=%d unsupported", d->C);
+  MMH_CHECK(d->N >= 16 && (d->N % 16) == 0, "N=%d must be a multiple of 16", d->N);
+  MMH_CHECK(d->N <= 256 || (d->N % 128) == 0, "N=%d unsupported", d->N);
+  MMH_CHECK((d->a_ld % 8) == 0 && d->a_ld >= d->C, "a_ld=%d invalid", d->a_ld);
+  MMH_CHECK((d->out_ld % 8) == 0, "out_ld=%d must be a multiple of 8", d->out_ld);
+  *plan = new MmhConvPlan{*d};
+  return 0;
+}
+extern "C" int mmh_conv_plan_destroy(MmhConvPlan* p) { delete p; return 0; }
+
+extern "C" int mmh_conv_run(const MmhConvPlan* plan, void*) {
+  const MmhConvDesc& d = plan->d;
+  const uint16_t* a = static_cast<const uint16_t*>(d.a);
+  const uint16_t* w = static_cast<const uint16_t*>(d.w);
+  const int w_taps = d.w_taps > 0 ? d.w_taps : d.T;
+  (void)w_taps;
+  const int64_t hw = static_cast<int64_t>(d.Hg) * d.Wg;
+  const int n_store = d.n_store > 0 ? ((d.n_store + 15) / 16 * 16) : d.N;
+  std::vector<float> acc(d.N);
+  std::vector<float> arow(d.C);
+  for (int64_t q = 0; q < d.M; ++q) {
+    const int64_t img = q / hw, rem = q % hw;
+    const int h = static_cast<int>(rem / d.Wg), x = static_cast<int>(rem % d.Wg);
+    const bool valid = h < d.Hv && x < d.Wv;
+    if (!valid && !d.zero_invalid) continue;
+    for (int n = 0; n < d.N; ++n) acc[n] = 0.f;
+    if (valid) {
+      for (int t = 0; t < d.T; ++t) {
+        const int64_t r = q + d.shift[t];
+        if (r < 0 || r >= d.a_rows) continue;
+        const uint16_t* ar = a + r * d.a_ld;
+        for (int c = 0; c < d.C; ++c) arow[c] = mmh::bf2f(ar[c]);
+        const int slot = d.w_taps > 0 ? d.w_slot[t] : t;
+        const uint16_t* wt = w + static_cast<int64_t>(slot) * d.N * d.C;
+        for (int n = 0; n < d.N; ++n) {
+          const uint16_t* wr = wt + static_cast<int64_t>(n) * d.C;
+          float s = 0.f;
+          for (int c = 0; c < d.C; ++c) s += arow[c] * mmh::bf2f(wr[c]);
+          acc[n] += s;
+        }
+      }
+      for (int n = 0; n < d.N; ++n) {
+        float v = acc[n];
+        if (d.bias) v += d.bias[n];
+        if (d.act == 1) v = v > 0.f ? v : 0.f;
+        else if (d.act == 2) v = tanhf(v);
+        acc[n] = v;
+      }
+    }
+    const int64_t orow = img * d.out_img_rows + static_cast<int64_t>(h * d.out_sh + d.out_h0) * d.out_wg +
+                         (x * d.out_sw + d.out_w0);
+    if (d.out_f32) {
+      float* o = static_cast<float*>(d.out) + orow * d.out_ld;
+      for (int n = 0; n < n_store && n < d.N; ++n) o[n] = acc[n];
+    } else {
+      uint16_t* o = static_cast<uint16_t*>(d.out) + orow * d.out_ld;
+      for (int n = 0; n < n_store && n < d.N; ++n) o[n] = mmh::f2bf(acc[n]);
+    }
+  }
+  return 0;
+}
+
+extern "C" int mmh_wgrad_plan_create(const MmhWgradDesc* d, MmhWgradPlan** plan) {
+  MMH_CHECK(d && plan, "null argument");
+  MMH_CHECK(d->T >= 1 && d->T <= MMH_MAX_TAPS, "T=%d out of range", d->T);
+  MMH_CHECK((d->C % 16) == 0 && (d->N % 16) == 0, "C=%d / N=%d must be multiples of 16", d->C, d->N);
+  MMH_CHECK(d->C <= 256 || (d->C % 256) == 0, "C=%d unsupported", d->C);
+  *plan = new MmhWgradPlan{*d};
+  return 0;
+}
+extern "C" int mmh_wgrad_plan_destroy(MmhWgradPlan* p) { delete p; return 0; }
+
+extern "C" int mmh_wgrad_run(const MmhWgradPlan* plan, void*) {
+  const MmhWgradDesc& d = plan->d;
+  const uint16_t* a = static_cast<const uint16_t*>(d.a);
+  const uint16_t* dy = static_cast<const uint16_t*>(d.dy);
+  const int Ns = d.N_store > 0 ? d.N_store : d.N;
+  const int Cs = d.C_store > 0 ? d.C_store : d.C;
+  std::vector<float> dyr(Ns), ar(Cs);
+  for (int t = 0; t < d.T; ++t) {
+    float* dw = d.dw + static_cast<int64_t>(d.tap_index[t]) * Ns * Cs;
+    for (int64_t q = 0; q < d.M; ++q) {
+      const int64_t r = q + d.shift[t];
+      if (r < 0 || r >= d.a_rows) continue;
+      bool any = false;
+      for (int n = 0; n < Ns; ++n) { dyr[n] = mmh::bf2f(dy[q * d.dy_ld + n]); any |= dyr[n] != 0.f; }
+      if (!any) continue;
+      for (int c = 0; c < Cs; ++c) ar[c] = mmh::bf2f(a[r * d.a_ld + c]);
+      for (int n = 0; n < Ns; ++n) {
+        const float g = dyr[n];
+        if (g == 0.f) continue;
+        float* row = dw + static_cast<int64_t>(n) * Cs;
+        for (int c = 0; c < Cs; ++c) row[c] += g * ar[c];
+      }
+    }
+  }
+  return 0;
+}

@@ -1,0 +1,40 @@
+// Helpers shared by the device kernels and their host emulation (tests): bf16 <-> fp32 by bit
+// manipulation (identical results on both sides), host/device qualifiers.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#ifdef MMH_HOST_EMU
+#define MMH_HD inline
+#else
+#include <cuda_runtime.h>
+#define MMH_HD __host__ __device__ __forceinline__
+#endif
+
+namespace mmh {
+
+MMH_HD float bf2f(uint16_t v) {
+  uint32_t u = static_cast<uint32_t>(v) << 16;
+  float f;
+#if defined(__CUDA_ARCH__)
+  f = __uint_as_float(u);
+#else
+  memcpy(&f, &u, 4);
+#endif
+  return f;
+}
+
+// round-to-nearest-even, NaN kept quiet
+MMH_HD uint16_t f2bf(float f) {
+  uint32_t u;
+#if defined(__CUDA_ARCH__)
+  u = __float_as_uint(f);
+#else
+  memcpy(&u, &f, 4);
+#endif
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return static_cast<uint16_t>((u >> 16) | 0x40u);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+
+}  // namespace mmh
