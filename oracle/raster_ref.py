@@ -1,0 +1,41 @@
+"""ORACLE (test infrastructure): CPU restatement of the reference's keypoint -> heatmap rasteriser.
+
+Follows data/generic_dataset.py:191-199 (get_heatmaps: one map per joint, stacked, float32),
+:208-217 (gen_heatmap: clamp >1 to 1, then zero everything < 0.0099, in float64, cast last) and
+:238-242 (gaussian_kernel: mgrid over (height, width), exp(-D2 / 2.0 / sigma / sigma), same evaluation order).
+The reference module itself cannot be imported (``from cv2 import cv2``, easydict), so this
+restatement is pinned by known-answer tests (tests/test_raster_oracle.py): parity unpinned by reference tests.
+"""
+import numpy as np
+
+
+def gaussian_kernel(width, height, x, y, sigma):
+    gridy, gridx = np.mgrid[0:height, 0:width]
+    D2 = (gridx - x) ** 2 + (gridy - y) ** 2
+    return np.exp(-D2 / 2.0 / sigma / sigma)
+
+
+def gen_heatmap(x, y, shape, sigma, thresh=0.0099):
+    # the reference passes (shape[0], shape[1]) as (width, height): Q15, harmless on square frames
+    m = gaussian_kernel(shape[0], shape[1], x, y, sigma)
+    m[m > 1] = 1
+    m[m < thresh] = 0
+    return m
+
+
+def get_heatmaps(uv, shape=(256, 256), sigma=6.0, thresh=0.0099):
+    """uv: [J, 2] float64 (x, y) -> [J, H, W] float32."""
+    return np.stack([gen_heatmap(float(x), float(y), shape, sigma, thresh).astype(np.float32) for x, y in uv])
+
+
+def get_heatmaps_batch(uv, shape=(256, 256), sigma=6.0, thresh=0.0099):
+    """uv: [N, J, 2] -> [N, J, H, W] float32 (vectorised, same arithmetic order)."""
+    uv = np.asarray(uv, dtype=np.float64)
+    H, W = shape[1], shape[0]
+    gy = np.arange(H, dtype=np.float64)[None, None, :, None]
+    gx = np.arange(W, dtype=np.float64)[None, None, None, :]
+    D2 = (gx - uv[..., 0][..., None, None]) ** 2 + (gy - uv[..., 1][..., None, None]) ** 2
+    m = np.exp(-D2 / 2.0 / sigma / sigma)
+    m[m > 1] = 1
+    m[m < thresh] = 0
+    return m.astype(np.float32)

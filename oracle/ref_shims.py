@@ -1,0 +1,97 @@
+"""ORACLE support (test infrastructure): import the *real* reference modules from /root/reference with the
+minimal shims of SURVEY.md section 8c (stub apex / skimage, random-init VGG19, CPU no-ops for .cuda()).
+Only usable where /root/reference exists (the build container); never on the GPU box and never by the product.
+"""
+import importlib
+import os
+import sys
+import types
+
+REF = os.environ.get("MMH_REFERENCE_ROOT", "/root/reference")
+
+
+def available():
+    return os.path.isdir(os.path.join(REF, "models"))
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    for k, v in attrs.items():
+        setattr(m, k, v)
+    sys.modules[name] = m
+    return m
+
+
+class _RefImport:
+    """Context manager: reference tree first on sys.path, our same-named packages hidden."""
+
+    NAMES = ("models", "losses", "util", "options", "data")
+
+    def __enter__(self):
+        self.saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in self.NAMES}
+        for k in self.saved:
+            del sys.modules[k]
+        sys.path.insert(0, REF)
+        return self
+
+    def __exit__(self, *a):
+        sys.path.remove(REF)
+        self.ref_modules = {k: v for k, v in sys.modules.items() if k.split(".")[0] in self.NAMES}
+        for k in self.ref_modules:
+            del sys.modules[k]
+        sys.modules.update(self.saved)
+
+
+def load_reference_nets():
+    """Returns (Generator, Discriminator, network_utils module, ImagePool, L1_plus_perceptualLoss)."""
+    with _RefImport():
+        gen = importlib.import_module("models.Generator")
+        dis = importlib.import_module("models.Discriminator")
+        nu = importlib.import_module("models.network_utils")
+        pool = importlib.import_module("util.image_pool")
+        l1p = importlib.import_module("losses.L1_plus_perceptualLoss")
+    return gen.Generator, dis.Discriminator, nu, pool.ImagePool, l1p.L1_plus_perceptualLoss
+
+
+def load_reference_model_class():
+    """models.MMHandModel.MMHandModel of the reference, importable on CPU."""
+    import torch
+    import torchvision
+
+    amp = _stub("apex.amp")
+    par = _stub("apex.parallel", DistributedDataParallel=object, convert_syncbn_model=lambda m: m)
+    _stub("apex", amp=amp, parallel=par)
+    _stub("skimage.draw", circle=None, line_aa=None, polygon=None)
+    _stub("skimage", draw=sys.modules["skimage.draw"])
+    _orig_vgg = torchvision.models.vgg19
+
+    def vgg19(pretrained=False, **kw):
+        return _orig_vgg(weights=None)
+
+    torchvision.models.vgg19 = vgg19
+    with _RefImport():
+        mm = importlib.import_module("models.MMHandModel")
+    if not torch.cuda.is_available():
+        class _Cuda:
+            @staticmethod
+            def is_available():
+                return True
+        mm.torch = types.SimpleNamespace(**{k: getattr(torch, k) for k in dir(torch) if not k.startswith("__")})
+        mm.torch.cuda = _Cuda
+        torch.nn.Module.cuda = lambda self, *a, **k: self
+        torch.nn.DataParallel = lambda m, device_ids=None: m
+    return mm.MMHandModel
+
+
+def make_opt(**over):
+    """Hand-built option namespace (the reference's BaseOptions.parse crashes without --distributed, Q8)."""
+    o = dict(batchSize=1, fineSize=256, H_input_nc=3, P_input_nc=21, D_input_nc=3, output_nc=3, ngf=64, ndf=64,
+             n_layers_D=3, norm='batch', no_dropout=False, no_dropout_D=False, init_type='normal',
+             G_n_downsampling=2, D_n_downsampling=2, padding_type='reflect', no_lsgan=True, lambda_A=10.0,
+             lambda_B=10.0, lambda_GAN=5.0, L1_type='l1_plus_perL1', perceptual_layers=3, percep_is_l1=1,
+             pool_size=50, DG_ratio=1, lr=2e-4, beta1=0.5, lr_policy='lambda', lr_decay_iters=50, niter=100,
+             niter_decay=0, epoch_count=1, continue_train=False, which_epoch='latest', isTrain=True,
+             local_rank='cpu', gpu='cpu', distributed=False, opt_level='O0', seed=49, gpu_ids=[],
+             checkpoints_dir='./checkpoints', name='oracle')
+    o.update(over)
+    return types.SimpleNamespace(**o)

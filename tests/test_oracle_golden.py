@@ -1,0 +1,77 @@
+"""The oracle (oracle/patn_ref.py) against golden vectors produced by the real reference modules
+(oracle/make_golden.py): networks, losses and four full optimisation steps."""
+import os
+import random
+
+import pytest
+import torch
+
+from oracle import patn_ref as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def nets():
+    return torch.load(os.path.join(GOLD, "nets_ngf4.pt"))
+
+
+def test_generator_eval(nets):
+    y = O.generator_forward(nets["g_sd"], nets["x"], train=False, use_dropout=True)
+    assert torch.allclose(y, nets["g_eval"], atol=1e-6)
+    assert y.shape == (2, 3, 32, 32)
+
+
+def test_generator_train_batchnorm(nets):
+    sd = {k: v.clone() for k, v in nets["g2_sd"].items()}
+    y = O.generator_forward(sd, nets["x"], train=True, use_dropout=False)
+    assert torch.allclose(y, nets["g2_train"], atol=1e-5)
+    for k, v in nets["g2_sd_after"].items():
+        assert torch.allclose(sd[k], v, atol=1e-6), k
+
+
+def test_discriminator(nets):
+    y = O.discriminator_forward(nets["d_sd"], nets["xd"], train=False, use_dropout=True)
+    assert torch.allclose(y, nets["d_eval"], atol=1e-5)
+    sd = {k: v.clone() for k, v in nets["d2_sd"].items()}
+    y2 = O.discriminator_forward(sd, nets["xd"], train=True, use_dropout=False)
+    assert torch.allclose(y2, nets["d2_train"], atol=1e-5)
+    assert y2.shape == (2, 16, 8, 8)     # no 1-channel head: logits are the last block's features (Q4)
+
+
+def test_gan_loss(nets):
+    assert abs(O.gan_loss(nets["d2_train"], True).item() - nets["gan_real"].item()) < 1e-6
+    assert abs(O.gan_loss(nets["d2_train"], False).item() - nets["gan_fake"].item()) < 1e-6
+    # known answer: BCE-with-logits of 0 against any label is ln 2
+    assert abs(O.gan_loss(torch.zeros(2, 3, 4, 4), True).item() - 0.6931471805599453) < 1e-7
+
+
+def test_swap_quirk(nets):
+    """Q1: perturbing only the pose input must reach block 1 through conv_block_stream3, not stream2."""
+    sd = nets["g_sd"]
+    x = [t.clone() for t in nets["x"]]
+    t0, t1 = {}, {}
+    O.generator_forward(sd, x, train=False, taps=t0)
+    x[1] = x[1] + 0.5
+    O.generator_forward(sd, x, train=False, taps=t1)
+    # the image-stream stem output is untouched, the block outputs are not
+    assert torch.equal(t0["down"][0], t1["down"][0])
+    assert not torch.equal(t0["att0"], t1["att0"])
+
+
+def test_four_training_steps():
+    g = torch.load(os.path.join(GOLD, "step_ngf4.pt"))
+    o = g["opt"]
+    random.seed(49)
+    tr = O.OracleTrainer(g["sd_g"], g["sd_dpb"], g["sd_dpp"], g["sd_vgg"], o["lambda_A"], o["lambda_B"],
+                         o["lambda_GAN"], o["lr"], o["beta1"], o["pool_size"], use_dropout_g=False,
+                         use_dropout_d=False)
+    for b, want, fake in zip(g["batches"], g["errors"], g["fake"]):
+        got = tr.step(b["H1"], b["P1"], b["D1"], b["H2"], b["P2"], b["D2"])
+        assert torch.allclose(tr.fake, fake, atol=2e-5)
+        for k in want:
+            assert abs(got[k] - want[k]) <= 2e-5 * max(1.0, abs(want[k])), (k, got[k], want[k])
+    for k, s in g["final_g_sum"].items():
+        assert abs(float(tr.g[k].double().abs().sum()) - s) <= 1e-4 * max(1.0, s), k
+    for k, s in g["final_dpb_sum"].items():
+        assert abs(float(tr.dpb[k].double().abs().sum()) - s) <= 1e-4 * max(1.0, s), k
