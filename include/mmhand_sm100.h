@@ -99,13 +99,175 @@ typedef struct MmhWgradDesc {
   int32_t dw_taps;                 /* size of dw's tap dimension */
   int32_t N_store, C_store;
   int32_t split_k; /* 0: choose */
-  int32_t dbg_lbo_sbo_swap; /* bring-up only: swap LBO/SBO roles of the MN-major descriptors */
 } MmhWgradDesc;
 
 typedef struct MmhWgradPlan MmhWgradPlan;
 int mmh_wgrad_plan_create(const MmhWgradDesc* desc, MmhWgradPlan** plan);
 int mmh_wgrad_plan_destroy(MmhWgradPlan* plan);
 int mmh_wgrad_run(const MmhWgradPlan* plan, void* stream);
+
+/* ---- pixel-grid layout descriptor used by every bandwidth-bound kernel ------------------------- */
+/*
+ * Logical pixel (b, h, w) of the H x W content lives at grid position (h + h0, w + w0) of image b;
+ * phase != 0 splits the grid into four parity planes of Hg x Wg each (plane = (row&1)*2 + (col&1)).
+ * ld = elements per row, c0 = first channel of this view, C = channels of this view (multiple of 8).
+ */
+typedef struct MmhLay {
+  int32_t B, H, W, Hg, Wg, h0, w0, phase, ld, c0, C, reserved;
+} MmhLay;
+
+/*
+ * Input assembly: replaces torch.cat + ReflectionPad2d(3) + the implicit NCHW->NHWC/bf16 conversion
+ * (models/MMHandModel.py:216-220,238-243,278-289; models/Generator.py:158-189) and the VGG re-normalisation
+ * (losses/L1_plus_perceptualLoss.py:40-58, scale/shift per channel, zero halo).
+ * dst[b,h,w,c] for h in [-pad_lo, H+pad_hi): channels [0,C0) from src0, [C0,C0+C1) from src1 (NCHW fp32),
+ * the rest zero.
+ */
+int mmh_assemble_nchw(const float* src0, int32_t C0, const float* src1, int32_t C1, const float* scale,
+                      const float* shift, void* dst, const MmhLay* dl, int32_t pad_lo, int32_t pad_hi,
+                      int32_t reflect, void* stream);
+
+/* BatchNorm2d statistics (cudnnBatchNorm in the reference; models/Generator.py:67,73,110 etc.).
+ * x: bf16 [rows][ld] whose invalid grid positions are zero; sums[0][c] += sum x, sums[1][c] += sum x^2. */
+int mmh_bn_stats(const void* x, int64_t rows, int32_t ld, int32_t C, float* sums, void* stream);
+/* train: mean/var from sums and count, running stats updated (momentum, unbiased var); eval: running stats.
+ * coef = (gamma*rstd, beta - mean*gamma*rstd), save = (mean, rstd). gamma/beta NULL -> 1/0. */
+int mmh_bn_finalize(const float* sums, float count, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, float momentum, float eps, int32_t train, int32_t C, float* coef,
+                    float* save, void* stream);
+
+/* Fused BN-apply + ReLU + Dropout(0.5) + residual + next layer's padding
+ * (models/Generator.py:62-77 sequence; models/Discriminator.py:53-55 residual). */
+typedef struct MmhNormAct {
+  const void* src;
+  MmhLay sl;
+  const float* coef; /* [2][C] or NULL (identity) */
+  int32_t relu, dropout;
+  uint32_t drop_key;
+  int32_t reserved;
+  const float* resid; /* fp32 plain [B*H*W][C] or NULL */
+  void* dst;          /* bf16, may be NULL */
+  MmhLay dl;
+  int32_t pad_lo, pad_hi, reflect, reserved2;
+  float* dst_f32; /* fp32 plain [B*H*W][C] or NULL */
+} MmhNormAct;
+int mmh_norm_act(const MmhNormAct* p, void* stream);
+
+/* PATBlock tail (models/Generator.py:120-130): out = x1 + BN(c1)*sigmoid(x2o)*sigmoid(x3o); writes the three
+ * next-block inputs x1' = out, x2' = [x3o | out], x3' = [x2o | out] (the reference's swapped unpacking). */
+typedef struct MmhGateFwd {
+  const void* c1;
+  const void* x2o;
+  const void* x3o;
+  MmhLay sl;
+  const float* coef;
+  const float* trunk_in;
+  float* trunk_out;
+  void* d1;
+  MmhLay d1l;
+  void* d2; /* may be NULL */
+  MmhLay d2l;
+  void* d3; /* may be NULL */
+  MmhLay d3l;
+  int32_t pad_lo, pad_hi, reflect, reserved;
+} MmhGateFwd;
+int mmh_gate_fwd(const MmhGateFwd* p, void* stream);
+
+/* Gradient sources: the data gradient of a consumer convolution, laid out like that convolution's input
+ * (with halo); folding the halo back is the backward of ReflectionPad2d / zero padding. */
+typedef struct MmhGradSrc {
+  const void* p; /* bf16 */
+  MmhLay l;
+  int32_t pad_lo, pad_hi, reflect, reserved;
+} MmhGradSrc;
+
+typedef struct MmhGradGather {
+  int32_t nsrc, dst_f32, B, H;
+  int32_t W, C, reserved0, reserved1;
+  MmhGradSrc src[4];
+  const float* trunk; /* fp32 plain or NULL */
+  const void* mask;   /* bf16, multiply by (mask > 0) or NULL */
+  MmhLay ml;
+  void* dst;
+  MmhLay dl;
+} MmhGradGather;
+int mmh_grad_gather(const MmhGradGather* p, void* stream);
+
+/* BatchNorm backward (+ ReLU / dropout masks recomputed from the saved raw output). */
+typedef struct MmhBnBwd {
+  const void* dz; /* plain [B*H*W][C] */
+  int32_t dz_f32, relu, dropout;
+  uint32_t drop_key;
+  const void* x;
+  MmhLay xl;
+  const float* coef;
+  const float* save;
+  float* sums;    /* reduce: [2][C] += (sum dz, sum dz*xhat) */
+  const float* k; /* apply: [2][C] (mean dz, mean dz*xhat) */
+  void* dy;       /* apply: bf16 on layout yl (interior only) */
+  MmhLay yl;
+} MmhBnBwd;
+int mmh_bn_bwd_reduce(const MmhBnBwd* p, void* stream);
+int mmh_bn_bwd_apply(const MmhBnBwd* p, void* stream);
+/* k = sums_global / count; dgamma += sums_local[1], dbeta += sums_local[0] (NULL to skip). */
+int mmh_bn_bwd_finalize(const float* sums_global, const float* sums_local, float count, float* k, float* dgamma,
+                        float* dbeta, int32_t C, void* stream);
+
+typedef struct MmhGateBwd {
+  const float* dout; /* fp32 plain [B*H*W][C] */
+  const void* c1;
+  const void* x2o;
+  const void* x3o;
+  MmhLay sl;
+  const float* coef;
+  const float* save;
+  float* sums;
+  const float* k;
+  MmhGradSrc ex2, ex3; /* p == NULL: none */
+  void* dy1;
+  void* dy2;
+  void* dy3;
+  MmhLay yl;
+} MmhGateBwd;
+int mmh_gate_bwd_reduce(const MmhGateBwd* p, void* stream);
+int mmh_gate_bwd_apply(const MmhGateBwd* p, void* stream);
+
+/* ---- losses ------------------------------------------------------------------------------------ */
+/* BCEWithLogitsLoss against a constant label (models/network_utils.py:141,160-163):
+ * *loss_acc += loss_scale * sum bce(x, target); grad[i] = grad_scale * (sigmoid(x) - target) (grad may be NULL) */
+int mmh_bce_logits(const float* x, int64_t n, float target, float loss_scale, float grad_scale, float* loss_acc,
+                   float* grad, void* stream);
+/* F.l1_loss on images (losses/L1_plus_perceptualLoss.py:37): grad_acc[i] += grad_scale*sign(a-b) (may be NULL) */
+int mmh_l1_f32(const float* a, const float* b, int64_t n, float loss_scale, float grad_scale, float* loss_acc,
+               float* grad_acc, void* stream);
+/* perceptual L1/MSE between two post-ReLU feature grids + gradient through the ReLU (:63-71) */
+int mmh_perc_loss(const void* ff, const void* ft, int64_t n, int32_t mse, float loss_scale, float grad_scale,
+                  float* loss_acc, void* dy, void* stream);
+/* tanh backward into the last conv's dY grid (models/Generator.py:259): dy = dfake * (1 - fake^2) */
+int mmh_tanh_bwd(const float* dfake_nchw, const float* fake_nchw, void* dy, const MmhLay* yl, int32_t C, void* stream);
+/* gradient w.r.t. an NCHW fp32 network input: fold the halo, take channels [0,C), optional per-channel scale */
+int mmh_input_grad_nchw(const MmhGradSrc* src, const float* scale, float* dst_nchw, int32_t B, int32_t C, int32_t H,
+                        int32_t W, int32_t accumulate, void* stream);
+/* fp32 grid rows -> NCHW fp32 (the generator's output image) */
+int mmh_grid_to_nchw(const float* src, const MmhLay* sl, float* dst_nchw, int32_t C, void* stream);
+
+/* ---- parameters --------------------------------------------------------------------------------- */
+/* fp32 master weight (any strides: n, c, tap) -> bf16 [T][Np][Cp] zero padded */
+int mmh_pack_weight(const float* src, int64_t s_n, int64_t s_c, int64_t s_t, int32_t N, int32_t C, int32_t T,
+                    void* dst, int32_t Np, int32_t Cp, void* stream);
+/* fp32 [T][N][C] packed gradient -> strided fp32 gradient (accumulate != 0: +=) */
+int mmh_unpack_wgrad(const float* src, float* dst, int64_t s_n, int64_t s_c, int64_t s_t, int32_t N, int32_t C,
+                     int32_t T, int32_t accumulate, void* stream);
+/* torch.optim.Adam step (models/MMHandModel.py:90-98) on a flat fp32 buffer; g is multiplied by grad_scale */
+int mmh_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+             int32_t step, float grad_scale, void* stream);
+int mmh_memset(void* p, int32_t byte, int64_t bytes, void* stream);
+
+/* ---- keypoints -> heatmaps (data/generic_dataset.py:191-217,238-242) ----------------------------- */
+/* uv: float64 [n_maps][2] (x, y); out: fp32 [n_maps][H][W] = exp(-((gx-x)^2+(gy-y)^2)/2/sigma/sigma),
+ * >1 -> 1, < thresh -> 0, all in fp64, cast last. */
+int mmh_heatmap_rasterize(const double* uv, int64_t n_maps, int32_t H, int32_t W, double sigma, double thresh,
+                          float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,95 @@
+"""Drop-in for the reference's ``losses/L1_plus_perceptualLoss.py`` (:11-75):
+``lambda_L1 * L1(inputs, targets) + lambda_perceptual * L1|MSE(VGG19[:perceptual_layers+1](n(inputs)), ...(n(targets)))``
+with n(x) = ((x + 1) / 2 - mean) / std, returning ``(loss, loss_l1, loss_perceptual)``.
+
+The VGG slice runs on the tcgen05 conv kernels (bias + ReLU in the epilogue), the two reductions and their
+gradients on the fused loss kernels. Only ``perceptual_layers == 3`` (conv1_1, ReLU, conv1_2, ReLU -- the value every
+shipped script uses) is built. ``torchvision``'s pretrained file cannot be downloaded here; weights are taken from
+``MMH_VGG19_WEIGHTS`` (a torchvision ``vgg19`` state_dict) when set, else from torchvision's cache, else they stay
+at their seeded random initialisation (parity tests give both sides the same tensors).
+"""
+import os
+import warnings
+
+import torch
+import torch.nn as nn
+
+from mmhand_b200 import runtime
+from mmhand_b200.engine import VggEngine
+
+
+def _vgg_slice(perceptual_layers):
+    if perceptual_layers != 3:
+        raise NotImplementedError("perceptual_layers=%r: only the shipped value 3 (VGG19.features[0:4]) is built"
+                                  % (perceptual_layers,))
+    seq = nn.Sequential()
+    seq.add_module("0", nn.Conv2d(3, 64, 3, padding=1))
+    seq.add_module("1", nn.ReLU(inplace=True))
+    seq.add_module("2", nn.Conv2d(64, 64, 3, padding=1))
+    seq.add_module("3", nn.ReLU(inplace=True))
+    path = os.environ.get("MMH_VGG19_WEIGHTS", "")
+    sd = None
+    if path and os.path.exists(path):
+        sd = torch.load(path, map_location="cpu")
+    else:
+        cache = os.path.expanduser("~/.cache/torch/hub/checkpoints/vgg19-dcbb9e9d.pth")
+        if os.path.exists(cache):
+            sd = torch.load(cache, map_location="cpu")
+    if sd is not None:
+        seq.load_state_dict({k[len("features."):]: v for k, v in sd.items()
+                             if k in ("features.0.weight", "features.0.bias", "features.2.weight", "features.2.bias")})
+    else:
+        warnings.warn("VGG19 weights not found (set MMH_VGG19_WEIGHTS): the perceptual loss uses random-init features")
+    return seq
+
+
+class _LossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, inputs, targets):
+        x = inputs.contiguous().float()
+        t = targets.contiguous().float()
+        ops = runtime.get_ops(x.device)
+        B, _, H, W = x.shape
+        acc = torch.zeros(2, dtype=torch.float32, device=x.device)
+        need = inputs.requires_grad
+        g = torch.zeros_like(x) if need else None
+        n = x.numel()
+        ops.l1(x, t, mod.lambda_L1 / n, mod.lambda_L1 / n, acc[0:1], g)
+        mod.vgg_engine(B, H, W).loss_and_backward(x, t, mod.lambda_perceptual, mod.percep_is_l1 != 1, acc[1:2], g)
+        ctx.g = g
+        ctx.mark_non_differentiable = None
+        return acc[0] + acc[1], acc[0].clone(), acc[1].clone()
+
+    @staticmethod
+    def backward(ctx, g_loss, g_l1, g_p):
+        if ctx.g is None:
+            return None, None, None
+        return None, ctx.g * g_loss, None
+
+
+class L1_plus_perceptualLoss(nn.Module):
+    def __init__(self, lambda_L1, lambda_perceptual, perceptual_layers, gpu_ids, percep_is_l1):
+        super().__init__()
+        self.lambda_L1 = lambda_L1
+        self.lambda_perceptual = lambda_perceptual
+        self.gpu_ids = gpu_ids
+        self.percep_is_l1 = percep_is_l1
+        self.vgg_submodel = _vgg_slice(perceptual_layers)
+        for p in self.vgg_submodel.parameters():
+            p.requires_grad_(False)       # never optimised by the reference either
+        self._eng = {}
+
+    def vgg_engine(self, B, H, W):
+        ops = runtime.get_ops(self.vgg_submodel[0].weight.device)
+        key = (B, H, W, str(ops.device))
+        if key not in self._eng:
+            self._eng.clear()
+            v = self.vgg_submodel
+            self._eng[key] = VggEngine(ops, v[0].weight, v[0].bias, v[2].weight, v[2].bias, B, H, W)
+        return self._eng[key]
+
+    def forward(self, inputs, targets):
+        if self.lambda_L1 == 0 and self.lambda_perceptual == 0:
+            z = torch.zeros(1, device=inputs.device)
+            return z, torch.zeros(1), torch.zeros(1)
+        return _LossFn.apply(self, inputs, targets)

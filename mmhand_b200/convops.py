@@ -68,7 +68,7 @@ def conv_desc(a, a_rows, a_ld, Cc, w, w_taps, N, taps, M, Hg, Wg, Hv, Wv, out, o
         d.shift[i] = sh
     d.M = M
     d.Hg, d.Wg, d.Hv, d.Wv = Hg, Wg, Hv, Wv
-    esz = 4 if out_f32 else 2
+    esz = out.element_size()
     d.out = out.data_ptr() + out_row_off * out_ld * esz
     d.out_f32 = 1 if out_f32 else 0
     d.out_ld = out_ld
@@ -115,7 +115,7 @@ def dgrad_plans(lib, g: ConvGeom, dy_buf, wd_packed, dx_buf, Cin_p, Cout_p, dx_l
     return plans
 
 
-def wgrad_plans(lib, g: ConvGeom, a_buf, dy_buf, dw_buf, Cin_p, Cout_p, Cin, Cout, split_k=0, dbg_swap=0):
+def wgrad_plans(lib, g: ConvGeom, a_buf, dy_buf, dw_buf, Cin_p, Cout_p, Cin, Cout, split_k=0):
     """dw_buf: fp32 [k*k][Cout][Cin] (packed-gradient layout, caller zeroes)."""
     plans = []
     il, ol = g.in_lay, g.out_lay
@@ -127,7 +127,7 @@ def wgrad_plans(lib, g: ConvGeom, a_buf, dy_buf, dw_buf, Cin_p, Cout_p, Cin, Cou
         d.a_ld = il.ld
         d.C = Cin_p
         off = ln.out_plane * ol.plane_rows if g.kind == 'up' else 0
-        d.dy = dy_buf.data_ptr() + off * ol.ld * 2
+        d.dy = dy_buf.data_ptr() + off * ol.ld * dy_buf.element_size()
         d.M = M
         d.dy_ld = ol.ld
         d.N = Cout_p
@@ -140,6 +140,5 @@ def wgrad_plans(lib, g: ConvGeom, a_buf, dy_buf, dw_buf, Cin_p, Cout_p, Cin, Cou
         d.N_store = Cout
         d.C_store = Cin
         d.split_k = split_k
-        d.dbg_lbo_sbo_swap = dbg_swap
         plans.append(WgradPlan(lib, d))
     return plans

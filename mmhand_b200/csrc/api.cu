@@ -74,7 +74,9 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, int64_t cols, int64_t 
 
 }  // namespace mmh
 
+#include "ew_common.h"
 extern "C" int mmh_version(void) { return 100; }
+extern "C" int mmh_act_bytes(void) { return static_cast<int>(sizeof(mmh::act_t)); }
 extern "C" const char* mmh_last_error(void) { return mmh::get_error(); }
 #ifdef MMH_HOST_EMU
 extern "C" int mmh_is_device_build(void) { return 0; }

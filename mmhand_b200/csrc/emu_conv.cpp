@@ -13,6 +13,7 @@
 #include "ew_common.h"
 #include "host_common.h"
 
+using mmh::act_t;
 struct MmhConvPlan { MmhConvDesc d; };
 struct MmhWgradPlan { MmhWgradDesc d; };
 
@@ -31,8 +32,8 @@ extern "C" int mmh_conv_plan_destroy(MmhConvPlan* p) { delete p; return 0; }
 
 extern "C" int mmh_conv_run(const MmhConvPlan* plan, void*) {
   const MmhConvDesc& d = plan->d;
-  const uint16_t* a = static_cast<const uint16_t*>(d.a);
-  const uint16_t* w = static_cast<const uint16_t*>(d.w);
+  const act_t* a = static_cast<const act_t*>(d.a);
+  const act_t* w = static_cast<const act_t*>(d.w);
   const int w_taps = d.w_taps > 0 ? d.w_taps : d.T;
   (void)w_taps;
   const int64_t hw = static_cast<int64_t>(d.Hg) * d.Wg;
@@ -49,14 +50,14 @@ extern "C" int mmh_conv_run(const MmhConvPlan* plan, void*) {
       for (int t = 0; t < d.T; ++t) {
         const int64_t r = q + d.shift[t];
         if (r < 0 || r >= d.a_rows) continue;
-        const uint16_t* ar = a + r * d.a_ld;
-        for (int c = 0; c < d.C; ++c) arow[c] = mmh::bf2f(ar[c]);
+        const act_t* ar = a + r * d.a_ld;
+        for (int c = 0; c < d.C; ++c) arow[c] = mmh::act2f(ar[c]);
         const int slot = d.w_taps > 0 ? d.w_slot[t] : t;
-        const uint16_t* wt = w + static_cast<int64_t>(slot) * d.N * d.C;
+        const act_t* wt = w + static_cast<int64_t>(slot) * d.N * d.C;
         for (int n = 0; n < d.N; ++n) {
-          const uint16_t* wr = wt + static_cast<int64_t>(n) * d.C;
+          const act_t* wr = wt + static_cast<int64_t>(n) * d.C;
           float s = 0.f;
-          for (int c = 0; c < d.C; ++c) s += arow[c] * mmh::bf2f(wr[c]);
+          for (int c = 0; c < d.C; ++c) s += arow[c] * mmh::act2f(wr[c]);
           acc[n] += s;
         }
       }
@@ -74,8 +75,8 @@ extern "C" int mmh_conv_run(const MmhConvPlan* plan, void*) {
       float* o = static_cast<float*>(d.out) + orow * d.out_ld;
       for (int n = 0; n < n_store && n < d.N; ++n) o[n] = acc[n];
     } else {
-      uint16_t* o = static_cast<uint16_t*>(d.out) + orow * d.out_ld;
-      for (int n = 0; n < n_store && n < d.N; ++n) o[n] = mmh::f2bf(acc[n]);
+      act_t* o = static_cast<act_t*>(d.out) + orow * d.out_ld;
+      for (int n = 0; n < n_store && n < d.N; ++n) o[n] = mmh::f2act(acc[n]);
     }
   }
   return 0;
@@ -93,8 +94,8 @@ extern "C" int mmh_wgrad_plan_destroy(MmhWgradPlan* p) { delete p; return 0; }
 
 extern "C" int mmh_wgrad_run(const MmhWgradPlan* plan, void*) {
   const MmhWgradDesc& d = plan->d;
-  const uint16_t* a = static_cast<const uint16_t*>(d.a);
-  const uint16_t* dy = static_cast<const uint16_t*>(d.dy);
+  const act_t* a = static_cast<const act_t*>(d.a);
+  const act_t* dy = static_cast<const act_t*>(d.dy);
   const int Ns = d.N_store > 0 ? d.N_store : d.N;
   const int Cs = d.C_store > 0 ? d.C_store : d.C;
   std::vector<float> dyr(Ns), ar(Cs);
@@ -104,9 +105,9 @@ extern "C" int mmh_wgrad_run(const MmhWgradPlan* plan, void*) {
       const int64_t r = q + d.shift[t];
       if (r < 0 || r >= d.a_rows) continue;
       bool any = false;
-      for (int n = 0; n < Ns; ++n) { dyr[n] = mmh::bf2f(dy[q * d.dy_ld + n]); any |= dyr[n] != 0.f; }
+      for (int n = 0; n < Ns; ++n) { dyr[n] = mmh::act2f(dy[q * d.dy_ld + n]); any |= dyr[n] != 0.f; }
       if (!any) continue;
-      for (int c = 0; c < Cs; ++c) ar[c] = mmh::bf2f(a[r * d.a_ld + c]);
+      for (int c = 0; c < Cs; ++c) ar[c] = mmh::act2f(a[r * d.a_ld + c]);
       for (int n = 0; n < Ns; ++n) {
         const float g = dyr[n];
         if (g == 0.f) continue;

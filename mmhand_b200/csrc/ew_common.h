@@ -37,4 +37,16 @@ MMH_HD uint16_t f2bf(float f) {
   return static_cast<uint16_t>(u >> 16);
 }
 
+// Storage type of activations: bf16 bit patterns in the product. -DMMH_EMU_F32 (host emulation only) widens it
+// to fp32 so that CPU tests can check the kernels' index arithmetic and calculus to fp32 accuracy.
+#ifdef MMH_EMU_F32
+typedef float act_t;
+MMH_HD float act2f(act_t v) { return v; }
+MMH_HD act_t f2act(float f) { return f; }
+#else
+typedef uint16_t act_t;
+MMH_HD float act2f(act_t v) { return bf2f(v); }
+MMH_HD act_t f2act(float f) { return f2bf(f); }
+#endif
+
 }  // namespace mmh

@@ -1,0 +1,90 @@
+// Parameter-side kernels: fused Adam over a flat fp32 buffer, weight packing (fp32 OIHW master ->
+// bf16 [tap][N][C] tensor-core operand) and packed-gradient unpacking. Dual-mode source.
+#include <math.h>
+#include <string.h>
+
+#include "ew_framework.h"
+
+namespace mmh {
+
+struct AdamF {
+  float* p; const float* g; float* m; float* v;
+  float lr_t, b1, b2, eps, inv_sqrt_bc2, gscale;   // lr_t = lr / (1 - b1^t)
+  MMH_HD void operator()(int64_t i) const {
+    const float gr = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gr;
+    const float vi = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  }
+};
+
+struct PackF {
+  const float* src; act_t* dst; int64_t s_n, s_c, s_t; int N, C, Np, Cp;
+  MMH_HD void operator()(int64_t i) const {
+    const int c = static_cast<int>(i % Cp);
+    const int n = static_cast<int>((i / Cp) % Np);
+    const int t = static_cast<int>(i / (static_cast<int64_t>(Cp) * Np));
+    float v = 0.f;
+    if (n < N && c < C) v = src[n * s_n + c * s_c + t * s_t];
+    dst[i] = f2act(v);
+  }
+};
+
+struct UnpackF {
+  const float* src; float* dst; int64_t s_n, s_c, s_t; int N, C, accumulate;
+  MMH_HD void operator()(int64_t i) const {
+    const int c = static_cast<int>(i % C);
+    const int n = static_cast<int>((i / C) % N);
+    const int t = static_cast<int>(i / (static_cast<int64_t>(C) * N));
+    const int64_t o = n * s_n + c * s_c + t * s_t;
+    dst[o] = accumulate ? dst[o] + src[i] : src[i];
+  }
+};
+
+}  // namespace mmh
+
+using namespace mmh;
+
+extern "C" int mmh_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                        float eps, int32_t step, float grad_scale, void* stream) {
+  MMH_CHECK(p && g && m && v && step >= 1, "bad argument");
+  AdamF f;
+  f.p = p; f.g = g; f.m = m; f.v = v;
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  f.lr_t = static_cast<float>(lr / bc1);
+  f.b1 = beta1; f.b2 = beta2; f.eps = eps;
+  f.inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(bc2));
+  f.gscale = grad_scale;
+  return launch_map(f, n, stream);
+}
+
+extern "C" int mmh_pack_weight(const float* src, int64_t s_n, int64_t s_c, int64_t s_t, int32_t N, int32_t C,
+                               int32_t T, void* dst, int32_t Np, int32_t Cp, void* stream) {
+  MMH_CHECK(src && dst && N <= Np && C <= Cp, "bad argument");
+  PackF f;
+  f.src = src; f.dst = static_cast<act_t*>(dst); f.s_n = s_n; f.s_c = s_c; f.s_t = s_t;
+  f.N = N; f.C = C; f.Np = Np; f.Cp = Cp;
+  return launch_map(f, static_cast<int64_t>(T) * Np * Cp, stream);
+}
+
+extern "C" int mmh_unpack_wgrad(const float* src, float* dst, int64_t s_n, int64_t s_c, int64_t s_t, int32_t N,
+                                int32_t C, int32_t T, int32_t accumulate, void* stream) {
+  MMH_CHECK(src && dst, "null argument");
+  UnpackF f;
+  f.src = src; f.dst = dst; f.s_n = s_n; f.s_c = s_c; f.s_t = s_t; f.N = N; f.C = C; f.accumulate = accumulate;
+  return launch_map(f, static_cast<int64_t>(T) * N * C, stream);
+}
+
+extern "C" int mmh_memset(void* p, int32_t byte, int64_t bytes, void* stream) {
+  MMH_CHECK(p || bytes == 0, "null argument");
+#ifdef MMH_HOST_EMU
+  (void)stream;
+  memset(p, byte, static_cast<size_t>(bytes));
+#else
+  MMH_CUDA(cudaMemsetAsync(p, byte, static_cast<size_t>(bytes), static_cast<cudaStream_t>(stream)));
+#endif
+  return 0;
+}

@@ -207,10 +207,6 @@ extern "C" int mmh_wgrad_plan_create(const MmhWgradDesc* d, MmhWgradPlan** out_p
   k.lbo_n = k.sub_n_bytes; k.sbo_n = 8 * k.cw_n * 2;
   k.lbo_c = k.sub_c_bytes; k.sbo_c = 8 * k.cw_c * 2;
   k.raw_sbo_n = k.sbo_n; k.raw_sbo_c = k.sbo_c;
-  if (d->dbg_lbo_sbo_swap) {
-    uint32_t x = k.lbo_n; k.lbo_n = k.sbo_n; k.sbo_n = x;
-    x = k.lbo_c; k.lbo_c = k.sbo_c; k.sbo_c = x;
-  }
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(k.BNc)) cols <<= 1;
   k.tmem_cols = cols;

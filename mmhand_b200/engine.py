@@ -1,0 +1,625 @@
+"""Execution engines of the three networks on the C-ABI kernels.
+
+An engine owns every activation / gradient buffer of one network for one (batch, frame size), the packed
+bf16 tensor-core operands of its weights and the conv plans bound to those buffers; ``forward`` and
+``backward`` are plain sequences of kernel launches on the current stream (no autograd, no allocation,
+no host synchronisation). Layer structure and arithmetic follow the reference modules:
+
+  GeneratorEngine      models/Generator.py:133-283 (PATNModel) incl. PATBlock :8-130
+  DiscriminatorEngine  models/Discriminator.py:58-154
+  VggEngine            losses/L1_plus_perceptualLoss.py:22-27,54-61 (VGG19.features[0:4])
+"""
+import torch
+
+from . import convops
+from .kernels import GradSource, Ops
+from .layouts import Lay, chan_pad, geom_s1, geom_s2, geom_up
+
+BN_EPS = 1e-5
+BN_MOM = 0.1
+M32 = 0xFFFFFFFF
+
+
+def dropout_key(seed, layer_id, step):
+    """Same key schedule as oracle/patn_ref.py::dropout_key."""
+    return (seed * 0x9E3779B1 + layer_id * 0x85EBCA77 + step * 0xC2B2AE3D + 0x27D4EB2F) & M32
+
+
+def plain_lay(B, H, W, Cc):
+    return Lay(B, H, W, H, W, 0, 0, False, Cc, 0, Cc)
+
+
+class ParamStore:
+    """Flat fp32 storage (values, grads, Adam moments) behind the nn.Parameters of one module."""
+
+    def __init__(self, ops: Ops, module):
+        self.ops, self.module = ops, module
+        self.params = [p for p in module.parameters()]
+        self.flat = None
+        self.step = 0
+        self.m = self.v = None
+        self.ensure()
+
+    def ensure(self):
+        """(Re)flatten when the module was moved / re-created since the last call."""
+        ok = self.flat is not None
+        if ok:
+            off = 0
+            for p in self.params:
+                if p.data.data_ptr() != self.flat.data_ptr() + off * 4 or p.data.device != self.flat.device:
+                    ok = False
+                    break
+                off += p.numel()
+        if ok:
+            return False
+        total = sum(p.numel() for p in self.params)
+        flat = torch.zeros(total, dtype=torch.float32, device=self.ops.device)
+        grad = torch.zeros(total, dtype=torch.float32, device=self.ops.device)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            flat[off:off + n].copy_(p.data.reshape(-1).to(self.ops.device, torch.float32))
+            p.data = flat[off:off + n].view(p.shape)
+            p.grad = grad[off:off + n].view(p.shape)
+            off += n
+        self.flat, self.grad = flat, grad
+        return True
+
+    def zero_grad(self):
+        self.ops.memset0(self.grad)
+
+    def adam(self, lr, beta1, beta2=0.999, eps=1e-8, grad_scale=1.0):
+        if self.m is None:
+            self.m = torch.zeros_like(self.flat)
+            self.v = torch.zeros_like(self.flat)
+        self.step += 1
+        self.ops.adam(self.flat, self.grad, self.m, self.v, lr, beta1, beta2, eps, self.step, grad_scale)
+
+    def versions(self):
+        return tuple(p._version for p in self.params) + (self.step, self.flat.data_ptr())
+
+
+class ConvL:
+    """One convolution: geometry, buffers, packed weights, plans."""
+
+    def __init__(self, eng, name, geom, Cin, Cout, weight, transposed=False, bias=None, act=0, out_f32=False,
+                 need_dx=True, x_buf=None, raw_buf=None):
+        ops = eng.ops
+        self.eng, self.name, self.g = eng, name, geom
+        self.Cin, self.Cout = Cin, Cout
+        self.Cin_p, self.Cout_p = geom.in_lay.ld, geom.out_lay.ld
+        self.weight, self.transposed, self.bias, self.act, self.out_f32 = weight, transposed, bias, act, out_f32
+        self.need_dx = need_dx
+        self.T = geom.k * geom.k
+        self.x = x_buf if x_buf is not None else ops.zeros(geom.in_lay.rows, self.Cin_p)
+        self.raw = raw_buf if raw_buf is not None else ops.zeros(
+            geom.out_lay.rows, self.Cout_p, dtype=torch.float32 if out_f32 else None)
+        self.wp = ops.zeros(self.T, self.Cout_p, self.Cin_p)
+        self.bias_p = None
+        if bias is not None:
+            self.bias_p = ops.zeros(self.Cout_p, dtype=torch.float32)
+        self.fwd = convops.fwd_plans(ops.lib, geom, self.x, self.wp, self.raw, self.Cin_p, self.Cout_p,
+                                     bias=self.bias_p, act=act, out_f32=out_f32)
+        self.bwd_ready = False
+
+    # weight strides (n = out channel, c = in channel, t = tap) of the fp32 master tensor
+    def _strides(self):
+        w = self.weight
+        if self.transposed:            # [Cin][Cout][kh][kw]
+            return w.stride(1), w.stride(0), 1
+        return w.stride(0), w.stride(1), 1
+
+    def pack(self, with_dgrad):
+        ops = self.eng.ops
+        sn, sc, st = self._strides()
+        ops.pack_weight(self.weight, sn, sc, st, self.Cout, self.Cin, self.T, self.wp, self.Cout_p, self.Cin_p)
+        if with_dgrad and self.need_dx and self.bwd_ready:
+            ops.pack_weight(self.weight, sc, sn, st, self.Cin, self.Cout, self.T, self.wd, self.Cin_p, self.Cout_p)
+        if self.bias is not None:
+            self.bias_p[:self.Cout].copy_(self.bias.detach())
+
+    def prepare_backward(self, dy_key, dx_key, need_wgrad=True):
+        if self.bwd_ready:
+            return
+        ops, g = self.eng.ops, self.g
+        self.dy = self.eng.scratch(("dy", dy_key, g.out_lay.rows, self.Cout_p), g.out_lay.rows, self.Cout_p)
+        if self.need_dx:
+            self.dx = self.eng.scratch(("dx", dx_key, g.in_lay.rows, self.Cin_p), g.in_lay.rows, self.Cin_p)
+            self.wd = ops.zeros(self.T, self.Cin_p, self.Cout_p)
+            self.dgrad = convops.dgrad_plans(ops.lib, g, self.dy, self.wd, self.dx, self.Cin_p, self.Cout_p)
+        if need_wgrad:
+            self.dw = ops.zeros(self.T, self.Cout, self.Cin, dtype=torch.float32)
+            self.wgrad = convops.wgrad_plans(ops.lib, g, self.x, self.dy, self.dw, self.Cin_p, self.Cout_p,
+                                             self.Cin, self.Cout)
+            if self.bias is not None:
+                self.dbias = ops.zeros(2 * self.Cout_p, dtype=torch.float32)
+        self.has_wgrad = need_wgrad
+        self.bwd_ready = True
+
+    def run_fwd(self):
+        st = self.eng.ops._stream()
+        for p in self.fwd:
+            p.run(st)
+            self.eng.ops.launches += 1
+
+    def run_bwd(self, want_wgrad=True, want_dx=True):
+        """Consumes self.dy. Weight gradient accumulates into weight.grad; data gradient lands in self.dx."""
+        ops = self.eng.ops
+        st = ops._stream()
+        if want_wgrad and self.has_wgrad:
+            ops.memset0(self.dw)
+            for p in self.wgrad:
+                p.run(st)
+                ops.launches += 1
+            sn, sc, stt = self._strides()
+            ops.unpack_wgrad(self.dw, self.weight.grad, sn, sc, stt, self.Cout, self.Cin, self.T, True)
+            if self.bias is not None:
+                ops.memset0(self.dbias)
+                ops.bn_stats(self.dy, self.g.out_lay.rows, self.Cout_p, self.Cout_p, self.dbias)
+                self.bias.grad.add_(self.dbias[:self.Cout])
+        if want_dx and self.need_dx:
+            for p in self.dgrad:
+                p.run(st)
+                ops.launches += 1
+
+    def dx_source(self):
+        g = self.g
+        return GradSource(self.dx, g.in_lay, g.in_pad_lo, g.in_pad_hi, g.pad_mode == 'reflect')
+
+
+class BNL:
+    """BatchNorm2d over a raw conv output (train: batch statistics; eval: running statistics)."""
+
+    def __init__(self, eng, mod, Cc):
+        ops = eng.ops
+        self.eng, self.mod, self.C = eng, mod, Cc
+        f = lambda n: ops.zeros(n, dtype=torch.float32)
+        self.sums, self.coef, self.save, self.bsums, self.bsums_g, self.k = f(2 * Cc), f(2 * Cc), f(2 * Cc), f(2 * Cc), f(2 * Cc), f(2 * Cc)
+
+    def forward(self, raw, rows, ld, count, training):
+        ops, m = self.eng.ops, self.mod
+        if training:
+            ops.memset0(self.sums)
+            ops.bn_stats(raw, rows, ld, self.C, self.sums)
+            count = self.eng.sync_stats(self.sums, count)
+            ops.bn_finalize(self.sums, count, m.weight, m.bias, m.running_mean, m.running_var, BN_MOM, BN_EPS, True,
+                            self.C, self.coef, self.save)
+            m.note_batch()
+        else:
+            ops.bn_finalize(None, 1.0, m.weight, m.bias, m.running_mean, m.running_var, BN_MOM, BN_EPS, False, self.C,
+                            self.coef, self.save)
+
+    def backward(self, dz, dz_f32, relu, dropout, key, x, xl, dy, yl, count, want_wgrad=True):
+        ops, m = self.eng.ops, self.mod
+        ops.memset0(self.bsums)
+        ops.bn_bwd_reduce(dz, dz_f32, relu, dropout, key, x, xl, self.coef, self.save, self.bsums)
+        sg, count = self.eng.sync_bwd_stats(self.bsums, self.bsums_g, count)
+        ops.bn_bwd_finalize(sg, self.bsums, count, self.k, m.weight.grad if want_wgrad else None,
+                            m.bias.grad if want_wgrad else None, self.C)
+        ops.bn_bwd_apply(dz, dz_f32, relu, dropout, key, x, xl, self.coef, self.save, self.k, dy, yl)
+
+
+class EngineBase:
+    def __init__(self, ops: Ops, module, B, H, W, world=None):
+        self.ops, self.module, self.B, self.H, self.W = ops, module, B, H, W
+        self._scratch = {}
+        self.world = world         # None or an object with all_reduce(tensor) and size
+        self.store = ParamStore(ops, module)
+        self.packed_version = None
+        self.seed = 0
+
+    def scratch(self, key, rows, ld, dtype=None):
+        t = self._scratch.get(key)
+        if t is None:
+            t = self.ops.zeros(rows, ld, dtype=dtype)
+            self._scratch[key] = t
+        return t
+
+    def sync_stats(self, sums, count):
+        if self.world is not None and self.world.size > 1:
+            self.world.all_reduce(sums)
+            return count * self.world.size
+        return count
+
+    def sync_bwd_stats(self, local, glob, count):
+        if self.world is not None and self.world.size > 1:
+            glob.copy_(local)
+            self.world.all_reduce(glob)
+            return glob, count * self.world.size
+        return local, count
+
+    def convs(self):
+        raise NotImplementedError
+
+    def repack(self, force=False):
+        self.store.ensure()
+        v = self.store.versions()
+        if not force and v == self.packed_version:
+            return
+        for c in self.convs():
+            c.pack(True)
+        self.packed_version = v
+
+    def _stage_fwd(self, conv: ConvL, bn: BNL, training):
+        conv.run_fwd()
+        ol = conv.g.out_lay
+        bn.forward(conv.raw, ol.rows, ol.ld, self.B * ol.H * ol.W, training)
+
+    def _stage_bwd(self, conv: ConvL, bn: BNL, srcs, relu, dropout, key, trunk=None, want_wgrad=True, want_dx=True,
+                   dz_out_f32=None):
+        """Backward of conv -> BN -> [ReLU] -> [dropout]: gather dz from the consumers, BN backward, conv backward."""
+        ops = self.ops
+        ol = conv.g.out_lay
+        B, H, W, Cc = ol.B, ol.H, ol.W, ol.C
+        if dz_out_f32 is not None:
+            dz, f32 = dz_out_f32, True
+        else:
+            dz, f32 = self.scratch(("dz", B * H * W, Cc), B * H * W, Cc), False
+        ops.grad_gather(srcs, B, H, W, Cc, dz, plain_lay(B, H, W, Cc), f32, trunk=trunk)
+        bn.backward(dz, f32, relu, dropout, key, conv.raw, ol, conv.dy, ol, B * H * W, want_wgrad)
+        conv.run_bwd(want_wgrad, want_dx)
+
+
+# ====================================================================================================
+class GeneratorEngine(EngineBase):
+    def __init__(self, ops, module, B, H, W, world=None):
+        super().__init__(ops, module, B, H, W, world)
+        m = module.model
+        assert m.n_downsampling == 2, "only n_downsampling=2 is built (the shipped configuration)"
+        assert H % 4 == 0 and W % 4 == 0
+        ngf, self.nb, self.use_dropout = m.ngf, m.n_blocks, m.use_dropout
+        assert ngf % 16 == 0, "ngf must be a multiple of 16"
+        self.in_nc = [m.input_nc_s1, m.input_nc_s2, m.input_nc_s3]
+        self.out_nc = m.output_nc
+        dim = ngf * 4
+        self.dim = dim
+        h4, w4 = H // 4, W // 4
+        E = self
+        # --- stems: conv7 -> BN ReLU -> conv3 s2 -> BN ReLU -> conv3 s2 -> BN ReLU
+        self.stem = []
+        for s in range(3):
+            seq = getattr(m, "stream%d_down" % (s + 1))
+            cin = self.in_nc[s]
+            c7 = ConvL(E, "s%d.c7" % s, geom_s1(B, H, W, 7, 'reflect', chan_pad(cin), ngf), cin, ngf, seq[1].weight,
+                       need_dx=False)
+            d1 = ConvL(E, "s%d.d1" % s, geom_s2(B, H, W, ngf, 2 * ngf), ngf, 2 * ngf, seq[4].weight)
+            d2 = ConvL(E, "s%d.d2" % s, geom_s2(B, H // 2, W // 2, 2 * ngf, dim), 2 * ngf, dim, seq[7].weight)
+            self.stem.append(dict(c7=c7, d1=d1, d2=d2, bn7=BNL(E, seq[2], ngf), bn1=BNL(E, seq[5], 2 * ngf),
+                                  bn2=BNL(E, seq[8], dim)))
+        # --- PAT blocks
+        j = 6 if self.use_dropout else 5
+        self.blocks = []
+        for i in range(self.nb):
+            blk = m.att[i]
+            cs = dim if i == 0 else 2 * dim
+            b = dict(c1=[], c2=[], bn1=[], bn2=None)
+            for s in range(3):
+                seq = getattr(blk, "conv_block_stream%d" % (s + 1))
+                cin = dim if s == 0 else cs
+                c1 = ConvL(E, "b%d.s%d.c1" % (i, s), geom_s1(B, h4, w4, 3, 'reflect', cin, cin), cin, cin, seq[1].weight)
+                c2 = ConvL(E, "b%d.s%d.c2" % (i, s), geom_s1(B, h4, w4, 3, 'reflect', cin, dim), cin, dim, seq[j].weight)
+                b["c1"].append(c1)
+                b["c2"].append(c2)
+                b["bn1"].append(BNL(E, seq[2], cin))
+                if s == 0:
+                    b["bn2"] = BNL(E, seq[j + 1], dim)
+            self.blocks.append(b)
+        # --- up path
+        up = m.stream1_up
+        self.up1 = ConvL(E, "up1", geom_up(B, h4, w4, dim, dim // 2), dim, dim // 2, up[0].weight, transposed=True)
+        self.up2 = ConvL(E, "up2", geom_up(B, 2 * h4, 2 * w4, dim // 2, ngf), dim // 2, ngf, up[3].weight,
+                         transposed=True)
+        self.bnu1, self.bnu2 = BNL(E, up[1], dim // 2), BNL(E, up[4], ngf)
+        self.cout = ConvL(E, "out", geom_s1(B, H, W, 7, 'reflect', ngf, chan_pad(self.out_nc)), ngf, self.out_nc,
+                          up[7].weight, bias=up[7].bias, act=2, out_f32=True)
+        self.trunk = [ops.zeros(B * h4 * w4, dim, dtype=torch.float32) for _ in range(2)]
+        self.fake = ops.zeros(B, self.out_nc, H, W, dtype=torch.float32)
+        self.h4, self.w4 = h4, w4
+        self.bwd_ready = False
+
+    def convs(self):
+        out = []
+        for st in self.stem:
+            out += [st["c7"], st["d1"], st["d2"]]
+        for b in self.blocks:
+            out += b["c1"] + b["c2"]
+        return out + [self.up1, self.up2, self.cout]
+
+    def _prepare_backward(self):
+        if self.bwd_ready:
+            return
+        for s, st in enumerate(self.stem):
+            st["c7"].prepare_backward("stem7", None)
+            st["d1"].prepare_backward("stemd1", "stemd1")
+            st["d2"].prepare_backward("stemd2", "stemd2")
+        for i, b in enumerate(self.blocks):
+            for s in range(3):
+                b["c1"][s].prepare_backward("c1", "c1.s%d" % s)     # dx kept until the previous block's gate backward
+                b["c2"][s].prepare_backward("c2.s%d" % s, "c2")
+        self.up1.prepare_backward("up1", "up1")
+        self.up2.prepare_backward("up2", "up2")
+        self.cout.prepare_backward("out", "out")
+        self.dtrunk = self.ops.zeros(self.B * self.h4 * self.w4, self.dim, dtype=torch.float32)
+        self.bwd_ready = True
+        self.repack(force=True)
+
+    # ------------------------------------------------------------------------------------------ forward
+    def forward(self, x1, x2a, x2b, x3a, x3b, training, step=0, net_id=0):
+        """x1: image [B,3,H,W]; (x2a | x2b): pose maps; (x3a | x3b): depth maps (NCHW fp32, second halves may be
+        None when the caller already concatenated). Returns the fp32 NCHW image buffer (owned by the engine)."""
+        ops, B, H, W = self.ops, self.B, self.H, self.W
+        if training:
+            self._prepare_backward()
+        self.repack()
+        self.training, self.step, self.net_id = training, step, net_id
+        b0 = self.blocks[0]
+        for s, (a, b_) in enumerate(((x1, None), (x2a, x2b), (x3a, x3b))):
+            st = self.stem[s]
+            c7, d1, d2 = st["c7"], st["d1"], st["d2"]
+            ops.assemble(a, b_, c7.x, c7.g.in_lay, 3, 3, True)
+            self._stage_fwd(c7, st["bn7"], training)
+            ops.norm_act(c7.raw, c7.g.out_lay, st["bn7"].coef, True, False, 0, d1.x, d1.g.in_lay, 1, 1, False)
+            self._stage_fwd(d1, st["bn1"], training)
+            ops.norm_act(d1.raw, d1.g.out_lay, st["bn1"].coef, True, False, 0, d2.x, d2.g.in_lay, 1, 1, False)
+            self._stage_fwd(d2, st["bn2"], training)
+            nxt = b0["c1"][s]
+            ops.norm_act(d2.raw, d2.g.out_lay, st["bn2"].coef, True, False, 0, nxt.x, nxt.g.in_lay, 1, 1, True,
+                         dst_f32=self.trunk[0] if s == 0 else None)
+        cur = 0
+        for i, b in enumerate(self.blocks):
+            for s in range(3):
+                c1, c2, bn1 = b["c1"][s], b["c2"][s], b["bn1"][s]
+                self._stage_fwd(c1, bn1, training)
+                drop = training and self.use_dropout
+                key = dropout_key(self.seed, net_id * 1000 + 3 * i + s, step) if drop else 0
+                ops.norm_act(c1.raw, c1.g.out_lay, bn1.coef, True, drop, key, c2.x, c2.g.in_lay, 1, 1, True)
+                c2.run_fwd()
+            c2s = b["c2"]
+            ol = c2s[0].g.out_lay
+            b["bn2"].forward(c2s[0].raw, ol.rows, ol.ld, B * ol.H * ol.W, training)
+            if i + 1 < self.nb:
+                n = self.blocks[i + 1]["c1"]
+                d1b, d1l = n[0].x, n[0].g.in_lay
+                d2b, d2l = n[1].x, n[1].g.in_lay
+                d3b, d3l = n[2].x, n[2].g.in_lay
+                lo, hi, refl = 1, 1, True
+            else:
+                d1b, d1l = self.up1.x, self.up1.g.in_lay
+                d2b = d3b = d2l = d3l = None
+                lo, hi, refl = 0, 1, False
+            ops.gate_fwd(c2s[0].raw, c2s[1].raw, c2s[2].raw, ol, b["bn2"].coef, self.trunk[cur], self.trunk[1 - cur],
+                         d1b, d1l, d2b, d2l, d3b, d3l, lo, hi, refl)
+            cur = 1 - cur
+        self._stage_fwd(self.up1, self.bnu1, training)
+        ops.norm_act(self.up1.raw, self.up1.g.out_lay, self.bnu1.coef, True, False, 0, self.up2.x, self.up2.g.in_lay,
+                     0, 1, False)
+        self._stage_fwd(self.up2, self.bnu2, training)
+        ops.norm_act(self.up2.raw, self.up2.g.out_lay, self.bnu2.coef, True, False, 0, self.cout.x,
+                     self.cout.g.in_lay, 3, 3, True)
+        self.cout.run_fwd()
+        ops.grid_to_nchw(self.cout.raw, self.cout.g.out_lay, self.fake, self.out_nc)
+        return self.fake
+
+    # ------------------------------------------------------------------------------------------ backward
+    def backward(self, dfake):
+        """dfake: fp32 NCHW gradient of the loss w.r.t. the generated image. Accumulates parameter gradients."""
+        assert self.training and self.bwd_ready
+        ops, B = self.ops, self.B
+        h4, w4, dim = self.h4, self.w4, self.dim
+        step, net_id = self.step, self.net_id
+        ops.tanh_bwd(dfake, self.fake, self.cout.dy, self.cout.g.out_lay, self.out_nc)
+        self.cout.run_bwd()
+        self._stage_bwd(self.up2, self.bnu2, [self.cout.dx_source()], True, False, 0)
+        self._stage_bwd(self.up1, self.bnu1, [self.up2.dx_source()], True, False, 0)
+        ops.grad_gather([self.up1.dx_source()], B, h4, w4, dim, self.dtrunk, plain_lay(B, h4, w4, dim), True)
+        for i in range(self.nb - 1, -1, -1):
+            b = self.blocks[i]
+            ex2 = ex3 = None
+            if i + 1 < self.nb:
+                n = self.blocks[i + 1]["c1"]
+                s1, s2, s3 = n[0].dx_source(), n[1].dx_source(), n[2].dx_source()
+                ops.grad_gather([s1, s2.view(dim, dim), s3.view(dim, dim)], B, h4, w4, dim, self.dtrunk,
+                                plain_lay(B, h4, w4, dim), True, trunk=self.dtrunk)
+                # swapped wiring: x2o of this block fed stream3 of the next one, x3o fed stream2
+                ex2, ex3 = s3.view(0, dim), s2.view(0, dim)
+            c2s, bn2 = b["c2"], b["bn2"]
+            ol = c2s[0].g.out_lay
+            ops.memset0(bn2.bsums)
+            ops.gate_bwd_reduce(self.dtrunk, c2s[0].raw, c2s[1].raw, c2s[2].raw, ol, bn2.coef, bn2.save, bn2.bsums)
+            sg, cnt = self.sync_bwd_stats(bn2.bsums, bn2.bsums_g, B * h4 * w4)
+            ops.bn_bwd_finalize(sg, bn2.bsums, cnt, bn2.k, bn2.mod.weight.grad, bn2.mod.bias.grad, dim)
+            ops.gate_bwd_apply(self.dtrunk, c2s[0].raw, c2s[1].raw, c2s[2].raw, ol, bn2.coef, bn2.save, bn2.k, ex2, ex3,
+                               c2s[0].dy, c2s[1].dy, c2s[2].dy, ol)
+            for s in range(3):
+                c1, c2, bn1 = b["c1"][s], b["c2"][s], b["bn1"][s]
+                c2.run_bwd()
+                drop = self.use_dropout
+                key = dropout_key(self.seed, net_id * 1000 + 3 * i + s, step) if drop else 0
+                self._stage_bwd(c1, bn1, [c2.dx_source()], True, drop, key)
+        b0 = self.blocks[0]["c1"]
+        for s in range(3):
+            st = self.stem[s]
+            self._stage_bwd(st["d2"], st["bn2"], [b0[s].dx_source()], True, False, 0,
+                            trunk=self.dtrunk if s == 0 else None)
+            self._stage_bwd(st["d1"], st["bn1"], [st["d2"].dx_source()], True, False, 0)
+            self._stage_bwd(st["c7"], st["bn7"], [st["d1"].dx_source()], True, False, 0, want_dx=False)
+
+
+# ====================================================================================================
+class DiscriminatorEngine(EngineBase):
+    def __init__(self, ops, module, B, H, W, world=None):
+        super().__init__(ops, module, B, H, W, world)
+        m = module
+        assert m.n_downsampling == 2, "only n_downsampling=2 is built (the shipped configuration)"
+        ndf, self.nb, self.use_dropout = m.ngf, m.n_blocks, m.use_dropout
+        assert ndf % 16 == 0
+        self.in_nc = m.input_nc
+        dim = ndf * 4
+        self.dim, self.h4, self.w4 = dim, H // 4, W // 4
+        h4, w4 = self.h4, self.w4
+        E, seq = self, m.model
+        self.c7 = ConvL(E, "c7", geom_s1(B, H, W, 7, 'reflect', chan_pad(self.in_nc), ndf), self.in_nc, ndf, seq[1].weight)
+        self.d1 = ConvL(E, "d1", geom_s2(B, H, W, ndf, 2 * ndf), ndf, 2 * ndf, seq[4].weight)
+        self.d2 = ConvL(E, "d2", geom_s2(B, H // 2, W // 2, 2 * ndf, dim), 2 * ndf, dim, seq[7].weight)
+        self.bn7, self.bn1, self.bn2 = BNL(E, seq[2], ndf), BNL(E, seq[5], 2 * ndf), BNL(E, seq[8], dim)
+        j = 6 if self.use_dropout else 5
+        self.blocks = []
+        for i in range(self.nb):
+            cb = seq[10 + i].conv_block
+            c1 = ConvL(E, "r%d.c1" % i, geom_s1(B, h4, w4, 3, 'reflect', dim, dim), dim, dim, cb[1].weight)
+            c2 = ConvL(E, "r%d.c2" % i, geom_s1(B, h4, w4, 3, 'reflect', dim, dim), dim, dim, cb[j].weight)
+            self.blocks.append(dict(c1=c1, c2=c2, bn1=BNL(E, cb[2], dim), bn2=BNL(E, cb[j + 1], dim)))
+        self.trunk = [ops.zeros(B * h4 * w4, dim, dtype=torch.float32) for _ in range(2)]
+        self.bwd_ready = False
+
+    def convs(self):
+        out = [self.c7, self.d1, self.d2]
+        for b in self.blocks:
+            out += [b["c1"], b["c2"]]
+        return out
+
+    def _prepare_backward(self):
+        if self.bwd_ready:
+            return
+        self.c7.prepare_backward("c7", "c7")
+        self.d1.prepare_backward("d1", "d1")
+        self.d2.prepare_backward("d2", "d2")
+        for b in self.blocks:
+            b["c1"].prepare_backward("c1", "c1")
+            b["c2"].prepare_backward("c2", "c2")
+        self.dtrunk = self.ops.zeros(self.B * self.h4 * self.w4, self.dim, dtype=torch.float32)
+        self.bwd_ready = True
+        self.repack(force=True)
+
+    def forward(self, xa, xb, training, step=0, net_id=0, need_backward=True):
+        """(xa | xb): NCHW fp32 input (channel concatenation). Returns the fp32 logits as a plain NHWC buffer
+        [B*h4*w4, 256] (owned by the engine)."""
+        ops, B = self.ops, self.B
+        if training and need_backward:
+            self._prepare_backward()
+        self.repack()
+        self.training, self.step, self.net_id = training, step, net_id
+        c7, d1, d2 = self.c7, self.d1, self.d2
+        ops.assemble(xa, xb, c7.x, c7.g.in_lay, 3, 3, True)
+        self._stage_fwd(c7, self.bn7, training)
+        ops.norm_act(c7.raw, c7.g.out_lay, self.bn7.coef, True, False, 0, d1.x, d1.g.in_lay, 1, 1, False)
+        self._stage_fwd(d1, self.bn1, training)
+        ops.norm_act(d1.raw, d1.g.out_lay, self.bn1.coef, True, False, 0, d2.x, d2.g.in_lay, 1, 1, False)
+        self._stage_fwd(d2, self.bn2, training)
+        n = self.blocks[0]["c1"]
+        ops.norm_act(d2.raw, d2.g.out_lay, self.bn2.coef, True, False, 0, n.x, n.g.in_lay, 1, 1, True,
+                     dst_f32=self.trunk[0])
+        cur = 0
+        for i, b in enumerate(self.blocks):
+            c1, c2 = b["c1"], b["c2"]
+            self._stage_fwd(c1, b["bn1"], training)
+            drop = training and self.use_dropout
+            key = dropout_key(self.seed, net_id * 1000 + i, step) if drop else 0
+            ops.norm_act(c1.raw, c1.g.out_lay, b["bn1"].coef, True, drop, key, c2.x, c2.g.in_lay, 1, 1, True)
+            self._stage_fwd(c2, b["bn2"], training)
+            if i + 1 < self.nb:
+                nx = self.blocks[i + 1]["c1"]
+                dst, dl = nx.x, nx.g.in_lay
+            else:
+                dst, dl = None, None
+            ops.norm_act(c2.raw, c2.g.out_lay, b["bn2"].coef, False, False, 0, dst, dl, 1, 1, True,
+                         resid=self.trunk[cur], dst_f32=self.trunk[1 - cur])
+            cur = 1 - cur
+        self.logits = self.trunk[cur]
+        return self.logits
+
+    def backward(self, dlogits, want_wgrad=True, want_input_grad=False):
+        """dlogits: fp32 plain [B*h4*w4, dim]. Returns the GradSource of the (padded) network input when asked."""
+        assert self.training and self.bwd_ready
+        ops, B, h4, w4, dim = self.ops, self.B, self.h4, self.w4, self.dim
+        step, net_id = self.step, self.net_id
+        dcur = dlogits
+        for i in range(self.nb - 1, -1, -1):
+            b = self.blocks[i]
+            c1, c2 = b["c1"], b["c2"]
+            ol = c2.g.out_lay
+            b["bn2"].backward(dcur, True, False, False, 0, c2.raw, ol, c2.dy, ol, B * h4 * w4, want_wgrad)
+            c2.run_bwd(want_wgrad)
+            drop = self.use_dropout
+            key = dropout_key(self.seed, net_id * 1000 + i, step) if drop else 0
+            self._stage_bwd(c1, b["bn1"], [c2.dx_source()], True, drop, key, want_wgrad=want_wgrad)
+            # d x_k = d x_{k+1} + fold(d pad(x_k))
+            ops.grad_gather([c1.dx_source()], B, h4, w4, dim, self.dtrunk, plain_lay(B, h4, w4, dim), True, trunk=dcur)
+            dcur = self.dtrunk
+        self._stage_bwd(self.d2, self.bn2, [], True, False, 0, trunk=dcur, want_wgrad=want_wgrad)
+        self._stage_bwd(self.d1, self.bn1, [self.d2.dx_source()], True, False, 0, want_wgrad=want_wgrad)
+        self._stage_bwd(self.c7, self.bn7, [self.d1.dx_source()], True, False, 0, want_wgrad=want_wgrad,
+                        want_dx=want_input_grad)
+        return self.c7.dx_source() if want_input_grad else None
+
+
+# ====================================================================================================
+VGG_MEAN = (0.485, 0.456, 0.406)
+VGG_STD = (0.229, 0.224, 0.225)
+
+
+class VggEngine:
+    """VGG19.features[0:4] on two inputs (generated image: slot 0, target: slot 1) + perceptual loss backward."""
+
+    def __init__(self, ops: Ops, w1, b1, w2, b2, B, H, W):
+        self.ops, self.B, self.H, self.W = ops, B, H, W
+        self._scratch = {}
+        E = self
+        self.w = [t.detach().to(ops.device, torch.float32).contiguous() for t in (w1, b1, w2, b2)]
+        g1 = geom_s1(B, H, W, 3, 'zero', 16, 64)
+        g2 = geom_s1(B, H, W, 3, 'zero', 64, 64)
+        self.c1, self.c2 = [], []
+        for slot in range(2):
+            c2 = ConvL(E, "vgg2.%d" % slot, g2, 64, 64, self.w[2], bias=self.w[3], act=1)
+            c1 = ConvL(E, "vgg1.%d" % slot, g1, 3, 64, self.w[0], bias=self.w[1], act=1, raw_buf=c2.x)
+            # conv1 writes straight into conv2's zero-haloed input
+            c1.fwd = convops.fwd_plans(ops.lib, g1, c1.x, c1.wp, c2.x, 16, 64, bias=c1.bias_p, act=1,
+                                       out_map=(g2.in_lay.Hg * g2.in_lay.Wg, g2.in_lay.Wg, 1, 1, 1, 1),
+                                       zero_invalid=False)
+            self.c1.append(c1)
+            self.c2.append(c2)
+        for c in self.c1 + self.c2:
+            c.pack(False)
+        mean = torch.tensor(VGG_MEAN, dtype=torch.float32)
+        std = torch.tensor(VGG_STD, dtype=torch.float32)
+        self.scale = (0.5 / std).to(ops.device)
+        self.shift = ((0.5 - mean) / std).to(ops.device)
+        self.bwd_ready = False
+
+    def scratch(self, key, rows, ld, dtype=None):
+        t = self._scratch.get(key)
+        if t is None:
+            t = self.ops.zeros(rows, ld, dtype=dtype)
+            self._scratch[key] = t
+        return t
+
+    def features(self, x, slot):
+        c1, c2 = self.c1[slot], self.c2[slot]
+        self.ops.assemble(x, None, c1.x, c1.g.in_lay, 1, 1, False, scale=self.scale, shift=self.shift)
+        c1.run_fwd()
+        c2.run_fwd()
+        return c2.raw
+
+    def loss_and_backward(self, fake, target, lambda_perc, mse, loss_acc, dfake):
+        """*loss_acc += lambda * mean|f - t| ; dfake (NCHW fp32) += d loss / d fake (None: loss only)."""
+        ops, B, H, W = self.ops, self.B, self.H, self.W
+        ff = self.features(fake, 0)
+        ft = self.features(target, 1)
+        n = B * 64 * H * W
+        c1, c2 = self.c1[0], self.c2[0]
+        if dfake is None:
+            ops.perc_loss(ff, ft, mse, lambda_perc / n, 0.0, loss_acc, None)
+            return
+        if not self.bwd_ready:
+            c2.need_dx = True
+            c2.prepare_backward("v2", "v2", need_wgrad=False)
+            c1.prepare_backward("v1", "v1", need_wgrad=False)
+            c2.pack(True)
+            c1.pack(True)
+            self.bwd_ready = True
+        ops.perc_loss(ff, ft, mse, lambda_perc / n, lambda_perc / n, loss_acc, c2.dy)
+        c2.run_bwd(False)
+        # through the ReLU of conv1 (its output lives in conv2's input buffer)
+        ops.grad_gather([c2.dx_source()], B, H, W, 64, c1.dy, c1.g.out_lay, False, mask=c2.x, ml=c2.g.in_lay)
+        c1.run_bwd(False)
+        ops.input_grad_nchw(c1.dx_source(), self.scale, dfake, B, 3, H, W, True)

@@ -1,0 +1,201 @@
+"""Python-side wrappers of the C-ABI kernels (include/mmhand_sm100.h): torch tensors in, ctypes structs out.
+
+``Ops`` binds a loaded library and a stream getter. The product constructs it with the CUDA library
+(``Ops.cuda()``); CPU tests of the host logic pass the host-emulation library explicitly.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as L
+from .layouts import Lay
+
+
+def clay(l: Lay) -> L.Lay:
+    return L.Lay(l.B, l.H, l.W, l.Hg, l.Wg, l.h0, l.w0, 1 if l.phase else 0, l.ld, l.c0, l.C, 0)
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class GradSource:
+    """Data gradient of a consumer convolution, addressed in the consumer's input layout."""
+
+    def __init__(self, buf, lay: Lay, pad_lo, pad_hi, reflect):
+        self.buf, self.lay, self.pad_lo, self.pad_hi, self.reflect = buf, lay, pad_lo, pad_hi, reflect
+
+    def view(self, c0, Cv):
+        return GradSource(self.buf, self.lay.view(c0, Cv), self.pad_lo, self.pad_hi, self.reflect)
+
+    def c(self):
+        s = L.GradSrc()
+        s.p = self.buf.data_ptr()
+        s.l = clay(self.lay)
+        s.pad_lo, s.pad_hi, s.reflect = self.pad_lo, self.pad_hi, 1 if self.reflect else 0
+        return s
+
+
+class Ops:
+    def __init__(self, lib, device, stream_fn):
+        self.lib = lib
+        self.device = torch.device(device)
+        self._stream = stream_fn
+        self.launches = 0
+        self.act_dtype = torch.bfloat16 if lib.act_bytes == 2 else torch.float32
+
+    @staticmethod
+    def cuda(device=None):
+        lib = L.load()
+        if not torch.cuda.is_available():
+            raise L.MmhError("mmhand_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        return Ops(lib, dev, lambda: torch.cuda.current_stream(dev).cuda_stream)
+
+    # ------------------------------------------------------------------ helpers
+    def st(self):
+        return C.c_void_p(self._stream())
+
+    def ck(self, rc):
+        self.launches += 1
+        if rc != 0:
+            raise L.MmhError(self.lib.mmh_last_error().decode("utf-8", "replace"))
+
+    def zeros(self, *shape, dtype=None):
+        dtype = dtype or self.act_dtype
+        return torch.zeros(*shape, dtype=dtype, device=self.device)
+
+    def empty(self, *shape, dtype=None):
+        dtype = dtype or self.act_dtype
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def memset0(self, t):
+        self.ck(self.lib.mmh_memset(t.data_ptr(), 0, t.numel() * t.element_size(), self.st()))
+
+    # ------------------------------------------------------------------ forward elementwise
+    def assemble(self, src0, src1, dst, dl: Lay, pad_lo, pad_hi, reflect, scale=None, shift=None):
+        c0 = src0.shape[1]
+        c1 = src1.shape[1] if src1 is not None else 0
+        cl = clay(dl)
+        self.ck(self.lib.mmh_assemble_nchw(_p(src0), c0, _p(src1), c1, _p(scale), _p(shift), _p(dst), C.byref(cl),
+                                           pad_lo, pad_hi, 1 if reflect else 0, self.st()))
+
+    def bn_stats(self, x, rows, ld, Cc, sums):
+        self.ck(self.lib.mmh_bn_stats(_p(x), rows, ld, Cc, _p(sums), self.st()))
+
+    def bn_finalize(self, sums, count, gamma, beta, rm, rv, momentum, eps, train, Cc, coef, save):
+        self.ck(self.lib.mmh_bn_finalize(_p(sums), float(count), _p(gamma), _p(beta), _p(rm), _p(rv), momentum, eps,
+                                         1 if train else 0, Cc, _p(coef), _p(save), self.st()))
+
+    def norm_act(self, src, sl: Lay, coef, relu, dropout, key, dst, dl: Lay, pad_lo, pad_hi, reflect, resid=None,
+                 dst_f32=None):
+        p = L.NormAct()
+        p.src, p.sl, p.coef = _p(src), clay(sl), _p(coef)
+        p.relu, p.dropout, p.drop_key = int(relu), int(dropout), key & 0xFFFFFFFF
+        p.resid, p.dst = _p(resid), _p(dst)
+        p.dl = clay(dl) if dl is not None else clay(sl)
+        p.pad_lo, p.pad_hi, p.reflect = pad_lo, pad_hi, 1 if reflect else 0
+        p.dst_f32 = _p(dst_f32)
+        self.ck(self.lib.mmh_norm_act(C.byref(p), self.st()))
+
+    def gate_fwd(self, c1, x2o, x3o, sl, coef, trunk_in, trunk_out, d1, d1l, d2, d2l, d3, d3l, pad_lo, pad_hi, reflect):
+        p = L.GateFwd()
+        p.c1, p.x2o, p.x3o, p.sl, p.coef = _p(c1), _p(x2o), _p(x3o), clay(sl), _p(coef)
+        p.trunk_in, p.trunk_out = _p(trunk_in), _p(trunk_out)
+        p.d1, p.d1l = _p(d1), clay(d1l)
+        p.d2, p.d2l = _p(d2), clay(d2l if d2l is not None else d1l)
+        p.d3, p.d3l = _p(d3), clay(d3l if d3l is not None else d1l)
+        p.pad_lo, p.pad_hi, p.reflect = pad_lo, pad_hi, 1 if reflect else 0
+        self.ck(self.lib.mmh_gate_fwd(C.byref(p), self.st()))
+
+    # ------------------------------------------------------------------ backward elementwise
+    def grad_gather(self, srcs, B, H, W, Cc, dst, dl: Lay, dst_f32, trunk=None, mask=None, ml=None):
+        p = L.GradGather()
+        p.nsrc, p.dst_f32, p.B, p.H, p.W, p.C = len(srcs), 1 if dst_f32 else 0, B, H, W, Cc
+        for i, s in enumerate(srcs):
+            p.src[i] = s.c()
+        p.trunk, p.mask = _p(trunk), _p(mask)
+        p.ml = clay(ml if ml is not None else dl)
+        p.dst, p.dl = _p(dst), clay(dl)
+        self.ck(self.lib.mmh_grad_gather(C.byref(p), self.st()))
+
+    def _bn_bwd(self, dz, dz_f32, relu, dropout, key, x, xl, coef, save, sums=None, k=None, dy=None, yl=None):
+        p = L.BnBwd()
+        p.dz, p.dz_f32, p.relu, p.dropout, p.drop_key = _p(dz), 1 if dz_f32 else 0, int(relu), int(dropout), key & 0xFFFFFFFF
+        p.x, p.xl, p.coef, p.save = _p(x), clay(xl), _p(coef), _p(save)
+        p.sums, p.k, p.dy = _p(sums), _p(k), _p(dy)
+        p.yl = clay(yl if yl is not None else xl)
+        return p
+
+    def bn_bwd_reduce(self, dz, dz_f32, relu, dropout, key, x, xl, coef, save, sums):
+        p = self._bn_bwd(dz, dz_f32, relu, dropout, key, x, xl, coef, save, sums=sums)
+        self.ck(self.lib.mmh_bn_bwd_reduce(C.byref(p), self.st()))
+
+    def bn_bwd_apply(self, dz, dz_f32, relu, dropout, key, x, xl, coef, save, k, dy, yl):
+        p = self._bn_bwd(dz, dz_f32, relu, dropout, key, x, xl, coef, save, k=k, dy=dy, yl=yl)
+        self.ck(self.lib.mmh_bn_bwd_apply(C.byref(p), self.st()))
+
+    def bn_bwd_finalize(self, sums_global, sums_local, count, k, dgamma, dbeta, Cc):
+        self.ck(self.lib.mmh_bn_bwd_finalize(_p(sums_global), _p(sums_local), float(count), _p(k), _p(dgamma),
+                                             _p(dbeta), Cc, self.st()))
+
+    def _gate_bwd(self, dout, c1, x2o, x3o, sl, coef, save, sums=None, k=None, ex2=None, ex3=None, dy1=None,
+                  dy2=None, dy3=None, yl=None):
+        p = L.GateBwd()
+        p.dout, p.c1, p.x2o, p.x3o, p.sl = _p(dout), _p(c1), _p(x2o), _p(x3o), clay(sl)
+        p.coef, p.save, p.sums, p.k = _p(coef), _p(save), _p(sums), _p(k)
+        if ex2 is not None:
+            p.ex2 = ex2.c()
+        if ex3 is not None:
+            p.ex3 = ex3.c()
+        p.dy1, p.dy2, p.dy3 = _p(dy1), _p(dy2), _p(dy3)
+        p.yl = clay(yl if yl is not None else sl)
+        return p
+
+    def gate_bwd_reduce(self, dout, c1, x2o, x3o, sl, coef, save, sums):
+        p = self._gate_bwd(dout, c1, x2o, x3o, sl, coef, save, sums=sums)
+        self.ck(self.lib.mmh_gate_bwd_reduce(C.byref(p), self.st()))
+
+    def gate_bwd_apply(self, dout, c1, x2o, x3o, sl, coef, save, k, ex2, ex3, dy1, dy2, dy3, yl):
+        p = self._gate_bwd(dout, c1, x2o, x3o, sl, coef, save, k=k, ex2=ex2, ex3=ex3, dy1=dy1, dy2=dy2, dy3=dy3, yl=yl)
+        self.ck(self.lib.mmh_gate_bwd_apply(C.byref(p), self.st()))
+
+    # ------------------------------------------------------------------ losses
+    def bce_logits(self, x, target, loss_scale, grad_scale, loss_acc, grad=None):
+        self.ck(self.lib.mmh_bce_logits(_p(x), x.numel(), float(target), loss_scale, grad_scale, _p(loss_acc),
+                                        _p(grad), self.st()))
+
+    def l1(self, a, b, loss_scale, grad_scale, loss_acc, grad_acc=None):
+        self.ck(self.lib.mmh_l1_f32(_p(a), _p(b), a.numel(), loss_scale, grad_scale, _p(loss_acc), _p(grad_acc),
+                                    self.st()))
+
+    def perc_loss(self, ff, ft, mse, loss_scale, grad_scale, loss_acc, dy=None):
+        self.ck(self.lib.mmh_perc_loss(_p(ff), _p(ft), ff.numel(), 1 if mse else 0, loss_scale, grad_scale,
+                                       _p(loss_acc), _p(dy), self.st()))
+
+    def tanh_bwd(self, dfake, fake, dy, yl: Lay, Cc):
+        cl = clay(yl)
+        self.ck(self.lib.mmh_tanh_bwd(_p(dfake), _p(fake), _p(dy), C.byref(cl), Cc, self.st()))
+
+    def input_grad_nchw(self, src: GradSource, scale, dst, B, Cc, H, W, accumulate):
+        s = src.c()
+        self.ck(self.lib.mmh_input_grad_nchw(C.byref(s), _p(scale), _p(dst), B, Cc, H, W, 1 if accumulate else 0,
+                                             self.st()))
+
+    def grid_to_nchw(self, src, sl: Lay, dst, Cc):
+        cl = clay(sl)
+        self.ck(self.lib.mmh_grid_to_nchw(_p(src), C.byref(cl), _p(dst), Cc, self.st()))
+
+    # ------------------------------------------------------------------ parameters
+    def pack_weight(self, src, s_n, s_c, s_t, N, Cc, T, dst, Np, Cp):
+        self.ck(self.lib.mmh_pack_weight(_p(src), s_n, s_c, s_t, N, Cc, T, _p(dst), Np, Cp, self.st()))
+
+    def unpack_wgrad(self, src, dst, s_n, s_c, s_t, N, Cc, T, accumulate):
+        self.ck(self.lib.mmh_unpack_wgrad(_p(src), _p(dst), s_n, s_c, s_t, N, Cc, T, 1 if accumulate else 0, self.st()))
+
+    def adam(self, p, g, m, v, lr, b1, b2, eps, step, grad_scale=1.0):
+        self.ck(self.lib.mmh_adam(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, b1, b2, eps, step, grad_scale, self.st()))
+
+    def heatmaps(self, uv, H, W, sigma, thresh, out):
+        n = uv.numel() // 2
+        self.ck(self.lib.mmh_heatmap_rasterize(_p(uv), n, H, W, float(sigma), float(thresh), _p(out), self.st()))

@@ -40,7 +40,61 @@ class WgradDesc(C.Structure):
         ("T", C.c_int32), ("shift", C.c_int32 * MAX_TAPS),
         ("dw", C.c_void_p), ("tap_index", C.c_int32 * MAX_TAPS), ("dw_taps", C.c_int32),
         ("N_store", C.c_int32), ("C_store", C.c_int32), ("split_k", C.c_int32),
-        ("dbg_lbo_sbo_swap", C.c_int32),
+    ]
+
+
+class Lay(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("B", "H", "W", "Hg", "Wg", "h0", "w0", "phase", "ld", "c0", "C", "reserved")]
+
+
+class NormAct(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("sl", Lay), ("coef", C.c_void_p),
+        ("relu", C.c_int32), ("dropout", C.c_int32), ("drop_key", C.c_uint32), ("reserved", C.c_int32),
+        ("resid", C.c_void_p), ("dst", C.c_void_p), ("dl", Lay),
+        ("pad_lo", C.c_int32), ("pad_hi", C.c_int32), ("reflect", C.c_int32), ("reserved2", C.c_int32),
+        ("dst_f32", C.c_void_p),
+    ]
+
+
+class GateFwd(C.Structure):
+    _fields_ = [
+        ("c1", C.c_void_p), ("x2o", C.c_void_p), ("x3o", C.c_void_p), ("sl", Lay), ("coef", C.c_void_p),
+        ("trunk_in", C.c_void_p), ("trunk_out", C.c_void_p),
+        ("d1", C.c_void_p), ("d1l", Lay), ("d2", C.c_void_p), ("d2l", Lay), ("d3", C.c_void_p), ("d3l", Lay),
+        ("pad_lo", C.c_int32), ("pad_hi", C.c_int32), ("reflect", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class GradSrc(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("l", Lay), ("pad_lo", C.c_int32), ("pad_hi", C.c_int32),
+                ("reflect", C.c_int32), ("reserved", C.c_int32)]
+
+
+class GradGather(C.Structure):
+    _fields_ = [
+        ("nsrc", C.c_int32), ("dst_f32", C.c_int32), ("B", C.c_int32), ("H", C.c_int32),
+        ("W", C.c_int32), ("C", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_int32),
+        ("src", GradSrc * 4), ("trunk", C.c_void_p), ("mask", C.c_void_p), ("ml", Lay),
+        ("dst", C.c_void_p), ("dl", Lay),
+    ]
+
+
+class BnBwd(C.Structure):
+    _fields_ = [
+        ("dz", C.c_void_p), ("dz_f32", C.c_int32), ("relu", C.c_int32), ("dropout", C.c_int32),
+        ("drop_key", C.c_uint32), ("x", C.c_void_p), ("xl", Lay), ("coef", C.c_void_p), ("save", C.c_void_p),
+        ("sums", C.c_void_p), ("k", C.c_void_p), ("dy", C.c_void_p), ("yl", Lay),
+    ]
+
+
+class GateBwd(C.Structure):
+    _fields_ = [
+        ("dout", C.c_void_p), ("c1", C.c_void_p), ("x2o", C.c_void_p), ("x3o", C.c_void_p), ("sl", Lay),
+        ("coef", C.c_void_p), ("save", C.c_void_p), ("sums", C.c_void_p), ("k", C.c_void_p),
+        ("ex2", GradSrc), ("ex3", GradSrc),
+        ("dy1", C.c_void_p), ("dy2", C.c_void_p), ("dy3", C.c_void_p), ("yl", Lay),
     ]
 
 
@@ -61,6 +115,8 @@ def load(path=None):
     lib.mmh_last_error.restype = C.c_char_p
     lib.mmh_version.restype = C.c_int
     lib.mmh_is_device_build.restype = C.c_int
+    lib.mmh_act_bytes.restype = C.c_int
+    lib.act_bytes = lib.mmh_act_bytes()      # 2 (bf16) in the product; 4 only in the fp32 host emulation
     _declare(lib)
     if path is None:
         _lib = lib
@@ -76,13 +132,38 @@ def _declare(lib):
     lib.mmh_wgrad_plan_destroy.argtypes = [vp]
     lib.mmh_wgrad_run.argtypes = [vp, vp]
     for name, args in _SIMPLE_SIGS.items():
-        fn = getattr(lib, name, None)
-        if fn is not None:
-            fn.argtypes = args
-            fn.restype = C.c_int
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
 
 
-_SIMPLE_SIGS = {}
+_vp, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
+_SIMPLE_SIGS = {
+    "mmh_assemble_nchw": [_vp, _i32, _vp, _i32, _vp, _vp, _vp, C.POINTER(Lay), _i32, _i32, _i32, _vp],
+    "mmh_bn_stats": [_vp, _i64, _i32, _i32, _vp, _vp],
+    "mmh_bn_finalize": [_vp, _f32, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _i32, _vp, _vp, _vp],
+    "mmh_norm_act": [C.POINTER(NormAct), _vp],
+    "mmh_gate_fwd": [C.POINTER(GateFwd), _vp],
+    "mmh_grad_gather": [C.POINTER(GradGather), _vp],
+    "mmh_bn_bwd_reduce": [C.POINTER(BnBwd), _vp],
+    "mmh_bn_bwd_apply": [C.POINTER(BnBwd), _vp],
+    "mmh_bn_bwd_finalize": [_vp, _vp, _f32, _vp, _vp, _vp, _i32, _vp],
+    "mmh_gate_bwd_reduce": [C.POINTER(GateBwd), _vp],
+    "mmh_gate_bwd_apply": [C.POINTER(GateBwd), _vp],
+    "mmh_bce_logits": [_vp, _i64, _f32, _f32, _f32, _vp, _vp, _vp],
+    "mmh_l1_f32": [_vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp],
+    "mmh_perc_loss": [_vp, _vp, _i64, _i32, _f32, _f32, _vp, _vp, _vp],
+    "mmh_tanh_bwd": [_vp, _vp, _vp, C.POINTER(Lay), _i32, _vp],
+    "mmh_input_grad_nchw": [C.POINTER(GradSrc), _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "mmh_grid_to_nchw": [_vp, C.POINTER(Lay), _vp, _i32, _vp],
+    "mmh_pack_weight": [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _vp],
+    "mmh_unpack_wgrad": [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp],
+    "mmh_adam": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _f32, _vp],
+    "mmh_memset": [_vp, _i32, _i64, _vp],
+    "mmh_heatmap_rasterize": [_vp, _i64, _i32, _i32, _f64, _f64, _vp, _vp],
+}
+EXPORTS = ["mmh_version", "mmh_last_error", "mmh_is_device_build", "mmh_conv_plan_create", "mmh_conv_plan_destroy",
+           "mmh_conv_run", "mmh_wgrad_plan_create", "mmh_wgrad_plan_destroy", "mmh_wgrad_run"] + list(_SIMPLE_SIGS)
 
 
 def check(lib, rc):

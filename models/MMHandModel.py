@@ -1,0 +1,264 @@
+"""Drop-in for the reference's ``models/MMHandModel.py`` (:26-384): same constructor (``opt``), attributes,
+``set_input / forward / test / optimize_parameters / get_current_errors / get_current_visuals / save`` flow and
+option names, with no APEX dependency. ``train.py`` runs unchanged with this package first on ``sys.path``.
+
+One optimisation step is the reference's (:310-330): generator step (D_PB and D_PP scored with the *real* label,
+L1 + VGG perceptual loss, ``pair_loss = L1 + (lambda_GAN*g_PB + lambda_GAN*g_PP)/2``), then D_PP, then D_PB (each
+``DG_ratio`` times, real batch and pooled fake batch), three Adam optimisers (lr, beta1, 0.999). It is executed as an
+explicit sequence of kernel launches on the engines of mmhand_b200.engine (no autograd tape): the discriminators'
+weight gradients that the reference computes and discards during the generator step and the VGG
+weight gradient (Q6) are simply not computed -- results are identical.
+
+Data parallel (``--distributed``): one process per GPU, per-rank batch = batchSize // world (options/base_options.py:178
+stays the caller's job), BatchNorm statistics and gradients all-reduced over NCCL (apex SyncBN + DDP in the reference).
+bf16 storage with fp32 accumulation / statistics / master weights replaces AMP (``--opt_level`` is accepted and ignored;
+``overflow`` is always False).
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from losses.L1_plus_perceptualLoss import L1_plus_perceptualLoss
+from mmhand_b200 import runtime
+from util.image_pool import ImagePool
+
+from .base_model import BaseModel
+from .Discriminator import Discriminator
+from .Generator import Generator
+from .network_utils import GANLoss, get_norm_layer, get_scheduler, init_weights, print_network
+
+
+class MMHandModel(BaseModel):
+    def name(self):
+        return 'MMHandModel'
+
+    def __init__(self, opt):
+        super(MMHandModel, self).__init__(opt)
+        self.overflow = False
+        self.device = self._device()
+        input_nc = [opt.H_input_nc, opt.P_input_nc + opt.P_input_nc, opt.D_input_nc + opt.D_input_nc]
+        self.netG = self.define_G(input_nc, opt.output_nc, opt.ngf, opt.norm, not opt.no_dropout, opt.init_type,
+                                  self.gpu_ids, n_downsampling=opt.G_n_downsampling)
+        if self.isTrain:
+            self.netD_PB = self.define_D(opt.H_input_nc + opt.P_input_nc, opt.ndf, opt.n_layers_D, opt.norm,
+                                         opt.no_lsgan, opt.init_type, self.gpu_ids, not opt.no_dropout_D,
+                                         n_downsampling=opt.D_n_downsampling)
+            self.netD_PP = self.define_D(opt.H_input_nc + opt.H_input_nc, opt.ndf, opt.n_layers_D, opt.norm,
+                                         opt.no_lsgan, opt.init_type, self.gpu_ids, not opt.no_dropout_D,
+                                         n_downsampling=opt.D_n_downsampling)
+        if not self.isTrain or opt.continue_train:
+            self.load_network()
+        self.world = runtime.World() if getattr(opt, 'distributed', False) else None
+        if self.isTrain:
+            self.old_lr = opt.lr
+            self.fake_PP_pool = ImagePool(opt.pool_size)
+            self.fake_PB_pool = ImagePool(opt.pool_size)
+            self.criterionGAN = GANLoss(use_lsgan=not opt.no_lsgan, gpu=self.opt.local_rank)
+            if opt.L1_type == 'origin':
+                self.criterionL1 = torch.nn.L1Loss()
+                raise NotImplementedError("L1_type 'origin' is not built on the B200 path (shipped: l1_plus_perL1)")
+            elif opt.L1_type == 'l1_plus_perL1':
+                self.criterionL1 = L1_plus_perceptualLoss(opt.lambda_A, opt.lambda_B, opt.perceptual_layers,
+                                                          self.gpu_ids, opt.percep_is_l1).to(self.device)
+            else:
+                raise Exception('Unsurportted type of L1!')
+            # torch optimisers are kept as the holders of lr / schedulers (API compatibility); the update itself is
+            # the fused Adam kernel over each network's flat parameter buffer
+            mk = lambda net: torch.optim.Adam(net.parameters(), lr=opt.lr, betas=(opt.beta1, 0.999))
+            self.optimizer_G, self.optimizer_D_PB, self.optimizer_D_PP = mk(self.netG), mk(self.netD_PB), mk(self.netD_PP)
+            self.optimizers = [self.optimizer_G, self.optimizer_D_PB, self.optimizer_D_PP]
+            self.schedulers = [get_scheduler(o, opt) for o in self.optimizers]
+            self._step = 0
+            self._acc = None
+        if self.master:
+            print('---------- Networks initialized -------------')
+            print_network(self.netG)
+            if self.isTrain:
+                print_network(self.netD_PB)
+                print_network(self.netD_PP)
+                print(opt.local_rank)
+            print('-----------------------------------------------')
+
+    def _device(self):
+        lr = self.opt.local_rank
+        if isinstance(lr, str):
+            return torch.device(lr)
+        return torch.device('cuda', lr) if torch.cuda.is_available() else torch.device('cpu')
+
+    def define_G(self, input_nc, output_nc, ngf, norm='batch', use_dropout=False, init_type='normal', gpu_ids=[],
+                 n_downsampling=2):
+        assert len(input_nc) == 3
+        netG = Generator(input_nc, output_nc, ngf, norm_layer=get_norm_layer(norm_type=norm), use_dropout=use_dropout,
+                         n_blocks=9, gpu_ids=gpu_ids, n_downsampling=n_downsampling)
+        netG = netG.to(self.device)
+        init_weights(netG, init_type=init_type)
+        return netG
+
+    def define_D(self, input_nc, ndf, n_layers_D=3, norm='batch', use_sigmoid=False, init_type='normal', gpu_ids=[],
+                 use_dropout=False, n_downsampling=2):
+        netD = Discriminator(input_nc, ndf, norm_layer=get_norm_layer(norm_type=norm), use_dropout=use_dropout,
+                             n_blocks=n_layers_D, gpu_ids=[], padding_type='reflect', use_sigmoid=False,
+                             n_downsampling=n_downsampling)
+        netD = netD.to(self.device)
+        init_weights(netD, init_type=init_type)
+        return netD
+
+    # ------------------------------------------------------------------------------------------ data
+    def set_input(self, input):
+        dev = self.device
+        f = lambda k: input[k].to(dev, torch.float32, non_blocking=True).contiguous()
+        self.input_H1, self.input_P1, self.input_D1 = f('H1'), f('P1'), f('D1')
+        self.input_H2, self.input_P2, self.input_D2 = f('H2'), f('P2'), f('D2')
+        if 'H1_path' in input:
+            self.image_paths = input['H1_path'][0] + '___' + input['H2_path'][0]
+
+    def _g_engine(self):
+        B, _, H, W = self.input_H1.shape
+        return self.netG.engine(B, H, W, self.world)
+
+    def forward(self):
+        eng = self._g_engine()
+        eng.seed = getattr(self.opt, 'seed', 0) if self.isTrain else 0
+        self.fake_p2 = eng.forward(self.input_H1, self.input_P1, self.input_P2, self.input_D1, self.input_D2,
+                                   self.netG.training, step=getattr(self, '_step', 0), net_id=0)
+
+    def test(self):
+        self.forward()
+
+    def get_image_paths(self):
+        return self.image_paths
+
+    # ------------------------------------------------------------------------------------------ training
+    def _d_engine(self, net):
+        B, _, H, W = self.input_H1.shape
+        eng = net.engine(B, H, W, self.world)
+        eng.seed = getattr(self.opt, 'seed', 0)
+        return eng
+
+    def _lr(self, optimizer):
+        return optimizer.param_groups[0]['lr']
+
+    def _adam(self, eng, optimizer):
+        if self.world is not None and self.world.size > 1:
+            self.world.all_reduce(eng.store.grad)
+            scale = 1.0 / self.world.size
+        else:
+            scale = 1.0
+        if not self.overflow:
+            eng.store.adam(self._lr(optimizer), self.opt.beta1, 0.999, 1e-8, grad_scale=scale)
+
+    def backward_G(self):
+        """reference :236-261; accumulators: 0 g_PB, 1 g_PP (mean BCE), 2 lambda_A*L1, 3 lambda_B*perceptual."""
+        opt, ops, acc = self.opt, self._ops, self._acc
+        fake, dfake = self.fake_p2, self._dfake
+        ops.memset0(dfake)
+        B, C3, H, W = fake.shape
+        for k, (net, other, ids) in enumerate(((self.netD_PB, self.input_P2, 1), (self.netD_PP, self.input_H1, 4))):
+            eng = self._d_engine(net)
+            logits = eng.forward(fake, other, True, step=self._step, net_id=ids)
+            n = logits.numel()
+            dl = self._dlogits(logits)
+            ops.bce_logits(logits, 1.0, 1.0 / n, opt.lambda_GAN / 2.0 / n, acc[k:k + 1], dl)
+            src = eng.backward(dl, want_wgrad=False, want_input_grad=True)
+            ops.input_grad_nchw(src, None, dfake, B, C3, H, W, True)
+        n = fake.numel()
+        crit = self.criterionL1
+        ops.l1(fake, self.input_H2, opt.lambda_A / n, opt.lambda_A / n, acc[2:3], dfake)
+        crit.vgg_engine(B, H, W).loss_and_backward(fake, self.input_H2, opt.lambda_B, opt.percep_is_l1 != 1, acc[3:4],
+                                                   dfake)
+        self._g_engine().backward(dfake)
+
+    def _dlogits(self, logits):
+        if getattr(self, '_dl', None) is None or self._dl.shape != logits.shape:
+            self._dl = torch.empty_like(logits)
+        return self._dl
+
+    def backward_D_basic(self, netD, real_a, real_b, fake, acc_idx, ids):
+        """reference :263-274: 0.5 * lambda_GAN * (BCE(D(real), 1) + BCE(D(fake), 0))."""
+        opt, ops, acc = self.opt, self._ops, self._acc
+        eng = self._d_engine(netD)
+        for j, (xa, xb, target, nid) in enumerate(((real_a, real_b, 1.0, ids), (fake, None, 0.0, ids + 1))):
+            logits = eng.forward(xa, xb, True, step=self._step, net_id=nid)
+            n = logits.numel()
+            dl = self._dlogits(logits)
+            s = 0.5 * opt.lambda_GAN / n
+            ops.bce_logits(logits, target, s, s, acc[acc_idx + j:acc_idx + j + 1], dl)
+            eng.backward(dl, want_wgrad=True, want_input_grad=False)
+        return eng
+
+    def backward_D_PB(self):
+        fake_PB = self.fake_PB_pool.query(torch.cat((self.fake_p2, self.input_P2), 1).data)
+        return self.backward_D_basic(self.netD_PB, self.input_H2, self.input_P2, fake_PB.contiguous(), 6, 2)
+
+    def backward_D_PP(self):
+        fake_PP = self.fake_PP_pool.query(torch.cat((self.fake_p2, self.input_H1), 1).data)
+        return self.backward_D_basic(self.netD_PP, self.input_H2, self.input_H1, fake_PP.contiguous(), 4, 5)
+
+    def optimize_parameters(self):
+        self._ops = runtime.get_ops(self.device)
+        ops = self._ops
+        if self._acc is None:
+            self._acc = torch.zeros(8, dtype=torch.float32, device=ops.device)
+        ops.memset0(self._acc)
+        self.forward()
+        if getattr(self, '_dfake', None) is None or self._dfake.shape != self.fake_p2.shape:
+            self._dfake = torch.zeros_like(self.fake_p2)
+        # G
+        g_eng = self._g_engine()
+        g_eng.store.zero_grad()
+        self.backward_G()
+        self._adam(g_eng, self.optimizer_G)
+        # D_PP then D_PB (reference order)
+        for _ in range(self.opt.DG_ratio):
+            eng = self._d_engine(self.netD_PP)
+            eng.store.zero_grad()
+            self._acc[4:6].zero_()
+            self.backward_D_PP()
+            self._adam(eng, self.optimizer_D_PP)
+        for _ in range(self.opt.DG_ratio):
+            eng = self._d_engine(self.netD_PB)
+            eng.store.zero_grad()
+            self._acc[6:8].zero_()
+            self.backward_D_PB()
+            self._adam(eng, self.optimizer_D_PB)
+        self.overflow = False
+        self._step += 1
+        a, lam = self._acc.clone(), self.opt.lambda_GAN
+        self.loss_G_GAN_PB, self.loss_G_GAN_PP = a[0], a[1]
+        self.loss_originL1, self.loss_perceptual = a[2], a[3]
+        self.loss_G_L1 = a[2] + a[3]
+        self.pair_L1loss = self.loss_G_L1
+        self.pair_GANloss = (a[0] * lam + a[1] * lam) / 2
+        self.loss_D_PP = a[4] + a[5]
+        self.loss_D_PB = a[6] + a[7]
+
+    def get_current_errors(self):
+        ret_errors = OrderedDict([('pair_L1loss', self.pair_L1loss)])
+        ret_errors['D_PP'] = self.loss_D_PP
+        ret_errors['D_PB'] = self.loss_D_PB
+        ret_errors['pair_GANloss'] = self.pair_GANloss
+        ret_errors['origin_L1'] = self.loss_originL1
+        ret_errors['perceptual'] = self.loss_perceptual
+        return ret_errors
+
+    def get_current_visuals(self):
+        import util.util as util
+        height, width = self.input_H1.size(2), self.input_H1.size(3)
+        panels = [util.tensor2im(self.input_H1.data), util.draw_pose_from_map(self.input_P1.data)[0],
+                  util.tensor2im(self.input_D1.data), util.tensor2im(self.input_H2.data),
+                  util.draw_pose_from_map(self.input_P2.data)[0], util.tensor2im(self.input_D2.data),
+                  util.tensor2im(self.fake_p2.data)]
+        vis = np.zeros((height, width * 7, 3)).astype(np.uint8)
+        for i, p in enumerate(panels):
+            vis[:, width * i:width * (i + 1), :] = p
+        return OrderedDict([('vis', vis)])
+
+    def save(self, label):
+        self.save_network(self.netG, 'netG', label, self.gpu_ids)
+        self.save_network(self.netD_PB, 'netD_PB', label, self.gpu_ids)
+        self.save_network(self.netD_PP, 'netD_PP', label, self.gpu_ids)
+
+    def pprint(self, msg):
+        if self.master:
+            print(msg)

@@ -211,7 +211,7 @@ def case_conv_dgrad(kind='s1', B=2, H=16, W=16, Cin=64, Cout=64, k=3, mode='refl
     return _cmp("dgrad_%s_B%d_%dx%d_%d-%d_k%d" % (kind, B, H, W, Cin, Cout, k), got, want)
 
 
-def case_conv_wgrad(kind='s1', B=2, H=16, W=16, Cin=64, Cout=64, k=3, mode='reflect', seed=7, split_k=0, dbg_swap=0):
+def case_conv_wgrad(kind='s1', B=2, H=16, W=16, Cin=64, Cout=64, k=3, mode='reflect', seed=7, split_k=0):
     lib = _lib()
     g, x, w, Cin_p, Cout_p = _conv_setup(kind, B, H, W, Cin, Cout, k, mode, seed)
     dy = _rand(B, Cout, g.Ho, g.Wo, seed=seed + 2)
@@ -221,15 +221,14 @@ def case_conv_wgrad(kind='s1', B=2, H=16, W=16, Cin=64, Cout=64, k=3, mode='refl
     a_buf = to_grid(x, g.in_lay, Cin_p, g.in_pad_lo, g.in_pad_hi, mode if kind == 's1' else 'zero')
     dy_buf = to_grid(dy, g.out_lay, Cout_p, 0, 0, 'zero')
     dw = torch.zeros(k * k, Cout, Cin, dtype=torch.float32, device=DEV)
-    plans = convops.wgrad_plans(lib, g, a_buf, dy_buf, dw, Cin_p, Cout_p, Cin, Cout, split_k=split_k,
-                                dbg_swap=dbg_swap)
+    plans = convops.wgrad_plans(lib, g, a_buf, dy_buf, dw, Cin_p, Cout_p, Cin, Cout, split_k=split_k)
     for p_ in plans:
         p_.run(_stream())
     _sync()
     got = dw.cpu().reshape(k, k, Cout, Cin).permute(2, 3, 0, 1)
     if kind == 'up':
         got = got.permute(1, 0, 2, 3)
-    r = _cmp("wgrad_%s_B%d_%dx%d_%d-%d_k%d_swap%d" % (kind, B, H, W, Cin, Cout, k, dbg_swap), got.contiguous(), want,
+    r = _cmp("wgrad_%s_B%d_%dx%d_%d-%d_k%d" % (kind, B, H, W, Cin, Cout, k), got.contiguous(), want,
              tol=1e-2)
     return r
 
@@ -293,7 +292,6 @@ CASES = {
     "dgrad_s2": lambda: case_conv_dgrad('s2', 2, 32, 32, 64, 128),
     "dgrad_up": lambda: case_conv_dgrad('up', 2, 16, 16, 256, 128),
     "wgrad_s1_3x3": lambda: case_conv_wgrad('s1', 2, 16, 16, 64, 64, 3),
-    "wgrad_s1_3x3_swap": lambda: case_conv_wgrad('s1', 2, 16, 16, 64, 64, 3, dbg_swap=1),
     "wgrad_s1_3x3_256": lambda: case_conv_wgrad('s1', 2, 32, 32, 256, 256, 3),
     "wgrad_s1_3x3_512": lambda: case_conv_wgrad('s1', 1, 32, 32, 512, 256, 3),
     "wgrad_s1_7x7_c3": lambda: case_conv_wgrad('s1', 1, 32, 32, 3, 64, 7),
