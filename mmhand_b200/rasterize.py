@@ -1,0 +1,27 @@
+"""Keypoint -> 21-joint Gaussian heatmap rasteriser on the GPU (mmh_heatmap_rasterize).
+
+Mirrors ``Genericdataset.get_heatmaps / gen_heatmap / gaussian_kernel`` of the reference
+(data/generic_dataset.py:191-199, :208-217, :238-242): one map per joint,
+``exp(-((gx-x)^2+(gy-y)^2)/2/sigma/sigma)`` in float64, values > 1 clamped to 1, values < 0.0099 zeroed, cast to
+float32 last. The reference passes ``(shape[0], shape[1])`` as ``(width, height)`` (harmless on square frames, Q15);
+here ``shape = (H, W)`` and x indexes columns.
+"""
+import torch
+
+from . import runtime
+
+SIGMA = 6.0
+THRESH = 0.0099
+
+
+def get_heatmaps(uv_coords, shape=(256, 256), sigma=SIGMA, thresh=THRESH, out=None, device=None):
+    """uv_coords: [..., J, 2] (x, y), any float dtype / device -> float32 [..., J, H, W] on the GPU."""
+    H, W = int(shape[0]), int(shape[1])
+    uv = torch.as_tensor(uv_coords)
+    ops = runtime.get_ops(device if device is not None else (uv.device if uv.is_cuda else None))
+    uv = uv.to(ops.device, torch.float64).contiguous()
+    lead = tuple(uv.shape[:-1])
+    if out is None:
+        out = torch.empty(lead + (H, W), dtype=torch.float32, device=ops.device)
+    ops.heatmaps(uv, H, W, sigma, thresh, out)
+    return out
