@@ -1,0 +1,192 @@
+"""Host logic of the engines (layouts, fused elementwise kernels' index arithmetic, backward wiring, optimiser,
+ImagePool, loss bookkeeping) against the oracle, on the HOST EMULATION of the C ABI.
+
+f32 emulation (activations stored as fp32): tight tolerances -- proves the calculus; bf16 emulation: the rounding
+the CUDA path applies -- sets expectations for the GPU tolerances. The product never loads these libraries."""
+import random
+
+import pytest
+import torch
+
+import hostemu
+from mmhand_b200 import runtime
+from oracle import patn_ref as O
+from oracle.ref_shims import make_opt
+
+
+@pytest.fixture
+def emu_f32():
+    runtime._TEST_OPS = hostemu.ops(f32=True)
+    yield
+    runtime._TEST_OPS = None
+
+
+@pytest.fixture
+def emu_bf16():
+    runtime._TEST_OPS = hostemu.ops(f32=False)
+    yield
+    runtime._TEST_OPS = None
+
+
+def _sd(net):
+    return {k: v.detach().clone() for k, v in net.state_dict().items()}
+
+
+def _grad_sd(sd):
+    return {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+            for k, v in sd.items()}
+
+
+def _gen(ngf=16):
+    from models.Generator import Generator
+    from models.network_utils import get_norm_layer, init_weights
+    g = Generator([3, 42, 6], 3, ngf, get_norm_layer('batch'), True, 9)
+    init_weights(g, 'normal')
+    return g
+
+
+def _calibrate_running_stats(net, x):
+    """running statistics := batch statistics of x (keeps eval-mode activations O(1) under N(0, 0.02) weights)."""
+    sd = _sd(net)
+    O.BN_MOM = 1.0
+    try:
+        with torch.no_grad():
+            O.generator_forward(sd, x, train=True, use_dropout=True)
+    finally:
+        O.BN_MOM = 0.1
+    net.load_state_dict(sd)
+
+
+def _x(B=2, S=32, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.rand(B, 3, S, S, generator=g) * 2 - 1, torch.rand(B, 42, S, S, generator=g),
+            torch.rand(B, 6, S, S, generator=g) * 2 - 1]
+
+
+def test_generator_eval_and_state_dict_roundtrip(emu_f32):
+    torch.manual_seed(1)
+    g = _gen()
+    x = _x()
+    _calibrate_running_stats(g, x)
+    sd = _sd(g)
+    g.eval()
+    with torch.no_grad():
+        y = g(x)
+        want = O.generator_forward(sd, x, train=False)
+    assert torch.allclose(y, want, atol=2e-5), (y - want).abs().max()
+    # reload other weights in place: the packed operands must follow
+    g2 = _gen()
+    g.load_state_dict(g2.state_dict())
+    with torch.no_grad():
+        y2 = g(x)
+        want2 = O.generator_forward(_sd(g2), x, train=False)
+    assert torch.allclose(y2, want2, atol=2e-5)
+
+
+def test_generator_train_backward_exact(emu_f32):
+    torch.manual_seed(2)
+    g = _gen()
+    sd = _sd(g)
+    x = _x(seed=3)
+    g.train()
+    y = g(x)
+    gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(4))
+    y.backward(gy)
+    sdo = _grad_sd(sd)
+    want = O.generator_forward(sdo, x, train=True, use_dropout=True, drop=O.DropCtx("hash", 0, 0, 0))
+    want.backward(gy)
+    assert torch.allclose(y.detach(), want.detach(), atol=5e-5)
+    for k, p in g.named_parameters():
+        r = sdo[k].grad
+        assert (p.grad - r).abs().max() <= 2e-4 * r.abs().max() + 1e-7, k
+    new = g.state_dict()
+    for k in new:
+        if "running" in k:
+            assert torch.allclose(new[k], sdo[k], atol=1e-6), k
+    assert int(new["model.stream1_down.2.num_batches_tracked"]) == 1
+
+
+def test_discriminator_and_losses_exact(emu_f32):
+    from losses.L1_plus_perceptualLoss import L1_plus_perceptualLoss
+    from models.Discriminator import Discriminator
+    from models.network_utils import GANLoss, get_norm_layer, init_weights
+    torch.manual_seed(5)
+    d = Discriminator(24, 16, get_norm_layer('batch'), True, 3, [], 'reflect', False, 2)
+    init_weights(d, 'normal')
+    sd = _sd(d)
+    x = (torch.rand(2, 24, 32, 32) * 2 - 1).requires_grad_(True)
+    d.train()
+    d.drop_net_id = 3
+    y = d(x)
+    loss = GANLoss(use_lsgan=False)(y, True)
+    loss.backward()
+    sdo = _grad_sd(sd)
+    xo = x.detach().clone().requires_grad_(True)
+    yo = O.discriminator_forward(sdo, xo, True, True, drop=O.DropCtx("hash", 0, 0, 3))
+    lo = O.gan_loss(yo, True)
+    lo.backward()
+    assert torch.allclose(y.detach(), yo.detach(), atol=1e-4)
+    assert abs(loss.item() - lo.item()) < 1e-6
+    assert (x.grad - xo.grad).abs().max() <= 1e-4 * xo.grad.abs().max()
+    for k, p in d.named_parameters():
+        r = sdo[k].grad
+        assert (p.grad - r).abs().max() <= 2e-4 * r.abs().max() + 1e-9, k
+    # L1 + perceptual
+    L = L1_plus_perceptualLoss(10.0, 10.0, 3, [0], 1)
+    fake = (torch.rand(2, 3, 32, 32) * 2 - 1).requires_grad_(True)
+    tgt = torch.rand(2, 3, 32, 32) * 2 - 1
+    out = L(fake, tgt)
+    out[0].backward()
+    vsd = {k: v.detach().clone() for k, v in L.vgg_submodel.state_dict().items()}
+    fo = fake.detach().clone().requires_grad_(True)
+    oo = O.l1_plus_perceptual(vsd, fo, tgt, 10.0, 10.0)
+    oo[0].backward()
+    for a, b in zip(out, oo):
+        assert abs(a.item() - b.item()) <= 1e-5 * abs(b.item())
+    assert (fake.grad - fo.grad).abs().max() <= 1e-5 * fo.grad.abs().max()
+    assert abs(GANLoss()(torch.zeros(1, 16, 4, 4), True).item() - 0.6931471805599453) < 1e-6
+
+
+def _run_steps(opt, n, seed):
+    from models.MMHandModel import MMHandModel
+    torch.manual_seed(5)
+    random.seed(5)
+    m = MMHandModel(opt)
+    vsd = {k: v.detach().clone() for k, v in m.criterionL1.vgg_submodel.state_dict().items()}
+    tr = O.OracleTrainer(_sd(m.netG), _sd(m.netD_PB), _sd(m.netD_PP), vsd, opt.lambda_A, opt.lambda_B, opt.lambda_GAN,
+                         opt.lr, opt.beta1, opt.pool_size, not opt.no_dropout, not opt.no_dropout_D, dropout="hash",
+                         seed=opt.seed)
+    gen = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.rand(*s, generator=gen)
+    B, S = opt.batchSize, opt.fineSize
+    batches = [dict(H1=r(B, 3, S, S) * 2 - 1, P1=r(B, 21, S, S), D1=r(B, 3, S, S) * 2 - 1, H2=r(B, 3, S, S) * 2 - 1,
+                    P2=r(B, 21, S, S), D2=r(B, 3, S, S) * 2 - 1) for _ in range(n)]
+    random.seed(9)
+    mine = []
+    for b in batches:
+        m.set_input(b)
+        m.optimize_parameters()
+        mine.append({k: float(v) for k, v in m.get_current_errors().items()})
+    random.seed(9)
+    ref = [tr.step(b["H1"], b["P1"], b["D1"], b["H2"], b["P2"], b["D2"]) for b in batches]
+    return m, tr, mine, ref
+
+
+def test_train_steps_exact(emu_f32):
+    """G, D_PP, D_PB steps with dropout, the image pool (size 3: swaps happen) and Adam, 3 steps, fp32 storage."""
+    opt = make_opt(batchSize=2, fineSize=32, ngf=16, ndf=16, pool_size=3, local_rank='cpu', seed=7)
+    m, tr, mine, ref = _run_steps(opt, 3, 11)
+    for a, b in zip(mine, ref):
+        for k in b:
+            assert abs(a[k] - b[k]) <= 5e-5 * max(1.0, abs(b[k])), (k, a[k], b[k])
+    for k, p in m.netG.named_parameters():
+        assert (p.detach() - tr.g[k].detach()).abs().max() <= 3 * 2.5 * opt.lr, k     # a few Adam steps at most
+
+
+def test_train_steps_bf16_tolerance(emu_bf16):
+    """Same with the bf16 storage the CUDA path uses: losses within the north-star tolerance (1e-2 relative)."""
+    opt = make_opt(batchSize=2, fineSize=32, ngf=16, ndf=16, pool_size=3, local_rank='cpu', seed=7)
+    m, tr, mine, ref = _run_steps(opt, 2, 11)
+    for a, b in zip(mine, ref):
+        for k in b:
+            assert abs(a[k] - b[k]) <= 1e-2 * abs(b[k]), (k, a[k], b[k])

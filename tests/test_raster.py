@@ -1,0 +1,35 @@
+"""Heatmap rasteriser: known answers of the oracle restatement and the kernel body on the host emulation."""
+import numpy as np
+import torch
+
+import hostemu
+from mmhand_b200 import runtime
+from oracle.raster_ref import get_heatmaps, get_heatmaps_batch
+
+
+def test_oracle_known_answers():
+    m = get_heatmaps(np.array([[100.0, 60.0]]))[0]
+    assert m.shape == (256, 256) and m.dtype == np.float32
+    assert m[60, 100] == 1.0                                   # row = y, column = x
+    assert abs(m[60, 103] - np.exp(-9.0 / 72.0)) < 1e-7
+    assert (m > 0).sum() == 1041
+    assert abs(m[m > 0].min() - 0.010508660465) < 1e-9
+    ys, xs = np.nonzero(m)
+    assert ((xs - 100) ** 2 + (ys - 60) ** 2).max() <= 332     # zero iff D2 > 332.2958...
+    assert np.array_equal(get_heatmaps_batch(np.array([[[100.0, 60.0]]]))[0, 0], m)
+
+
+def test_kernel_body_matches_oracle_bit_exactly():
+    runtime._TEST_OPS = hostemu.ops()
+    try:
+        from mmhand_b200.rasterize import get_heatmaps as gpu_heatmaps
+        rng = np.random.RandomState(49)
+        uv = rng.uniform(-20, 276, size=(6, 21, 2))
+        uv[0, 0] = (0.0, 0.0)
+        uv[0, 1] = (255.0, 255.0)
+        uv[0, 2] = (128.0, 128.0 + np.sqrt(332.2958775))       # threshold grazing
+        got = gpu_heatmaps(torch.from_numpy(uv), (256, 256)).numpy()
+        want = get_heatmaps_batch(uv, (256, 256))
+        assert np.array_equal(got, want)
+    finally:
+        runtime._TEST_OPS = None
