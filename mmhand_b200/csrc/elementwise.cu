@@ -15,16 +15,30 @@ struct PixIter {
   int b, h, w, g;
 };
 // item -> (b, h, w, g) over an extended window [-lo, H+hi) x [-lo, W+hi)
-MMH_HD PixIter decode_ext(int64_t i, int groups, int H, int W, int lo, int hi) {
+// (32-bit arithmetic: the launchers reject item counts >= 2^31; 64-bit divisions would make these kernels
+// ALU-bound instead of HBM-bound)
+MMH_HD PixIter decode_ext(int64_t i64, int groups, int H, int W, int lo, int hi) {
   PixIter p;
-  const int He = H + lo + hi, We = W + lo + hi;
-  p.g = static_cast<int>(i % groups);
-  int64_t pix = i / groups;
-  p.w = static_cast<int>(pix % We) - lo;
-  pix /= We;
-  p.h = static_cast<int>(pix % He) - lo;
-  p.b = static_cast<int>(pix / He);
+  const uint32_t He = H + lo + hi, We = W + lo + hi;
+  const uint32_t i = static_cast<uint32_t>(i64);
+  uint32_t pix = i / static_cast<uint32_t>(groups);
+  p.g = static_cast<int>(i - pix * groups);
+  uint32_t t = pix / We;
+  p.w = static_cast<int>(pix - t * We) - lo;
+  pix = t;
+  t = pix / He;
+  p.h = static_cast<int>(pix - t * He) - lo;
+  p.b = static_cast<int>(t);
   return p;
+}
+// plain pixel index r -> (b, h, w)
+MMH_HD void decode_pix(int64_t r64, int H, int W, int& b, int& h, int& w) {
+  const uint32_t r = static_cast<uint32_t>(r64);
+  uint32_t t = r / static_cast<uint32_t>(W);
+  w = static_cast<int>(r - t * W);
+  const uint32_t u = t / static_cast<uint32_t>(H);
+  h = static_cast<int>(t - u * H);
+  b = static_cast<int>(u);
 }
 
 // ------------------------------------------------------------------------------------------------ assemble
@@ -262,9 +276,8 @@ struct BnBwdReduceF {
   BnBwdCommon cm;
   MMH_HD void operator()(int64_t r, int g, float (&acc)[2][8]) const {
     const int W = cm.xl.W, H = cm.xl.H;
-    const int w = static_cast<int>(r % W);
-    const int h = static_cast<int>((r / W) % H);
-    const int b = static_cast<int>(r / (static_cast<int64_t>(W) * H));
+    int b, h, w;
+    decode_pix(r, H, W, b, h, w);
     float dze[8], xhat[8];
     cm.load(b, h, w, g, dze, xhat);
 #pragma unroll
@@ -324,9 +337,8 @@ struct GateBwdReduceF {
   GateBwdCommon cm;
   MMH_HD void operator()(int64_t r, int g, float (&acc)[2][8]) const {
     const int W = cm.sl.W, H = cm.sl.H;
-    const int w = static_cast<int>(r % W);
-    const int h = static_cast<int>((r / W) % H);
-    const int b = static_cast<int>(r / (static_cast<int64_t>(W) * H));
+    int b, h, w;
+    decode_pix(r, H, W, b, h, w);
     float d1[8], xhat[8], d2[8], d3[8];
     cm.load(b, h, w, g, d1, xhat, d2, d3);
 #pragma unroll

@@ -51,9 +51,10 @@ struct TanhBwdF {
   const float* d; const float* y; act_t* dy; LayD yl; int C;
   MMH_HD void operator()(int64_t i) const {
     const int H = yl.H, W = yl.W;
-    const int w = static_cast<int>(i % W);
-    const int h = static_cast<int>((i / W) % H);
-    const int b = static_cast<int>(i / (static_cast<int64_t>(W) * H));
+    const uint32_t iu = static_cast<uint32_t>(i);
+    const int w = static_cast<int>(iu % W);
+    const int h = static_cast<int>((iu / W) % H);
+    const int b = static_cast<int>(iu / (static_cast<uint32_t>(W) * H));
     float o[8];
     zero8(o);
     for (int c = 0; c < C; ++c) {
@@ -79,10 +80,11 @@ MMH_HD int preimages1(int i, int n, int lo, int hi, int reflect, int (&out)[3]) 
 struct InputGradF {
   GradSrc1 s; const float* scale; float* dst; int C, H, W, accumulate;
   MMH_HD void operator()(int64_t i) const {
-    const int w = static_cast<int>(i % W);
-    const int h = static_cast<int>((i / W) % H);
-    const int c = static_cast<int>((i / (static_cast<int64_t>(W) * H)) % C);
-    const int b = static_cast<int>(i / (static_cast<int64_t>(W) * H * C));
+    const uint32_t iu = static_cast<uint32_t>(i);
+    const int w = static_cast<int>(iu % W);
+    const int h = static_cast<int>((iu / W) % H);
+    const int c = static_cast<int>((iu / (static_cast<uint32_t>(W) * H)) % C);
+    const int b = static_cast<int>(iu / (static_cast<uint32_t>(W) * H * C));
     int hs[3], ws[3];
     const int nh = preimages1(h, H, s.lo, s.hi, s.reflect, hs);
     const int nw = preimages1(w, W, s.lo, s.hi, s.reflect, ws);
@@ -98,10 +100,11 @@ struct GridToNchwF {
   const float* src; LayD sl; float* dst; int C;
   MMH_HD void operator()(int64_t i) const {
     const int H = sl.H, W = sl.W;
-    const int w = static_cast<int>(i % W);
-    const int h = static_cast<int>((i / W) % H);
-    const int c = static_cast<int>((i / (static_cast<int64_t>(W) * H)) % C);
-    const int b = static_cast<int>(i / (static_cast<int64_t>(W) * H * C));
+    const uint32_t iu = static_cast<uint32_t>(i);
+    const int w = static_cast<int>(iu % W);
+    const int h = static_cast<int>((iu / W) % H);
+    const int c = static_cast<int>((iu / (static_cast<uint32_t>(W) * H)) % C);
+    const int b = static_cast<int>(iu / (static_cast<uint32_t>(W) * H * C));
     dst[i] = src[lay_off(sl, b, h, w) + c];
   }
 };

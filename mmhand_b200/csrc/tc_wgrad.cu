@@ -4,8 +4,12 @@
 // dimension of the NHWC grids, channels are contiguous. TMA brings 64-row x CW-channel boxes (CW = 64,
 // 32 or 16 channels with 128/64/32-byte swizzle); the UMMA descriptors walk them with
 // LBO = bytes between channel groups (one box), SBO = bytes between 8-row groups.
-// One CTA = one (tap, 128 dy-channels, <=256 a-channels, K split); fp32 partial sums are reduced into
-// dw with red.global.add.f32.
+//
+// One CTA = one (tap group, 128 dy-channels, <=256 a-channels, K split). A tap group is G consecutive taps
+// whose accumulators sit side by side in TMEM (G * BNc <= 384 columns): the dy tile of a pipeline stage is
+// loaded once and multiplied against the G shifted activation tiles, which is what makes the 49-tap stem
+// convolutions (tiny channel counts, 1.1 M pixel rows) cheap. fp32 partial sums are reduced into dw with
+// red.global.add.f32.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -22,16 +26,17 @@ namespace mmh {
 constexpr int kWgThreads = 192;
 constexpr int kWgBK = 64;      // pixel rows per pipeline stage
 constexpr int kWgMaxStages = 8;
+constexpr int kWgMaxCols = 384;
 
 struct WgradKParams {
-  int32_t T, tiles_n, tiles_c, split;
+  int32_t T, G, n_tg, tiles_n, tiles_c, split;
   int32_t BNc;                 // a-channels per tile (instruction N)
   int32_t cw_n, cw_c;          // channel-group widths (elements) of dy / a boxes
-  int32_t boxes_n, boxes_c;    // boxes per stage for dy (128/cw_n) and a (BNc/cw_c)
+  int32_t boxes_n, boxes_c;    // boxes per stage for dy (128/cw_n) and per tap for a (BNc/cw_c)
   int32_t ksteps_total;        // ceil(M / 64)
   int32_t N_store, C_store, dw_taps;
-  uint32_t sub_n_bytes, sub_c_bytes, stage_bytes, n_stages, a_stage_off;
-  uint32_t swz_n, swz_c, lbo_n, sbo_n, lbo_c, sbo_c, raw_sbo_n, raw_sbo_c, tmem_cols;
+  uint32_t sub_n_bytes, sub_c_bytes, tap_bytes, stage_bytes, n_stages, a_stage_off;
+  uint32_t swz_n, swz_c, lbo_n, sbo_n, lbo_c, sbo_c, tmem_cols;
   float* dw;
   int32_t shift[MMH_MAX_TAPS];
   int32_t tap_index[MMH_MAX_TAPS];
@@ -56,7 +61,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
   const int ks = unit % p.split; unit /= p.split;
   const int tc = unit % p.tiles_c; unit /= p.tiles_c;
   const int tn = unit % p.tiles_n; unit /= p.tiles_n;
-  const int t = unit;
+  const int tg = unit;
+  const int t0 = tg * p.G;
+  const int g_cnt = min(p.G, p.T - t0);
   const int per = (p.ksteps_total + p.split - 1) / p.split;
   const int k_begin = ks * per;
   const int k_end = min(p.ksteps_total, k_begin + per);
@@ -85,7 +92,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
     if (warp == 0) {
       if (lane == 0) {
         uint32_t stage = 0, phase = 0;
-        const uint32_t bytes = p.boxes_n * p.sub_n_bytes + p.boxes_c * p.sub_c_bytes;
+        const uint32_t bytes = p.boxes_n * p.sub_n_bytes + g_cnt * p.tap_bytes;
         for (int it = 0; it < n_iters; ++it) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], bytes);
@@ -94,8 +101,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
           const int q0 = (k_begin + it) * kWgBK;
           for (int b = 0; b < p.boxes_n; ++b)
             tma_load_2d(&tmDy, &full_bar[stage], sn + b * p.sub_n_bytes, tn * 128 + b * p.cw_n, q0);
-          for (int b = 0; b < p.boxes_c; ++b)
-            tma_load_2d(&tmA, &full_bar[stage], sc + b * p.sub_c_bytes, tc * p.BNc + b * p.cw_c, q0 + p.shift[t]);
+          for (int j = 0; j < g_cnt; ++j) {
+            const int row = q0 + p.shift[t0 + j];
+            for (int b = 0; b < p.boxes_c; ++b)
+              tma_load_2d(&tmA, &full_bar[stage], sc + j * p.tap_bytes + b * p.sub_c_bytes, tc * p.BNc + b * p.cw_c, row);
+          }
           if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -111,9 +121,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
 #pragma unroll
           for (int k = 0; k < kWgBK / 16; ++k) {
             // 16 pixel rows per MMA = two 8-row groups
-            const uint64_t ad = make_smem_desc(sn + k * 2 * p.raw_sbo_n, p.lbo_n, p.sbo_n, p.swz_n);
-            const uint64_t bd = make_smem_desc(sc + k * 2 * p.raw_sbo_c, p.lbo_c, p.sbo_c, p.swz_c);
-            umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+            const uint64_t ad = make_smem_desc(sn + k * 2 * p.sbo_n, p.lbo_n, p.sbo_n, p.swz_n);
+            for (int j = 0; j < g_cnt; ++j) {
+              const uint64_t bd = make_smem_desc(sc + j * p.tap_bytes + k * 2 * p.sbo_c, p.lbo_c, p.sbo_c, p.swz_c);
+              umma_bf16(tmem_base + j * p.BNc, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
@@ -127,16 +139,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
       mbar_wait(acc_bar, 0);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-      float* dst_row = p.dw + (static_cast<int64_t>(p.tap_index[t]) * p.N_store + n) * p.C_store;
-      for (int j = 0; j < p.BNc / 16; ++j) {
-        uint32_t v[16];
-        tmem_ld16(t_addr + j * 16, v);
-        tmem_ld_wait();
-        const int c0 = tc * p.BNc + j * 16;
-        if (n < p.N_store) {
+      for (int j = 0; j < g_cnt; ++j) {
+        float* dst_row = p.dw + (static_cast<int64_t>(p.tap_index[t0 + j]) * p.N_store + n) * p.C_store;
+        for (int c16 = 0; c16 < p.BNc / 16; ++c16) {
+          uint32_t v[16];
+          tmem_ld16(t_addr + j * p.BNc + c16 * 16, v);
+          tmem_ld_wait();
+          const int c0 = tc * p.BNc + c16 * 16;
+          if (n < p.N_store) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (c0 + i < p.C_store) atomicAdd(dst_row + c0 + i, __uint_as_float(v[i]));
+            for (int i = 0; i < 16; ++i) {
+              if (c0 + i < p.C_store) atomicAdd(dst_row + c0 + i, __uint_as_float(v[i]));
+            }
           }
         }
       }
@@ -167,11 +181,17 @@ static CUtensorMapSwizzle swz_of(int cw) {
   return cw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (cw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
+static int wgrad_fail(MmhWgradPlan* plan) {
+  delete plan;
+  return 1;
+}
+
 extern "C" int mmh_wgrad_plan_create(const MmhWgradDesc* d, MmhWgradPlan** out_plan) {
   MMH_CHECK(d && out_plan, "null argument");
   MMH_CHECK(d->T >= 1 && d->T <= MMH_MAX_TAPS, "T=%d out of range", d->T);
   MMH_CHECK(d->C >= 16 && (d->C % 16) == 0 && d->N >= 16 && (d->N % 16) == 0, "C=%d / N=%d must be multiples of 16",
             d->C, d->N);
+  MMH_CHECK(d->C <= 256 || (d->C % 256) == 0, "C=%d unsupported (must be <=256 or a multiple of 256)", d->C);
   MMH_CHECK((d->a_ld % 8) == 0 && (d->dy_ld % 8) == 0, "leading dimensions must be multiples of 8");
   MMH_CHECK(d->M > 0 && d->M < (int64_t(1) << 31) - 256, "M out of range");
   auto* plan = new MmhWgradPlan();
@@ -181,13 +201,14 @@ extern "C" int mmh_wgrad_plan_create(const MmhWgradDesc* d, MmhWgradPlan** out_p
   k.cw_n = pick_cw(d->N);
   k.cw_c = pick_cw(d->C);
   k.tiles_n = (d->N + 127) / 128;
-  if (d->C <= 256) {
-    k.BNc = d->C;
-  } else {
-    MMH_CHECK((d->C % 256) == 0, "C=%d unsupported (must be <=256 or a multiple of 256)", d->C);
-    k.BNc = 256;
-  }
+  k.BNc = d->C <= 256 ? d->C : 256;
   k.tiles_c = d->C / k.BNc;
+  // taps per CTA: as many accumulators as fit in kWgMaxCols TMEM columns, balanced over the groups
+  int gmax = kWgMaxCols / k.BNc;
+  if (gmax < 1) gmax = 1;
+  if (gmax > d->T) gmax = d->T;
+  k.n_tg = (d->T + gmax - 1) / gmax;
+  k.G = (d->T + k.n_tg - 1) / k.n_tg;
   k.boxes_n = 128 / k.cw_n;
   k.boxes_c = k.BNc / k.cw_c;
   k.ksteps_total = static_cast<int32_t>((d->M + kWgBK - 1) / kWgBK);
@@ -196,31 +217,38 @@ extern "C" int mmh_wgrad_plan_create(const MmhWgradDesc* d, MmhWgradPlan** out_p
   k.dw_taps = d->dw_taps > 0 ? d->dw_taps : d->T;
   k.sub_n_bytes = kWgBK * k.cw_n * 2;
   k.sub_c_bytes = kWgBK * k.cw_c * 2;
+  k.tap_bytes = k.boxes_c * k.sub_c_bytes;
   k.a_stage_off = k.boxes_n * k.sub_n_bytes;  // 16 KB
-  k.stage_bytes = k.a_stage_off + k.boxes_c * k.sub_c_bytes;
+  k.stage_bytes = k.a_stage_off + k.G * k.tap_bytes;
   k.stage_bytes = (k.stage_bytes + 1023u) & ~1023u;
   const uint32_t budget = 227 * 1024 - 1024 - 256;
   k.n_stages = budget / k.stage_bytes;
   if (k.n_stages > kWgMaxStages) k.n_stages = kWgMaxStages;
+  if (k.n_stages < 2) {
+    set_error("wgrad tile does not fit in shared memory");
+    return wgrad_fail(plan);
+  }
   k.swz_n = k.cw_n == 64 ? 2u : (k.cw_n == 32 ? 4u : 6u);
   k.swz_c = k.cw_c == 64 ? 2u : (k.cw_c == 32 ? 4u : 6u);
   k.lbo_n = k.sub_n_bytes; k.sbo_n = 8 * k.cw_n * 2;
   k.lbo_c = k.sub_c_bytes; k.sbo_c = 8 * k.cw_c * 2;
-  k.raw_sbo_n = k.sbo_n; k.raw_sbo_c = k.sbo_c;
   uint32_t cols = 32;
-  while (cols < static_cast<uint32_t>(k.BNc)) cols <<= 1;
+  while (cols < static_cast<uint32_t>(k.G * k.BNc)) cols <<= 1;
   k.tmem_cols = cols;
   k.dw = d->dw;
   for (int t = 0; t < d->T; ++t) {
     k.shift[t] = d->shift[t];
     k.tap_index[t] = d->tap_index[t];
-    MMH_CHECK(d->tap_index[t] >= 0 && d->tap_index[t] < k.dw_taps, "tap_index[%d] out of range", t);
+    if (d->tap_index[t] < 0 || d->tap_index[t] >= k.dw_taps) {
+      set_error("tap_index[%d] out of range", t);
+      return wgrad_fail(plan);
+    }
   }
-  const int units = k.T * k.tiles_n * k.tiles_c;
+  const int units = k.n_tg * k.tiles_n * k.tiles_c;
   int split = d->split_k;
   if (split <= 0) {
     const int sms = num_sms();
-    split = (sms + units - 1) / units;
+    split = sms / units;
     const int max_split = k.ksteps_total / 8 > 0 ? k.ksteps_total / 8 : 1;
     if (split > max_split) split = max_split;
     if (split < 1) split = 1;
@@ -230,14 +258,12 @@ extern "C" int mmh_wgrad_plan_create(const MmhWgradDesc* d, MmhWgradPlan** out_p
   plan->smem = static_cast<size_t>(k.n_stages) * k.stage_bytes + 1024 + 256;
   if (make_tmap_2d_bf16(&plan->tmDy, d->dy, d->N, d->M, d->dy_ld, k.cw_n, kWgBK, swz_of(k.cw_n)) ||
       make_tmap_2d_bf16(&plan->tmA, d->a, d->C, d->a_rows, d->a_ld, k.cw_c, kWgBK, swz_of(k.cw_c))) {
-    delete plan;
-    return 1;
+    return wgrad_fail(plan);
   }
   cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(wgrad_kernel): %s", cudaGetErrorString(e));
-    delete plan;
-    return 1;
+    return wgrad_fail(plan);
   }
   *out_plan = plan;
   return 0;

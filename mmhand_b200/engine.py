@@ -12,18 +12,11 @@ no host synchronisation). Layer structure and arithmetic follow the reference mo
 import torch
 
 from . import convops
-from .kernels import GradSource, Ops
+from .kernels import GradSource, KeyRef, Ops, dropout_key  # noqa: F401
 from .layouts import Lay, chan_pad, geom_s1, geom_s2, geom_up
 
 BN_EPS = 1e-5
 BN_MOM = 0.1
-M32 = 0xFFFFFFFF
-
-
-def dropout_key(seed, layer_id, step):
-    """Same key schedule as oracle/patn_ref.py::dropout_key."""
-    return (seed * 0x9E3779B1 + layer_id * 0x85EBCA77 + step * 0xC2B2AE3D + 0x27D4EB2F) & M32
-
 
 def plain_lay(B, H, W, Cc):
     return Lay(B, H, W, H, W, 0, 0, False, Cc, 0, Cc)
@@ -72,8 +65,14 @@ class ParamStore:
         if self.m is None:
             self.m = torch.zeros_like(self.flat)
             self.v = torch.zeros_like(self.flat)
-        self.step += 1
-        self.ops.adam(self.flat, self.grad, self.m, self.v, lr, beta1, beta2, eps, self.step, grad_scale)
+        lr_fn = lr if callable(lr) else (lambda: lr)
+
+        def bump():
+            self.step += 1
+
+        self.ops.host(bump)
+        self.ops.adam(self.flat, self.grad, self.m, self.v, lr_fn(), beta1, beta2, eps, self.step, grad_scale,
+                      dyn=lambda: (lr_fn(), self.step))
 
     def versions(self):
         return tuple(p._version for p in self.params) + (self.step, self.flat.data_ptr())
@@ -116,7 +115,7 @@ class ConvL:
         if with_dgrad and self.need_dx and self.bwd_ready:
             ops.pack_weight(self.weight, sc, sn, st, self.Cin, self.Cout, self.T, self.wd, self.Cin_p, self.Cout_p)
         if self.bias is not None:
-            self.bias_p[:self.Cout].copy_(self.bias.detach())
+            ops.unpack_wgrad(self.bias, self.bias_p, 1, 0, 0, self.Cout, 1, 1, False)      # fp32 copy
 
     def prepare_backward(self, dy_key, dx_key, need_wgrad=True):
         if self.bwd_ready:
@@ -137,30 +136,25 @@ class ConvL:
         self.bwd_ready = True
 
     def run_fwd(self):
-        st = self.eng.ops._stream()
         for p in self.fwd:
-            p.run(st)
-            self.eng.ops.launches += 1
+            self.eng.ops.run_conv(p)
 
     def run_bwd(self, want_wgrad=True, want_dx=True):
         """Consumes self.dy. Weight gradient accumulates into weight.grad; data gradient lands in self.dx."""
         ops = self.eng.ops
-        st = ops._stream()
         if want_wgrad and self.has_wgrad:
             ops.memset0(self.dw)
             for p in self.wgrad:
-                p.run(st)
-                ops.launches += 1
+                ops.run_wgrad(p)
             sn, sc, stt = self._strides()
             ops.unpack_wgrad(self.dw, self.weight.grad, sn, sc, stt, self.Cout, self.Cin, self.T, True)
             if self.bias is not None:
                 ops.memset0(self.dbias)
                 ops.bn_stats(self.dy, self.g.out_lay.rows, self.Cout_p, self.Cout_p, self.dbias)
-                self.bias.grad.add_(self.dbias[:self.Cout])
+                ops.unpack_wgrad(self.dbias, self.bias.grad, 1, 0, 0, self.Cout, 1, 1, True)
         if want_dx and self.need_dx:
             for p in self.dgrad:
-                p.run(st)
-                ops.launches += 1
+                ops.run_conv(p)
 
     def dx_source(self):
         g = self.g
@@ -184,7 +178,7 @@ class BNL:
             count = self.eng.sync_stats(self.sums, count)
             ops.bn_finalize(self.sums, count, m.weight, m.bias, m.running_mean, m.running_var, BN_MOM, BN_EPS, True,
                             self.C, self.coef, self.save)
-            m.note_batch()
+            ops.host(m.note_batch)
         else:
             ops.bn_finalize(None, 1.0, m.weight, m.bias, m.running_mean, m.running_var, BN_MOM, BN_EPS, False, self.C,
                             self.coef, self.save)
@@ -217,14 +211,16 @@ class EngineBase:
 
     def sync_stats(self, sums, count):
         if self.world is not None and self.world.size > 1:
-            self.world.all_reduce(sums)
+            self.ops.host(lambda: self.world.all_reduce(sums))
             return count * self.world.size
         return count
 
     def sync_bwd_stats(self, local, glob, count):
         if self.world is not None and self.world.size > 1:
-            glob.copy_(local)
-            self.world.all_reduce(glob)
+            def exchange():
+                glob.copy_(local)
+                self.world.all_reduce(glob)
+            self.ops.host(exchange)
             return glob, count * self.world.size
         return local, count
 
@@ -352,6 +348,7 @@ class GeneratorEngine(EngineBase):
             self._prepare_backward()
         self.repack()
         self.training, self.step, self.net_id = training, step, net_id
+        self.ops.step = step
         b0 = self.blocks[0]
         for s, (a, b_) in enumerate(((x1, None), (x2a, x2b), (x3a, x3b))):
             st = self.stem[s]
@@ -371,7 +368,7 @@ class GeneratorEngine(EngineBase):
                 c1, c2, bn1 = b["c1"][s], b["c2"][s], b["bn1"][s]
                 self._stage_fwd(c1, bn1, training)
                 drop = training and self.use_dropout
-                key = dropout_key(self.seed, net_id * 1000 + 3 * i + s, step) if drop else 0
+                key = KeyRef(self.seed, net_id * 1000 + 3 * i + s) if drop else 0
                 ops.norm_act(c1.raw, c1.g.out_lay, bn1.coef, True, drop, key, c2.x, c2.g.in_lay, 1, 1, True)
                 c2.run_fwd()
             c2s = b["c2"]
@@ -407,6 +404,7 @@ class GeneratorEngine(EngineBase):
         ops, B = self.ops, self.B
         h4, w4, dim = self.h4, self.w4, self.dim
         step, net_id = self.step, self.net_id
+        ops.step = step
         ops.tanh_bwd(dfake, self.fake, self.cout.dy, self.cout.g.out_lay, self.out_nc)
         self.cout.run_bwd()
         self._stage_bwd(self.up2, self.bnu2, [self.cout.dx_source()], True, False, 0)
@@ -434,7 +432,7 @@ class GeneratorEngine(EngineBase):
                 c1, c2, bn1 = b["c1"][s], b["c2"][s], b["bn1"][s]
                 c2.run_bwd()
                 drop = self.use_dropout
-                key = dropout_key(self.seed, net_id * 1000 + 3 * i + s, step) if drop else 0
+                key = KeyRef(self.seed, net_id * 1000 + 3 * i + s) if drop else 0
                 self._stage_bwd(c1, bn1, [c2.dx_source()], True, drop, key)
         b0 = self.blocks[0]["c1"]
         for s in range(3):
@@ -499,6 +497,7 @@ class DiscriminatorEngine(EngineBase):
             self._prepare_backward()
         self.repack()
         self.training, self.step, self.net_id = training, step, net_id
+        self.ops.step = step
         c7, d1, d2 = self.c7, self.d1, self.d2
         ops.assemble(xa, xb, c7.x, c7.g.in_lay, 3, 3, True)
         self._stage_fwd(c7, self.bn7, training)
@@ -514,7 +513,7 @@ class DiscriminatorEngine(EngineBase):
             c1, c2 = b["c1"], b["c2"]
             self._stage_fwd(c1, b["bn1"], training)
             drop = training and self.use_dropout
-            key = dropout_key(self.seed, net_id * 1000 + i, step) if drop else 0
+            key = KeyRef(self.seed, net_id * 1000 + i) if drop else 0
             ops.norm_act(c1.raw, c1.g.out_lay, b["bn1"].coef, True, drop, key, c2.x, c2.g.in_lay, 1, 1, True)
             self._stage_fwd(c2, b["bn2"], training)
             if i + 1 < self.nb:
@@ -533,6 +532,7 @@ class DiscriminatorEngine(EngineBase):
         assert self.training and self.bwd_ready
         ops, B, h4, w4, dim = self.ops, self.B, self.h4, self.w4, self.dim
         step, net_id = self.step, self.net_id
+        ops.step = step
         dcur = dlogits
         for i in range(self.nb - 1, -1, -1):
             b = self.blocks[i]
@@ -541,7 +541,7 @@ class DiscriminatorEngine(EngineBase):
             b["bn2"].backward(dcur, True, False, False, 0, c2.raw, ol, c2.dy, ol, B * h4 * w4, want_wgrad)
             c2.run_bwd(want_wgrad)
             drop = self.use_dropout
-            key = dropout_key(self.seed, net_id * 1000 + i, step) if drop else 0
+            key = KeyRef(self.seed, net_id * 1000 + i) if drop else 0
             self._stage_bwd(c1, b["bn1"], [c2.dx_source()], True, drop, key, want_wgrad=want_wgrad)
             # d x_k = d x_{k+1} + fold(d pad(x_k))
             ops.grad_gather([c1.dx_source()], B, h4, w4, dim, self.dtrunk, plain_lay(B, h4, w4, dim), True, trunk=dcur)

@@ -2,13 +2,22 @@
 
 ``Ops`` binds a loaded library and a stream getter. The product constructs it with the CUDA library
 (``Ops.cuda()``); CPU tests of the host logic pass the host-emulation library explicitly.
+
+Launch tapes. A training step is ~1.7k kernel launches whose arguments (buffer pointers, layouts) never change
+once the engines are built, so building the ctypes descriptors again every step would make the step host-bound.
+``Ops.record()`` captures every C call of a code region as ``(function, argument tuple)``; ``Tape.replay()`` re-issues
+them with a tight loop. The few step-dependent scalars (dropout keys, Adam bias correction / lr) are refreshed by
+small patch callbacks registered at record time.
 """
 import ctypes as C
+from contextlib import contextmanager
 
 import torch
 
 from . import lib as L
 from .layouts import Lay
+
+M32 = 0xFFFFFFFF
 
 
 def clay(l: Lay) -> L.Lay:
@@ -17,6 +26,21 @@ def clay(l: Lay) -> L.Lay:
 
 def _p(t):
     return None if t is None else t.data_ptr()
+
+
+def dropout_key(seed, layer_id, step):
+    """Same key schedule as oracle/patn_ref.py::dropout_key."""
+    return (seed * 0x9E3779B1 + layer_id * 0x85EBCA77 + step * 0xC2B2AE3D + 0x27D4EB2F) & M32
+
+
+class KeyRef:
+    """Dropout key of one layer as a function of the training step (resolved at launch / replay time)."""
+
+    def __init__(self, seed, layer_id):
+        self.seed, self.layer_id = seed, layer_id
+
+    def resolve(self, step):
+        return dropout_key(self.seed, self.layer_id, step)
 
 
 class GradSource:
@@ -36,6 +60,32 @@ class GradSource:
         return s
 
 
+class Tape:
+    """Recorded launch sequence. Entries: [fn, args(list), patch] with fn None for host callbacks."""
+
+    def __init__(self, ops, stream):
+        self.ops, self.stream, self.cmds, self.keep = ops, stream, [], []
+
+    def replay(self, step):
+        ops = self.ops
+        ops.step = step
+        err = 0
+        for fn, args, patch in self.cmds:
+            if patch is not None:
+                patch(step, args)
+            if fn is None:
+                args()
+            else:
+                err |= fn(*args)
+        ops.launches += self.n_launches
+        if err:
+            raise L.MmhError(ops.lib.mmh_last_error().decode("utf-8", "replace"))
+
+    @property
+    def n_launches(self):
+        return sum(1 for c in self.cmds if c[0] is not None)
+
+
 class Ops:
     def __init__(self, lib, device, stream_fn):
         self.lib = lib
@@ -43,6 +93,9 @@ class Ops:
         self._stream = stream_fn
         self.launches = 0
         self.act_dtype = torch.bfloat16 if lib.act_bytes == 2 else torch.float32
+        self.tape = None
+        self.step = 0            # training step used to resolve KeyRefs in immediate mode
+        self.conv_hook = None    # optional callable(kind, plan, launch) wrapping conv launches (bench instrumentation)
 
     @staticmethod
     def cuda(device=None):
@@ -52,14 +105,35 @@ class Ops:
         dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         return Ops(lib, dev, lambda: torch.cuda.current_stream(dev).cuda_stream)
 
-    # ------------------------------------------------------------------ helpers
+    # ------------------------------------------------------------------ launch plumbing
     def st(self):
         return C.c_void_p(self._stream())
 
-    def ck(self, rc):
+    def _run(self, fn, args, patch=None, keep=None):
+        rc = fn(*args)
         self.launches += 1
         if rc != 0:
             raise L.MmhError(self.lib.mmh_last_error().decode("utf-8", "replace"))
+        if self.tape is not None:
+            self.tape.cmds.append([fn, list(args), patch])
+            if keep is not None:
+                self.tape.keep.append(keep)
+
+    def host(self, fn):
+        """Host-side bookkeeping that must be repeated on every replay (e.g. BN batch counters)."""
+        fn()
+        if self.tape is not None:
+            self.tape.cmds.append([None, fn, None])
+
+    @contextmanager
+    def record(self):
+        assert self.tape is None, "nested tape recording"
+        tape = Tape(self, self._stream())
+        self.tape = tape
+        try:
+            yield tape
+        finally:
+            self.tape = None
 
     def zeros(self, *shape, dtype=None):
         dtype = dtype or self.act_dtype
@@ -70,33 +144,55 @@ class Ops:
         return torch.empty(*shape, dtype=dtype, device=self.device)
 
     def memset0(self, t):
-        self.ck(self.lib.mmh_memset(t.data_ptr(), 0, t.numel() * t.element_size(), self.st()))
+        self._run(self.lib.mmh_memset, (t.data_ptr(), 0, t.numel() * t.element_size(), self.st()), keep=t)
+
+    def _key(self, key, struct):
+        """Resolve a dropout key now and return the patch that refreshes it on replay."""
+        if isinstance(key, KeyRef):
+            struct.drop_key = key.resolve(self.step)
+            return lambda step, args, s=struct, k=key: setattr(s, "drop_key", k.resolve(step))
+        struct.drop_key = int(key) & M32
+        return None
+
+    # ------------------------------------------------------------------ convolutions
+    def run_conv(self, plan):
+        if self.conv_hook is not None and self.tape is None:
+            self.conv_hook("conv", plan, lambda: self._run(self.lib.mmh_conv_run, (plan.handle, self.st())))
+        else:
+            self._run(self.lib.mmh_conv_run, (plan.handle, self.st()), keep=plan)
+
+    def run_wgrad(self, plan):
+        if self.conv_hook is not None and self.tape is None:
+            self.conv_hook("wgrad", plan, lambda: self._run(self.lib.mmh_wgrad_run, (plan.handle, self.st())))
+        else:
+            self._run(self.lib.mmh_wgrad_run, (plan.handle, self.st()), keep=plan)
 
     # ------------------------------------------------------------------ forward elementwise
     def assemble(self, src0, src1, dst, dl: Lay, pad_lo, pad_hi, reflect, scale=None, shift=None):
         c0 = src0.shape[1]
         c1 = src1.shape[1] if src1 is not None else 0
         cl = clay(dl)
-        self.ck(self.lib.mmh_assemble_nchw(_p(src0), c0, _p(src1), c1, _p(scale), _p(shift), _p(dst), C.byref(cl),
-                                           pad_lo, pad_hi, 1 if reflect else 0, self.st()))
+        self._run(self.lib.mmh_assemble_nchw, (_p(src0), c0, _p(src1), c1, _p(scale), _p(shift), _p(dst), C.byref(cl),
+                                               pad_lo, pad_hi, 1 if reflect else 0, self.st()), keep=(cl, src0, src1))
 
     def bn_stats(self, x, rows, ld, Cc, sums):
-        self.ck(self.lib.mmh_bn_stats(_p(x), rows, ld, Cc, _p(sums), self.st()))
+        self._run(self.lib.mmh_bn_stats, (_p(x), rows, ld, Cc, _p(sums), self.st()))
 
     def bn_finalize(self, sums, count, gamma, beta, rm, rv, momentum, eps, train, Cc, coef, save):
-        self.ck(self.lib.mmh_bn_finalize(_p(sums), float(count), _p(gamma), _p(beta), _p(rm), _p(rv), momentum, eps,
-                                         1 if train else 0, Cc, _p(coef), _p(save), self.st()))
+        self._run(self.lib.mmh_bn_finalize, (_p(sums), float(count), _p(gamma), _p(beta), _p(rm), _p(rv), momentum, eps,
+                                             1 if train else 0, Cc, _p(coef), _p(save), self.st()))
 
     def norm_act(self, src, sl: Lay, coef, relu, dropout, key, dst, dl: Lay, pad_lo, pad_hi, reflect, resid=None,
                  dst_f32=None):
         p = L.NormAct()
         p.src, p.sl, p.coef = _p(src), clay(sl), _p(coef)
-        p.relu, p.dropout, p.drop_key = int(relu), int(dropout), key & 0xFFFFFFFF
+        p.relu, p.dropout = int(relu), int(dropout)
+        patch = self._key(key, p)
         p.resid, p.dst = _p(resid), _p(dst)
         p.dl = clay(dl) if dl is not None else clay(sl)
         p.pad_lo, p.pad_hi, p.reflect = pad_lo, pad_hi, 1 if reflect else 0
         p.dst_f32 = _p(dst_f32)
-        self.ck(self.lib.mmh_norm_act(C.byref(p), self.st()))
+        self._run(self.lib.mmh_norm_act, (C.byref(p), self.st()), patch, keep=p)
 
     def gate_fwd(self, c1, x2o, x3o, sl, coef, trunk_in, trunk_out, d1, d1l, d2, d2l, d3, d3l, pad_lo, pad_hi, reflect):
         p = L.GateFwd()
@@ -106,7 +202,7 @@ class Ops:
         p.d2, p.d2l = _p(d2), clay(d2l if d2l is not None else d1l)
         p.d3, p.d3l = _p(d3), clay(d3l if d3l is not None else d1l)
         p.pad_lo, p.pad_hi, p.reflect = pad_lo, pad_hi, 1 if reflect else 0
-        self.ck(self.lib.mmh_gate_fwd(C.byref(p), self.st()))
+        self._run(self.lib.mmh_gate_fwd, (C.byref(p), self.st()), keep=p)
 
     # ------------------------------------------------------------------ backward elementwise
     def grad_gather(self, srcs, B, H, W, Cc, dst, dl: Lay, dst_f32, trunk=None, mask=None, ml=None):
@@ -117,27 +213,28 @@ class Ops:
         p.trunk, p.mask = _p(trunk), _p(mask)
         p.ml = clay(ml if ml is not None else dl)
         p.dst, p.dl = _p(dst), clay(dl)
-        self.ck(self.lib.mmh_grad_gather(C.byref(p), self.st()))
+        self._run(self.lib.mmh_grad_gather, (C.byref(p), self.st()), keep=p)
 
     def _bn_bwd(self, dz, dz_f32, relu, dropout, key, x, xl, coef, save, sums=None, k=None, dy=None, yl=None):
         p = L.BnBwd()
-        p.dz, p.dz_f32, p.relu, p.dropout, p.drop_key = _p(dz), 1 if dz_f32 else 0, int(relu), int(dropout), key & 0xFFFFFFFF
+        p.dz, p.dz_f32, p.relu, p.dropout = _p(dz), 1 if dz_f32 else 0, int(relu), int(dropout)
+        patch = self._key(key, p)
         p.x, p.xl, p.coef, p.save = _p(x), clay(xl), _p(coef), _p(save)
         p.sums, p.k, p.dy = _p(sums), _p(k), _p(dy)
         p.yl = clay(yl if yl is not None else xl)
-        return p
+        return p, patch
 
     def bn_bwd_reduce(self, dz, dz_f32, relu, dropout, key, x, xl, coef, save, sums):
-        p = self._bn_bwd(dz, dz_f32, relu, dropout, key, x, xl, coef, save, sums=sums)
-        self.ck(self.lib.mmh_bn_bwd_reduce(C.byref(p), self.st()))
+        p, patch = self._bn_bwd(dz, dz_f32, relu, dropout, key, x, xl, coef, save, sums=sums)
+        self._run(self.lib.mmh_bn_bwd_reduce, (C.byref(p), self.st()), patch, keep=p)
 
     def bn_bwd_apply(self, dz, dz_f32, relu, dropout, key, x, xl, coef, save, k, dy, yl):
-        p = self._bn_bwd(dz, dz_f32, relu, dropout, key, x, xl, coef, save, k=k, dy=dy, yl=yl)
-        self.ck(self.lib.mmh_bn_bwd_apply(C.byref(p), self.st()))
+        p, patch = self._bn_bwd(dz, dz_f32, relu, dropout, key, x, xl, coef, save, k=k, dy=dy, yl=yl)
+        self._run(self.lib.mmh_bn_bwd_apply, (C.byref(p), self.st()), patch, keep=p)
 
     def bn_bwd_finalize(self, sums_global, sums_local, count, k, dgamma, dbeta, Cc):
-        self.ck(self.lib.mmh_bn_bwd_finalize(_p(sums_global), _p(sums_local), float(count), _p(k), _p(dgamma),
-                                             _p(dbeta), Cc, self.st()))
+        self._run(self.lib.mmh_bn_bwd_finalize, (_p(sums_global), _p(sums_local), float(count), _p(k), _p(dgamma),
+                                                 _p(dbeta), Cc, self.st()))
 
     def _gate_bwd(self, dout, c1, x2o, x3o, sl, coef, save, sums=None, k=None, ex2=None, ex3=None, dy1=None,
                   dy2=None, dy3=None, yl=None):
@@ -154,48 +251,55 @@ class Ops:
 
     def gate_bwd_reduce(self, dout, c1, x2o, x3o, sl, coef, save, sums):
         p = self._gate_bwd(dout, c1, x2o, x3o, sl, coef, save, sums=sums)
-        self.ck(self.lib.mmh_gate_bwd_reduce(C.byref(p), self.st()))
+        self._run(self.lib.mmh_gate_bwd_reduce, (C.byref(p), self.st()), keep=p)
 
     def gate_bwd_apply(self, dout, c1, x2o, x3o, sl, coef, save, k, ex2, ex3, dy1, dy2, dy3, yl):
         p = self._gate_bwd(dout, c1, x2o, x3o, sl, coef, save, k=k, ex2=ex2, ex3=ex3, dy1=dy1, dy2=dy2, dy3=dy3, yl=yl)
-        self.ck(self.lib.mmh_gate_bwd_apply(C.byref(p), self.st()))
+        self._run(self.lib.mmh_gate_bwd_apply, (C.byref(p), self.st()), keep=p)
 
     # ------------------------------------------------------------------ losses
     def bce_logits(self, x, target, loss_scale, grad_scale, loss_acc, grad=None):
-        self.ck(self.lib.mmh_bce_logits(_p(x), x.numel(), float(target), loss_scale, grad_scale, _p(loss_acc),
-                                        _p(grad), self.st()))
+        self._run(self.lib.mmh_bce_logits, (_p(x), x.numel(), float(target), loss_scale, grad_scale, _p(loss_acc),
+                                            _p(grad), self.st()), keep=(x, loss_acc, grad))
 
     def l1(self, a, b, loss_scale, grad_scale, loss_acc, grad_acc=None):
-        self.ck(self.lib.mmh_l1_f32(_p(a), _p(b), a.numel(), loss_scale, grad_scale, _p(loss_acc), _p(grad_acc),
-                                    self.st()))
+        self._run(self.lib.mmh_l1_f32, (_p(a), _p(b), a.numel(), loss_scale, grad_scale, _p(loss_acc), _p(grad_acc),
+                                        self.st()), keep=(a, b, loss_acc, grad_acc))
 
     def perc_loss(self, ff, ft, mse, loss_scale, grad_scale, loss_acc, dy=None):
-        self.ck(self.lib.mmh_perc_loss(_p(ff), _p(ft), ff.numel(), 1 if mse else 0, loss_scale, grad_scale,
-                                       _p(loss_acc), _p(dy), self.st()))
+        self._run(self.lib.mmh_perc_loss, (_p(ff), _p(ft), ff.numel(), 1 if mse else 0, loss_scale, grad_scale,
+                                           _p(loss_acc), _p(dy), self.st()), keep=(loss_acc,))
 
     def tanh_bwd(self, dfake, fake, dy, yl: Lay, Cc):
         cl = clay(yl)
-        self.ck(self.lib.mmh_tanh_bwd(_p(dfake), _p(fake), _p(dy), C.byref(cl), Cc, self.st()))
+        self._run(self.lib.mmh_tanh_bwd, (_p(dfake), _p(fake), _p(dy), C.byref(cl), Cc, self.st()), keep=(cl, dfake))
 
     def input_grad_nchw(self, src: GradSource, scale, dst, B, Cc, H, W, accumulate):
         s = src.c()
-        self.ck(self.lib.mmh_input_grad_nchw(C.byref(s), _p(scale), _p(dst), B, Cc, H, W, 1 if accumulate else 0,
-                                             self.st()))
+        self._run(self.lib.mmh_input_grad_nchw, (C.byref(s), _p(scale), _p(dst), B, Cc, H, W, 1 if accumulate else 0,
+                                                 self.st()), keep=(s, dst))
 
     def grid_to_nchw(self, src, sl: Lay, dst, Cc):
         cl = clay(sl)
-        self.ck(self.lib.mmh_grid_to_nchw(_p(src), C.byref(cl), _p(dst), Cc, self.st()))
+        self._run(self.lib.mmh_grid_to_nchw, (_p(src), C.byref(cl), _p(dst), Cc, self.st()), keep=cl)
 
     # ------------------------------------------------------------------ parameters
     def pack_weight(self, src, s_n, s_c, s_t, N, Cc, T, dst, Np, Cp):
-        self.ck(self.lib.mmh_pack_weight(_p(src), s_n, s_c, s_t, N, Cc, T, _p(dst), Np, Cp, self.st()))
+        self._run(self.lib.mmh_pack_weight, (_p(src), s_n, s_c, s_t, N, Cc, T, _p(dst), Np, Cp, self.st()))
 
     def unpack_wgrad(self, src, dst, s_n, s_c, s_t, N, Cc, T, accumulate):
-        self.ck(self.lib.mmh_unpack_wgrad(_p(src), _p(dst), s_n, s_c, s_t, N, Cc, T, 1 if accumulate else 0, self.st()))
+        self._run(self.lib.mmh_unpack_wgrad, (_p(src), _p(dst), s_n, s_c, s_t, N, Cc, T, 1 if accumulate else 0,
+                                              self.st()))
 
-    def adam(self, p, g, m, v, lr, b1, b2, eps, step, grad_scale=1.0):
-        self.ck(self.lib.mmh_adam(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, b1, b2, eps, step, grad_scale, self.st()))
+    def adam(self, p, g, m, v, lr, b1, b2, eps, step, grad_scale=1.0, dyn=None):
+        """dyn: optional callable() -> (lr, step) evaluated again on every replay."""
+        patch = None
+        if dyn is not None:
+            def patch(_step, args, dyn=dyn):
+                args[5], args[9] = dyn()
+        self._run(self.lib.mmh_adam, (_p(p), _p(g), _p(m), _p(v), p.numel(), lr, b1, b2, eps, step, grad_scale,
+                                      self.st()), patch)
 
     def heatmaps(self, uv, H, W, sigma, thresh, out):
         n = uv.numel() // 2
-        self.ck(self.lib.mmh_heatmap_rasterize(_p(uv), n, H, W, float(sigma), float(thresh), _p(out), self.st()))
+        self._run(self.lib.mmh_heatmap_rasterize, (_p(uv), n, H, W, float(sigma), float(thresh), _p(out), self.st()))

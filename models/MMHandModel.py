@@ -106,10 +106,19 @@ class MMHandModel(BaseModel):
 
     # ------------------------------------------------------------------------------------------ data
     def set_input(self, input):
+        """H2D of the six tensors (reference :200-213) straight into static device buffers, so that the recorded
+        launch tapes (fixed pointers) stay valid from step to step."""
         dev = self.device
-        f = lambda k: input[k].to(dev, torch.float32, non_blocking=True).contiguous()
-        self.input_H1, self.input_P1, self.input_D1 = f('H1'), f('P1'), f('D1')
-        self.input_H2, self.input_P2, self.input_D2 = f('H2'), f('P2'), f('D2')
+        names = ('H1', 'P1', 'D1', 'H2', 'P2', 'D2')
+        shapes = tuple(tuple(input[k].shape) for k in names)
+        if getattr(self, '_in_shapes', None) != shapes:
+            self._in = {k: torch.empty(input[k].shape, dtype=torch.float32, device=dev) for k in names}
+            self._in_shapes = shapes
+            self._tapes = None
+        for k in names:
+            self._in[k].copy_(input[k], non_blocking=True)
+        self.input_H1, self.input_P1, self.input_D1 = self._in['H1'], self._in['P1'], self._in['D1']
+        self.input_H2, self.input_P2, self.input_D2 = self._in['H2'], self._in['P2'], self._in['D2']
         if 'H1_path' in input:
             self.image_paths = input['H1_path'][0] + '___' + input['H2_path'][0]
 
@@ -140,13 +149,15 @@ class MMHandModel(BaseModel):
         return optimizer.param_groups[0]['lr']
 
     def _adam(self, eng, optimizer):
+        """Gradient all-reduce (data parallel), fused Adam over the flat parameter buffer, repack of the bf16
+        tensor-core operands. Recordable: lr and the step count are re-read on every tape replay."""
+        ops = eng.ops
+        scale = 1.0
         if self.world is not None and self.world.size > 1:
-            self.world.all_reduce(eng.store.grad)
+            ops.host(lambda: self.world.all_reduce(eng.store.grad))
             scale = 1.0 / self.world.size
-        else:
-            scale = 1.0
-        if not self.overflow:
-            eng.store.adam(self._lr(optimizer), self.opt.beta1, 0.999, 1e-8, grad_scale=scale)
+        eng.store.adam(lambda: self._lr(optimizer), self.opt.beta1, 0.999, 1e-8, grad_scale=scale)
+        eng.repack(force=True)
 
     def backward_G(self):
         """reference :236-261; accumulators: 0 g_PB, 1 g_PP (mean BCE), 2 lambda_A*L1, 3 lambda_B*perceptual."""
@@ -187,41 +198,75 @@ class MMHandModel(BaseModel):
             eng.backward(dl, want_wgrad=True, want_input_grad=False)
         return eng
 
+    def _pool_inputs(self, which=('pp', 'pb')):
+        """ImagePool queries (host RNG, reference :279-289) into static buffers."""
+        for w in which:
+            pool, other = ((self.fake_PP_pool, self.input_H1) if w == 'pp' else (self.fake_PB_pool, self.input_P2))
+            picked = pool.query(torch.cat((self.fake_p2, other), 1).data)
+            name = '_pool_' + w
+            if getattr(self, name, None) is None or getattr(self, name).shape != picked.shape:
+                setattr(self, name, torch.empty_like(picked))
+                self._tapes = None
+            getattr(self, name).copy_(picked)
+
     def backward_D_PB(self):
-        fake_PB = self.fake_PB_pool.query(torch.cat((self.fake_p2, self.input_P2), 1).data)
-        return self.backward_D_basic(self.netD_PB, self.input_H2, self.input_P2, fake_PB.contiguous(), 6, 2)
+        return self.backward_D_basic(self.netD_PB, self.input_H2, self.input_P2, self._pool_pb, 6, 2)
 
     def backward_D_PP(self):
-        fake_PP = self.fake_PP_pool.query(torch.cat((self.fake_p2, self.input_H1), 1).data)
-        return self.backward_D_basic(self.netD_PP, self.input_H2, self.input_H1, fake_PP.contiguous(), 4, 5)
+        return self.backward_D_basic(self.netD_PP, self.input_H2, self.input_H1, self._pool_pp, 4, 5)
 
-    def optimize_parameters(self):
-        self._ops = runtime.get_ops(self.device)
+    def _segment_G(self):
         ops = self._ops
-        if self._acc is None:
-            self._acc = torch.zeros(8, dtype=torch.float32, device=ops.device)
         ops.memset0(self._acc)
         self.forward()
-        if getattr(self, '_dfake', None) is None or self._dfake.shape != self.fake_p2.shape:
-            self._dfake = torch.zeros_like(self.fake_p2)
-        # G
         g_eng = self._g_engine()
         g_eng.store.zero_grad()
         self.backward_G()
         self._adam(g_eng, self.optimizer_G)
-        # D_PP then D_PB (reference order)
-        for _ in range(self.opt.DG_ratio):
-            eng = self._d_engine(self.netD_PP)
+
+    def _segment_D(self, which=('pp', 'pb')):
+        ops = self._ops
+        table = {'pp': (self.netD_PP, self.backward_D_PP, self.optimizer_D_PP, 4),
+                 'pb': (self.netD_PB, self.backward_D_PB, self.optimizer_D_PB, 6)}
+        for w in which:
+            net, bwd, optim, lo = table[w]
+            eng = self._d_engine(net)
             eng.store.zero_grad()
-            self._acc[4:6].zero_()
-            self.backward_D_PP()
-            self._adam(eng, self.optimizer_D_PP)
-        for _ in range(self.opt.DG_ratio):
-            eng = self._d_engine(self.netD_PB)
-            eng.store.zero_grad()
-            self._acc[6:8].zero_()
-            self.backward_D_PB()
-            self._adam(eng, self.optimizer_D_PB)
+            ops.memset0(self._acc[lo:lo + 2])
+            bwd()
+            self._adam(eng, optim)
+
+    def optimize_parameters(self):
+        """reference :310-330. The first call runs eagerly while recording the launch sequence of the generator
+        segment and of the two discriminator segments; later calls replay the tapes (use_tape=False: always eager).
+        The image-pool queries between the segments stay on the host, as in the reference."""
+        self._ops = runtime.get_ops(self.device)
+        ops = self._ops
+        if self._acc is None:
+            self._acc = torch.zeros(8, dtype=torch.float32, device=ops.device)
+        B, C3, H, W = self.input_H1.shape
+        if getattr(self, '_dfake', None) is None or self._dfake.shape != (B, self.opt.output_nc, H, W):
+            self._dfake = torch.zeros(B, self.opt.output_nc, H, W, dtype=torch.float32, device=ops.device)
+            self._tapes = None
+        use_tape = getattr(self, 'use_tape', True) and self.opt.DG_ratio == 1
+        tapes = getattr(self, '_tapes', None)
+        if use_tape and tapes is not None and tapes[0].stream == ops._stream():
+            tapes[0].replay(self._step)
+            self._pool_inputs()
+            tapes[1].replay(self._step)
+        elif use_tape:
+            with ops.record() as tg:
+                self._segment_G()
+            self._pool_inputs()
+            with ops.record() as td:
+                self._segment_D()
+            self._tapes = (tg, td)
+        else:
+            self._segment_G()
+            for w in ('pp', 'pb'):              # reference order: D_PP DG_ratio times, then D_PB DG_ratio times
+                for _ in range(self.opt.DG_ratio):
+                    self._pool_inputs((w,))
+                    self._segment_D((w,))
         self.overflow = False
         self._step += 1
         a, lam = self._acc.clone(), self.opt.lambda_GAN

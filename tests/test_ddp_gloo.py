@@ -1,0 +1,81 @@
+"""Data-parallel path on CPU: world_size 2 over gloo with the host emulation. Two ranks with one sample each
+(synchronised BatchNorm statistics + gradient all-reduce) must take the same optimisation steps as one process
+with both samples (dropout off: the hash masks are indexed by the local sample id)."""
+import os
+import random
+import sys
+import tempfile
+
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _batches(n, B, S):
+    g = torch.Generator().manual_seed(123)
+    r = lambda *s: torch.rand(*s, generator=g)
+    return [dict(H1=r(B, 3, S, S) * 2 - 1, P1=r(B, 21, S, S), D1=r(B, 3, S, S) * 2 - 1, H2=r(B, 3, S, S) * 2 - 1,
+                 P2=r(B, 21, S, S), D2=r(B, 3, S, S) * 2 - 1) for _ in range(n)]
+
+
+def _run(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import hostemu
+    from mmhand_b200 import runtime
+    from oracle.ref_shims import make_opt
+    runtime._TEST_OPS = hostemu.ops(f32=True)
+    if world > 1:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    from models.MMHandModel import MMHandModel
+    torch.manual_seed(5)
+    random.seed(5)
+    torch.set_num_threads(2)
+    opt = make_opt(batchSize=2 // world, fineSize=32, ngf=16, ndf=16, pool_size=0, local_rank='cpu', seed=7,
+                   no_dropout=True, no_dropout_D=True, distributed=(world > 1))
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = MMHandModel(opt)
+    m.master = False
+    errs = []
+    for b in _batches(3, 2, 32):
+        if world > 1:
+            b = {k: v[rank:rank + 1] for k, v in b.items()}
+        m.set_input(b)
+        m.optimize_parameters()
+        errs.append({k: float(v) for k, v in m.get_current_errors().items()})
+    if rank == 0:
+        torch.save({"g": {k: v.detach().clone() for k, v in m.netG.state_dict().items()},
+                    "d": {k: v.detach().clone() for k, v in m.netD_PB.state_dict().items()}, "errs": errs}, out_path)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def test_two_ranks_match_one_process():
+    with tempfile.TemporaryDirectory() as td:
+        single, multi = os.path.join(td, "single.pt"), os.path.join(td, "multi.pt")
+        _run(0, 1, 0, single)
+        from mmhand_b200 import runtime
+        runtime._TEST_OPS = None
+        port = 29500 + (os.getpid() % 500)
+        mp.spawn(_run, args=(2, port, multi), nprocs=2, join=True)
+        a, b = torch.load(single), torch.load(multi)
+        lr = 2e-4
+        for part in ("g", "d"):
+            for k in a[part]:
+                if not a[part][k].is_floating_point():
+                    assert torch.equal(a[part][k], b[part][k]), k
+                    continue
+                d = (a[part][k] - b[part][k]).abs()
+                # identical gradients up to fp32 summation order. Adam normalises the update, so a weight whose
+                # gradient is ~0 (conv weights in front of a BatchNorm are scale-invariant) may move by up to
+                # ~2*lr per step in either run: bound the maximum by that and require the bulk to agree closely.
+                assert d.max().item() <= 2 * 3 * lr + 1e-4 * a[part][k].abs().max().item(), (part, k, d.max().item())
+                assert d.mean().item() <= 0.05 * lr + 1e-3 * a[part][k].abs().mean().item() + 1e-6, (part, k, d.mean().item())
+        # the G-side losses average to the single-process values; rank 0 only sees its own sample, so compare loosely
+        for ea, eb in zip(a["errs"], b["errs"]):
+            assert abs(ea["pair_L1loss"] - eb["pair_L1loss"]) < 0.5
