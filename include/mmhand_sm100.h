@@ -42,6 +42,8 @@ int mmh_is_device_build(void);
  *   out[map(q)][n] = act( bias[n] + sum_{t<T} sum_{c<C} a[q + shift[t]][c] * w[w_slot[t]][n][c] ),  q in [0,M)
  *
  * a : bf16 [a_rows][a_ld], only channels [0,C) of each row are read; rows outside [0,a_rows) read 0.
+ *     C may exceed a_ld: a row then runs on into the following pixels (overlapping-row view), which folds the
+ *     kw taps of a small-channel k x k convolution into the contraction dimension (K = kw * a_ld per kh tap).
  * w : bf16 [w_taps][N][C] (K-major B operand); tap t reads slab w_slot[t].
  * q is decoded on the GEMM grid: img = q / (Hg*Wg), h = (q % (Hg*Wg)) / Wg, x = q % Wg; the row is
  * "valid" iff h < Hv && x < Wv. Valid rows are stored at
@@ -255,6 +257,10 @@ int mmh_grid_to_nchw(const float* src, const MmhLay* sl, float* dst_nchw, int32_
 /* fp32 master weight (any strides: n, c, tap) -> bf16 [T][Np][Cp] zero padded */
 int mmh_pack_weight(const float* src, int64_t s_n, int64_t s_c, int64_t s_t, int32_t N, int32_t C, int32_t T,
                     void* dst, int32_t Np, int32_t Cp, void* stream);
+/* same for the kw-folded operand: dst bf16 [kh][Np][Kw] with dst[t][n][j*Cin_p + c] = src[n][c][t*kw + (reverse ? kw-1-j : j)] */
+int mmh_pack_weight_folded(const float* src, int64_t s_n, int64_t s_c, int64_t s_t, int32_t N, int32_t C, int32_t kh,
+                           int32_t kw, void* dst, int32_t Np, int32_t Cin_p, int32_t Kw, int32_t reverse,
+                           void* stream);
 /* fp32 [T][N][C] packed gradient -> strided fp32 gradient (accumulate != 0: +=) */
 int mmh_unpack_wgrad(const float* src, float* dst, int64_t s_n, int64_t s_c, int64_t s_t, int32_t N, int32_t C,
                      int32_t T, int32_t accumulate, void* stream);

@@ -32,6 +32,19 @@ struct PackF {
   }
 };
 
+struct PackFoldF {
+  const float* src; act_t* dst; int64_t s_n, s_c, s_t; int N, C, kw, Np, Cin_p, Kw, reverse;
+  MMH_HD void operator()(int64_t i) const {
+    const int cc = static_cast<int>(i % Kw);
+    const int n = static_cast<int>((i / Kw) % Np);
+    const int t = static_cast<int>(i / (static_cast<int64_t>(Kw) * Np));
+    const int j = cc / Cin_p, c = cc % Cin_p;
+    float v = 0.f;
+    if (n < N && j < kw && c < C) v = src[n * s_n + c * s_c + (t * kw + (reverse ? kw - 1 - j : j)) * s_t];
+    dst[i] = f2act(v);
+  }
+};
+
 struct UnpackF {
   const float* src; float* dst; int64_t s_n, s_c, s_t; int N, C, accumulate;
   MMH_HD void operator()(int64_t i) const {
@@ -68,6 +81,16 @@ extern "C" int mmh_pack_weight(const float* src, int64_t s_n, int64_t s_c, int64
   f.src = src; f.dst = static_cast<act_t*>(dst); f.s_n = s_n; f.s_c = s_c; f.s_t = s_t;
   f.N = N; f.C = C; f.Np = Np; f.Cp = Cp;
   return launch_map(f, static_cast<int64_t>(T) * Np * Cp, stream);
+}
+
+extern "C" int mmh_pack_weight_folded(const float* src, int64_t s_n, int64_t s_c, int64_t s_t, int32_t N, int32_t C,
+                                      int32_t kh, int32_t kw, void* dst, int32_t Np, int32_t Cin_p, int32_t Kw,
+                                      int32_t reverse, void* stream) {
+  MMH_CHECK(src && dst && N <= Np && C <= Cin_p && kw * Cin_p <= Kw, "bad argument");
+  PackFoldF f;
+  f.src = src; f.dst = static_cast<act_t*>(dst); f.s_n = s_n; f.s_c = s_c; f.s_t = s_t;
+  f.N = N; f.C = C; f.kw = kw; f.Np = Np; f.Cin_p = Cin_p; f.Kw = Kw; f.reverse = reverse;
+  return launch_map(f, static_cast<int64_t>(kh) * Np * Kw, stream);
 }
 
 extern "C" int mmh_unpack_wgrad(const float* src, float* dst, int64_t s_n, int64_t s_c, int64_t s_t, int32_t N,

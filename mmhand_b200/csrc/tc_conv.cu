@@ -234,7 +234,7 @@ extern "C" int mmh_conv_plan_create(const MmhConvDesc* d, MmhConvPlan** out_plan
   MMH_CHECK(d->C >= 16 && (d->C % 16) == 0, "C=%d must be a multiple of 16", d->C);
   MMH_CHECK(d->C == 16 || d->C == 32 || d->C == 48 || (d->C % 64) == 0, "C=%d unsupported", d->C);
   MMH_CHECK(d->N >= 16 && (d->N % 16) == 0, "N=%d must be a multiple of 16", d->N);
-  MMH_CHECK((d->a_ld % 8) == 0 && d->a_ld >= d->C, "a_ld=%d invalid", d->a_ld);
+  MMH_CHECK((d->a_ld % 8) == 0, "a_ld=%d invalid", d->a_ld);
   MMH_CHECK((d->out_ld % 8) == 0, "out_ld=%d must be a multiple of 8", d->out_ld);
   MMH_CHECK(d->M > 0 && d->M < (int64_t(1) << 31) - 256, "M out of range");
   MMH_CHECK((reinterpret_cast<uintptr_t>(d->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->w) & 15) == 0 &&

@@ -90,15 +90,27 @@ class ConvL:
         self.weight, self.transposed, self.bias, self.act, self.out_f32 = weight, transposed, bias, act, out_f32
         self.need_dx = need_dx
         self.T = geom.k * geom.k
-        self.x = x_buf if x_buf is not None else ops.zeros(geom.in_lay.rows, self.Cin_p)
+        # few-channel k x k stems: fold the k column taps into the contraction (128-byte TMA rows instead of 32)
+        self.fold = geom.kind == 's1' and geom.k >= 5 and self.Cin_p <= 48 and x_buf is None
+        if x_buf is not None:
+            self.x = x_buf
+        else:
+            self.x_store = ops.zeros(geom.in_lay.rows + 2 * geom.k, self.Cin_p)    # tail slack for folded views
+            self.x = self.x_store[:geom.in_lay.rows]
         self.raw = raw_buf if raw_buf is not None else ops.zeros(
             geom.out_lay.rows, self.Cout_p, dtype=torch.float32 if out_f32 else None)
-        self.wp = ops.zeros(self.T, self.Cout_p, self.Cin_p)
         self.bias_p = None
         if bias is not None:
             self.bias_p = ops.zeros(self.Cout_p, dtype=torch.float32)
-        self.fwd = convops.fwd_plans(ops.lib, geom, self.x, self.wp, self.raw, self.Cin_p, self.Cout_p,
-                                     bias=self.bias_p, act=act, out_f32=out_f32)
+        if self.fold:
+            self.Kw = convops.fold_width(geom.k, self.Cin_p)
+            self.wp = ops.zeros(geom.k, self.Cout_p, self.Kw)
+            self.fwd = convops.fwd_plans_folded(ops.lib, geom, self.x, self.wp, self.raw, self.Cin_p, self.Cout_p,
+                                                bias=self.bias_p, act=act, out_f32=out_f32)
+        else:
+            self.wp = ops.zeros(self.T, self.Cout_p, self.Cin_p)
+            self.fwd = convops.fwd_plans(ops.lib, geom, self.x, self.wp, self.raw, self.Cin_p, self.Cout_p,
+                                         bias=self.bias_p, act=act, out_f32=out_f32)
         self.bwd_ready = False
 
     # weight strides (n = out channel, c = in channel, t = tap) of the fp32 master tensor
@@ -111,7 +123,11 @@ class ConvL:
     def pack(self, with_dgrad):
         ops = self.eng.ops
         sn, sc, st = self._strides()
-        ops.pack_weight(self.weight, sn, sc, st, self.Cout, self.Cin, self.T, self.wp, self.Cout_p, self.Cin_p)
+        if self.fold:
+            ops.pack_weight_folded(self.weight, sn, sc, st, self.Cout, self.Cin, self.g.k, self.g.k, self.wp,
+                                   self.Cout_p, self.Cin_p, self.Kw)
+        else:
+            ops.pack_weight(self.weight, sn, sc, st, self.Cout, self.Cin, self.T, self.wp, self.Cout_p, self.Cin_p)
         if with_dgrad and self.need_dx and self.bwd_ready:
             ops.pack_weight(self.weight, sc, sn, st, self.Cin, self.Cout, self.T, self.wd, self.Cin_p, self.Cout_p)
         if self.bias is not None:

@@ -287,6 +287,10 @@ class Ops:
     def pack_weight(self, src, s_n, s_c, s_t, N, Cc, T, dst, Np, Cp):
         self._run(self.lib.mmh_pack_weight, (_p(src), s_n, s_c, s_t, N, Cc, T, _p(dst), Np, Cp, self.st()))
 
+    def pack_weight_folded(self, src, s_n, s_c, s_t, N, Cc, kh, kw, dst, Np, Cin_p, Kw, reverse=False):
+        self._run(self.lib.mmh_pack_weight_folded, (_p(src), s_n, s_c, s_t, N, Cc, kh, kw, _p(dst), Np, Cin_p, Kw,
+                                                    1 if reverse else 0, self.st()))
+
     def unpack_wgrad(self, src, dst, s_n, s_c, s_t, N, Cc, T, accumulate):
         self._run(self.lib.mmh_unpack_wgrad, (_p(src), _p(dst), s_n, s_c, s_t, N, Cc, T, 1 if accumulate else 0,
                                               self.st()))

@@ -157,6 +157,7 @@ _SIMPLE_SIGS = {
     "mmh_input_grad_nchw": [C.POINTER(GradSrc), _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "mmh_grid_to_nchw": [_vp, C.POINTER(Lay), _vp, _i32, _vp],
     "mmh_pack_weight": [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _vp],
+    "mmh_pack_weight_folded": [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp],
     "mmh_unpack_wgrad": [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp],
     "mmh_adam": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _f32, _vp],
     "mmh_memset": [_vp, _i32, _i64, _vp],
