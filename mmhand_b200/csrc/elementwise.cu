@@ -1,7 +1,7 @@
 // Bandwidth-bound kernels between the convolutions: input assembly, BatchNorm statistics / apply /
 // backward, ReLU, dropout, reflect / zero halos, the PAT gate and its backward, gradient gathering.
 // Every kernel moves 16-byte bf16 vectors (8 channels) per work item on NHWC pixel grids and is bounded by
-// HBM bandwidth; the algorithmic bytes per element are listed in DESIGN.md section 5.
+// HBM bandwidth; the algorithmic bytes per element are listed in DESIGN.md section 4.3.
 // Dual-mode source: CUDA by default, host loops with -DMMH_HOST_EMU (CPU tests of the index arithmetic).
 #include <math.h>
 
@@ -11,68 +11,52 @@ namespace mmh {
 
 MMH_HD float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-struct PixIter {
-  int b, h, w, g;
-};
-// item -> (b, h, w, g) over an extended window [-lo, H+hi) x [-lo, W+hi)
-// (32-bit arithmetic: the launchers reject item counts >= 2^31; 64-bit divisions would make these kernels
-// ALU-bound instead of HBM-bound)
-MMH_HD PixIter decode_ext(int64_t i64, int groups, int H, int W, int lo, int hi) {
-  PixIter p;
-  const uint32_t He = H + lo + hi, We = W + lo + hi;
-  const uint32_t i = static_cast<uint32_t>(i64);
-  uint32_t pix = i / static_cast<uint32_t>(groups);
-  p.g = static_cast<int>(i - pix * groups);
-  uint32_t t = pix / We;
-  p.w = static_cast<int>(pix - t * We) - lo;
-  pix = t;
-  t = pix / He;
-  p.h = static_cast<int>(pix - t * He) - lo;
-  p.b = static_cast<int>(t);
-  return p;
-}
-// plain pixel index r -> (b, h, w)
-MMH_HD void decode_pix(int64_t r64, int H, int W, int& b, int& h, int& w) {
-  const uint32_t r = static_cast<uint32_t>(r64);
-  uint32_t t = r / static_cast<uint32_t>(W);
-  w = static_cast<int>(r - t * W);
-  const uint32_t u = t / static_cast<uint32_t>(H);
-  h = static_cast<int>(t - u * H);
-  b = static_cast<int>(u);
-}
+struct NoCtx {};
 
 // ------------------------------------------------------------------------------------------------ assemble
 struct AssembleF {
+  struct Ctx { float sc[8], sh[8]; };
   const float* src0; const float* src1; const float* scale; const float* shift;
-  act_t* dst; LayD dl;
-  int C0, C1, lo, hi, reflect, groups;
-  MMH_HD void operator()(int64_t i) const {
-    const PixIter p = decode_ext(i, groups, dl.H, dl.W, lo, hi);
-    const bool inside = p.h >= 0 && p.h < dl.H && p.w >= 0 && p.w < dl.W;
+  act_t* dst; LayD dl; PixDec pd;
+  int C0, C1, reflect;
+  MMH_HD void prep(int g, Ctx& c) const {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = g * 8 + j;
+      const bool on = scale != nullptr && ch < C0 + C1;
+      c.sc[j] = on ? scale[ch] : 1.f;
+      c.sh[j] = on ? shift[ch] : 0.f;
+    }
+  }
+  MMH_HD void operator()(uint32_t pix, int g, const Ctx& c) const {
+    int b, h, w;
+    pix_decode(pd, pix, b, h, w);
+    const bool inside = h >= 0 && h < dl.H && w >= 0 && w < dl.W;
     float v[8];
     zero8(v);
     if (inside || reflect) {
-      const int hs = reflect_idx(p.h, dl.H), ws = reflect_idx(p.w, dl.W);
+      const int hs = reflect_idx(h, dl.H), ws = reflect_idx(w, dl.W);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int c = p.g * 8 + j;
+        const int ch = g * 8 + j;
         float x = 0.f;
-        if (c < C0) x = src0[((static_cast<int64_t>(p.b) * C0 + c) * dl.H + hs) * dl.W + ws];
-        else if (c < C0 + C1) x = src1[((static_cast<int64_t>(p.b) * C1 + (c - C0)) * dl.H + hs) * dl.W + ws];
-        if (scale != nullptr && c < C0 + C1) x = x * scale[c] + shift[c];
-        v[j] = x;
+        if (ch < C0) x = src0[((static_cast<int64_t>(b) * C0 + ch) * dl.H + hs) * dl.W + ws];
+        else if (ch < C0 + C1) x = src1[((static_cast<int64_t>(b) * C1 + (ch - C0)) * dl.H + hs) * dl.W + ws];
+        v[j] = ch < C0 + C1 ? x * c.sc[j] + c.sh[j] : 0.f;
       }
     }
-    st8_bf16(dst + lay_off(dl, p.b, p.h, p.w) + p.g * 8, v);
+    st8_bf16(dst + lay_off(dl, b, h, w) + g * 8, v);
   }
 };
 
 // ------------------------------------------------------------------------------------------------ BN stats
 struct BnStatsF {
+  typedef NoCtx Ctx;
   const act_t* x; int ld;
-  MMH_HD void operator()(int64_t r, int g, float (&acc)[2][8]) const {
+  MMH_HD void prep(int, Ctx&) const {}
+  MMH_HD void operator()(uint32_t r, int g, const Ctx&, float (&acc)[2][8]) const {
     float v[8];
-    ld8_bf16(x + r * ld + g * 8, v);
+    ld8_bf16(x + static_cast<int64_t>(r) * ld + g * 8, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[0][j] += v[j]; acc[1][j] += v[j] * v[j]; }
   }
@@ -107,80 +91,92 @@ struct BnFinalizeF {
 
 // ------------------------------------------------------------------------------------------------ norm + act + pad
 struct NormActF {
+  struct Ctx { float a[8], b[8]; };
   const act_t* src; LayD sl; const float* coef; int relu, dropout; uint32_t key;
-  const float* resid; act_t* dst; LayD dl; int lo, hi, reflect; float* dst_f32; int groups;
-  MMH_HD void operator()(int64_t i) const {
+  const float* resid; act_t* dst; LayD dl; PixDec pd; int reflect; float* dst_f32;
+  MMH_HD void prep(int g, Ctx& c) const {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      c.a[j] = coef != nullptr ? coef[g * 8 + j] : 1.f;
+      c.b[j] = coef != nullptr ? coef[sl.C + g * 8 + j] : 0.f;
+    }
+  }
+  MMH_HD void operator()(uint32_t pix, int g, const Ctx& c) const {
     const int H = sl.H, W = sl.W, C = sl.C;
-    const PixIter p = decode_ext(i, groups, H, W, lo, hi);
-    const bool inside = p.h >= 0 && p.h < H && p.w >= 0 && p.w < W;
+    int b, h, w;
+    pix_decode(pd, pix, b, h, w);
+    const bool inside = h >= 0 && h < H && w >= 0 && w < W;
     float y[8];
     zero8(y);
     if (inside || reflect) {
-      const int hs = reflect_idx(p.h, H), ws = reflect_idx(p.w, W);
-      ld8_bf16(src + lay_off(sl, p.b, hs, ws) + p.g * 8, y);
-      if (coef != nullptr) {
+      const int hs = reflect_idx(h, H), ws = reflect_idx(w, W);
+      ld8_bf16(src + lay_off(sl, b, hs, ws) + g * 8, y);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = coef[p.g * 8 + j] * y[j] + coef[C + p.g * 8 + j];
-      }
+      for (int j = 0; j < 8; ++j) y[j] = c.a[j] * y[j] + c.b[j];
       if (relu) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) y[j] = y[j] > 0.f ? y[j] : 0.f;
       }
       if (dropout) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] *= drop_keep2(key, p.b, p.g * 8 + j, hs, ws, C, H, W);
+        for (int j = 0; j < 8; ++j) y[j] *= drop_keep2(key, b, g * 8 + j, hs, ws, C, H, W);
       }
       if (resid != nullptr) {
         float r[8];
-        ld8_f32(resid + ((static_cast<int64_t>(p.b) * H + hs) * W + ws) * C + p.g * 8, r);
+        ld8_f32(resid + ((static_cast<int64_t>(b) * H + hs) * W + ws) * C + g * 8, r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) y[j] += r[j];
       }
     }
-    if (dst != nullptr) st8_bf16(dst + lay_off(dl, p.b, p.h, p.w) + p.g * 8, y);
-    if (inside && dst_f32 != nullptr)
-      st8_f32(dst_f32 + ((static_cast<int64_t>(p.b) * H + p.h) * W + p.w) * C + p.g * 8, y);
+    if (dst != nullptr) st8_bf16(dst + lay_off(dl, b, h, w) + g * 8, y);
+    if (inside && dst_f32 != nullptr) st8_f32(dst_f32 + ((static_cast<int64_t>(b) * H + h) * W + w) * C + g * 8, y);
   }
 };
 
 // ------------------------------------------------------------------------------------------------ PAT gate
 struct GateFwdF {
+  struct Ctx { float a[8], b[8]; };
   const act_t* c1; const act_t* x2o; const act_t* x3o; LayD sl; const float* coef;
   const float* trunk_in; float* trunk_out;
   act_t* d1; LayD d1l; act_t* d2; LayD d2l; act_t* d3; LayD d3l;
-  int lo, hi, reflect, groups;
-  MMH_HD void operator()(int64_t i) const {
+  PixDec pd; int reflect;
+  MMH_HD void prep(int g, Ctx& c) const {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { c.a[j] = coef[g * 8 + j]; c.b[j] = coef[sl.C + g * 8 + j]; }
+  }
+  MMH_HD void operator()(uint32_t pix, int g, const Ctx& c) const {
     const int H = sl.H, W = sl.W, C = sl.C;
-    const PixIter p = decode_ext(i, groups, H, W, lo, hi);
-    const bool inside = p.h >= 0 && p.h < H && p.w >= 0 && p.w < W;
+    int b, h, w;
+    pix_decode(pd, pix, b, h, w);
+    const bool inside = h >= 0 && h < H && w >= 0 && w < W;
     float out[8], a2[8], a3[8];
     zero8(out); zero8(a2); zero8(a3);
     if (inside || reflect) {
-      const int hs = reflect_idx(p.h, H), ws = reflect_idx(p.w, W);
-      const int64_t so = lay_off(sl, p.b, hs, ws) + p.g * 8;
+      const int hs = reflect_idx(h, H), ws = reflect_idx(w, W);
+      const int64_t so = lay_off(sl, b, hs, ws) + g * 8;
       float v1[8], t[8];
       ld8_bf16(c1 + so, v1);
       ld8_bf16(x2o + so, a2);
       ld8_bf16(x3o + so, a3);
-      ld8_f32(trunk_in + ((static_cast<int64_t>(p.b) * H + hs) * W + ws) * C + p.g * 8, t);
+      ld8_f32(trunk_in + ((static_cast<int64_t>(b) * H + hs) * W + ws) * C + g * 8, t);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float bn = coef[p.g * 8 + j] * v1[j] + coef[C + p.g * 8 + j];
+        const float bn = c.a[j] * v1[j] + c.b[j];
         out[j] = t[j] + bn * sigmoidf_(a2[j]) * sigmoidf_(a3[j]);
       }
     }
-    st8_bf16(d1 + lay_off(d1l, p.b, p.h, p.w) + p.g * 8, out);
+    st8_bf16(d1 + lay_off(d1l, b, h, w) + g * 8, out);
     if (d2 != nullptr) {
-      const int64_t o = lay_off(d2l, p.b, p.h, p.w) + p.g * 8;
+      const int64_t o = lay_off(d2l, b, h, w) + g * 8;
       st8_bf16(d2 + o, a3);
       st8_bf16(d2 + o + C, out);
     }
     if (d3 != nullptr) {
-      const int64_t o = lay_off(d3l, p.b, p.h, p.w) + p.g * 8;
+      const int64_t o = lay_off(d3l, b, h, w) + g * 8;
       st8_bf16(d3 + o, a2);
       st8_bf16(d3 + o + C, out);
     }
-    if (inside) st8_f32(trunk_out + ((static_cast<int64_t>(p.b) * H + p.h) * W + p.w) * C + p.g * 8, out);
+    if (inside) st8_f32(trunk_out + ((static_cast<int64_t>(b) * H + h) * W + w) * C + g * 8, out);
   }
 };
 
@@ -217,86 +213,99 @@ MMH_HD void fold_add8(const GradSrcD& s, int b, int h, int w, int cg, float (&ac
       for (int j = 0; j < 8; ++j) acc[j] += v[j];
     }
 }
-MMH_HD float fold_add1(const GradSrcD& s, int b, int h, int w, int c) {
-  int hs[3], ws[3];
-  const int nh = preimages(h, s.l.H, s.lo, s.hi, s.reflect, hs);
-  const int nw = preimages(w, s.l.W, s.lo, s.hi, s.reflect, ws);
-  float acc = 0.f;
-  for (int a = 0; a < nh; ++a)
-    for (int d = 0; d < nw; ++d) acc += act2f(s.p[lay_off(s.l, b, hs[a], ws[d]) + c]);
-  return acc;
-}
 
 struct GradGatherF {
+  typedef NoCtx Ctx;
   int nsrc; GradSrcD src[4]; const float* trunk; const act_t* mask; LayD ml;
-  void* dst; LayD dl; int dst_f32, H, W, C, groups;
-  MMH_HD void operator()(int64_t i) const {
-    const PixIter p = decode_ext(i, groups, H, W, 0, 0);
+  void* dst; LayD dl; PixDec pd; int dst_f32, H, W, C;
+  MMH_HD void prep(int, Ctx&) const {}
+  MMH_HD void operator()(uint32_t pix, int g, const Ctx&) const {
+    int b, h, w;
+    pix_decode(pd, pix, b, h, w);
     float acc[8];
-    const int64_t plain = ((static_cast<int64_t>(p.b) * H + p.h) * W + p.w) * C + p.g * 8;
+    const int64_t plain = static_cast<int64_t>(pix) * C + g * 8;
     if (trunk != nullptr) ld8_f32(trunk + plain, acc); else zero8(acc);
-    for (int s = 0; s < nsrc; ++s) fold_add8(src[s], p.b, p.h, p.w, p.g * 8, acc);
+    for (int s = 0; s < nsrc; ++s) fold_add8(src[s], b, h, w, g * 8, acc);
     if (mask != nullptr) {
       float m[8];
-      ld8_bf16(mask + lay_off(ml, p.b, p.h, p.w) + p.g * 8, m);
+      ld8_bf16(mask + lay_off(ml, b, h, w) + g * 8, m);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = m[j] > 0.f ? acc[j] : 0.f;
     }
-    const int64_t o = lay_off(dl, p.b, p.h, p.w) + p.g * 8;
+    const int64_t o = lay_off(dl, b, h, w) + g * 8;
     if (dst_f32) st8_f32(static_cast<float*>(dst) + o, acc);
     else st8_bf16(static_cast<act_t*>(dst) + o, acc);
   }
 };
 
 // ------------------------------------------------------------------------------------------------ BN backward
-struct BnBwdCommon {
+// dy = a*(dz_eff - k0 - xhat*k1) with xhat = (x - mean)*rstd is evaluated as  a*dz_eff + bx*x + cc
+struct BnBwdBase {
   const void* dz; int dz_f32, relu, dropout; uint32_t key;
-  const act_t* x; LayD xl; const float* coef; const float* save;
-  // effective upstream gradient (after ReLU / dropout masks) and normalised activation of one vector
-  MMH_HD void load(int b, int h, int w, int g, float (&dze)[8], float (&xhat)[8]) const {
+  const act_t* x; LayD xl; const float* coef; const float* save; PixDec pd;
+  // effective upstream gradient (after the recomputed ReLU / dropout masks) and raw activation of one vector
+  MMH_HD void load(uint32_t pix, int g, const float (&a)[8], const float (&bb)[8], float (&dze)[8], float (&xv)[8]) const {
     const int H = xl.H, W = xl.W, C = xl.C;
-    const int64_t plain = ((static_cast<int64_t>(b) * H + h) * W + w) * C + g * 8;
+    int b, h, w;
+    pix_decode(pd, pix, b, h, w);
+    const int64_t plain = static_cast<int64_t>(pix) * C + g * 8;
     if (dz_f32) ld8_f32(static_cast<const float*>(dz) + plain, dze);
     else ld8_bf16(static_cast<const act_t*>(dz) + plain, dze);
-    float xv[8];
     ld8_bf16(x + lay_off(xl, b, h, w) + g * 8, xv);
+    if (relu) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = g * 8 + j;
-      xhat[j] = (xv[j] - save[c]) * save[C + c];
-      if (relu) {
-        const float y = coef[c] * xv[j] + coef[C + c];
-        if (!(y > 0.f)) dze[j] = 0.f;
-      }
-      if (dropout) dze[j] *= drop_keep2(key, b, c, h, w, C, H, W);
+      for (int j = 0; j < 8; ++j)
+        if (!(a[j] * xv[j] + bb[j] > 0.f)) dze[j] = 0.f;
+    }
+    if (dropout) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dze[j] *= drop_keep2(key, b, g * 8 + j, h, w, C, H, W);
     }
   }
 };
 struct BnBwdReduceF {
-  BnBwdCommon cm;
-  MMH_HD void operator()(int64_t r, int g, float (&acc)[2][8]) const {
-    const int W = cm.xl.W, H = cm.xl.H;
-    int b, h, w;
-    decode_pix(r, H, W, b, h, w);
-    float dze[8], xhat[8];
-    cm.load(b, h, w, g, dze, xhat);
+  struct Ctx { float a[8], b[8], mean[8], rstd[8]; };
+  BnBwdBase cm;
+  MMH_HD void prep(int g, Ctx& c) const {
+    const int C = cm.xl.C;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { acc[0][j] += dze[j]; acc[1][j] += dze[j] * xhat[j]; }
+    for (int j = 0; j < 8; ++j) {
+      c.a[j] = cm.coef[g * 8 + j]; c.b[j] = cm.coef[C + g * 8 + j];
+      c.mean[j] = cm.save[g * 8 + j]; c.rstd[j] = cm.save[C + g * 8 + j];
+    }
+  }
+  MMH_HD void operator()(uint32_t pix, int g, const Ctx& c, float (&acc)[2][8]) const {
+    float dze[8], xv[8];
+    cm.load(pix, g, c.a, c.b, dze, xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[0][j] += dze[j];
+      acc[1][j] += dze[j] * ((xv[j] - c.mean[j]) * c.rstd[j]);
+    }
   }
 };
 struct BnBwdApplyF {
-  BnBwdCommon cm; const float* k; act_t* dy; LayD yl; int groups;
-  MMH_HD void operator()(int64_t i) const {
+  struct Ctx { float a[8], b[8], bx[8], cc[8]; };
+  BnBwdBase cm; const float* k; act_t* dy; LayD yl;
+  MMH_HD void prep(int g, Ctx& c) const {
     const int C = cm.xl.C;
-    const PixIter p = decode_ext(i, groups, cm.xl.H, cm.xl.W, 0, 0);
-    float dze[8], xhat[8], o[8];
-    cm.load(p.b, p.h, p.w, p.g, dze, xhat);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = p.g * 8 + j;
-      o[j] = cm.coef[c] * (dze[j] - k[c] - xhat[j] * k[C + c]);
+      const int ch = g * 8 + j;
+      const float a = cm.coef[ch], mean = cm.save[ch], rstd = cm.save[C + ch];
+      c.a[j] = a; c.b[j] = cm.coef[C + ch];
+      c.bx[j] = -a * k[C + ch] * rstd;
+      c.cc[j] = -a * k[ch] + a * k[C + ch] * rstd * mean;
     }
-    st8_bf16(dy + lay_off(yl, p.b, p.h, p.w) + p.g * 8, o);
+  }
+  MMH_HD void operator()(uint32_t pix, int g, const Ctx& c) const {
+    float dze[8], xv[8], o[8];
+    cm.load(pix, g, c.a, c.b, dze, xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = c.a[j] * dze[j] + c.bx[j] * xv[j] + c.cc[j];
+    int b, h, w;
+    pix_decode(cm.pd, pix, b, h, w);
+    st8_bf16(dy + lay_off(yl, b, h, w) + g * 8, o);
   }
 };
 struct BnBwdFinalizeF {
@@ -310,23 +319,23 @@ struct BnBwdFinalizeF {
 };
 
 // ------------------------------------------------------------------------------------------------ gate backward
-struct GateBwdCommon {
+struct GateBwdBase {
   const float* dout; const act_t* c1; const act_t* x2o; const act_t* x3o; LayD sl;
-  const float* coef; const float* save;
-  MMH_HD void load(int b, int h, int w, int g, float (&d1)[8], float (&xhat)[8], float (&d2)[8], float (&d3)[8]) const {
-    const int H = sl.H, W = sl.W, C = sl.C;
-    float dv[8], v1[8], v2[8], v3[8];
-    ld8_f32(dout + ((static_cast<int64_t>(b) * H + h) * W + w) * C + g * 8, dv);
+  const float* coef; const float* save; PixDec pd;
+  MMH_HD void load(uint32_t pix, int g, const float (&a)[8], const float (&bb)[8], float (&d1)[8], float (&v1)[8],
+                   float (&d2)[8], float (&d3)[8], int& b, int& h, int& w) const {
+    const int C = sl.C;
+    pix_decode(pd, pix, b, h, w);
+    float dv[8], v2[8], v3[8];
+    ld8_f32(dout + static_cast<int64_t>(pix) * C + g * 8, dv);
     const int64_t so = lay_off(sl, b, h, w) + g * 8;
     ld8_bf16(c1 + so, v1);
     ld8_bf16(x2o + so, v2);
     ld8_bf16(x3o + so, v3);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = g * 8 + j;
       const float s2 = sigmoidf_(v2[j]), s3 = sigmoidf_(v3[j]);
-      const float bn = coef[c] * v1[j] + coef[C + c];
-      xhat[j] = (v1[j] - save[c]) * save[C + c];
+      const float bn = a[j] * v1[j] + bb[j];
       d1[j] = dv[j] * s2 * s3;
       d2[j] = dv[j] * bn * s3 * s2 * (1.f - s2);
       d3[j] = dv[j] * bn * s2 * s3 * (1.f - s3);
@@ -334,33 +343,51 @@ struct GateBwdCommon {
   }
 };
 struct GateBwdReduceF {
-  GateBwdCommon cm;
-  MMH_HD void operator()(int64_t r, int g, float (&acc)[2][8]) const {
-    const int W = cm.sl.W, H = cm.sl.H;
-    int b, h, w;
-    decode_pix(r, H, W, b, h, w);
-    float d1[8], xhat[8], d2[8], d3[8];
-    cm.load(b, h, w, g, d1, xhat, d2, d3);
+  struct Ctx { float a[8], b[8], mean[8], rstd[8]; };
+  GateBwdBase cm;
+  MMH_HD void prep(int g, Ctx& c) const {
+    const int C = cm.sl.C;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { acc[0][j] += d1[j]; acc[1][j] += d1[j] * xhat[j]; }
+    for (int j = 0; j < 8; ++j) {
+      c.a[j] = cm.coef[g * 8 + j]; c.b[j] = cm.coef[C + g * 8 + j];
+      c.mean[j] = cm.save[g * 8 + j]; c.rstd[j] = cm.save[C + g * 8 + j];
+    }
+  }
+  MMH_HD void operator()(uint32_t pix, int g, const Ctx& c, float (&acc)[2][8]) const {
+    float d1[8], v1[8], d2[8], d3[8];
+    int b, h, w;
+    cm.load(pix, g, c.a, c.b, d1, v1, d2, d3, b, h, w);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[0][j] += d1[j];
+      acc[1][j] += d1[j] * ((v1[j] - c.mean[j]) * c.rstd[j]);
+    }
   }
 };
 struct GateBwdApplyF {
-  GateBwdCommon cm; const float* k; GradSrcD ex2, ex3;
-  act_t* dy1; act_t* dy2; act_t* dy3; LayD yl; int groups;
-  MMH_HD void operator()(int64_t i) const {
+  struct Ctx { float a[8], b[8], bx[8], cc[8]; };
+  GateBwdBase cm; const float* k; GradSrcD ex2, ex3;
+  act_t* dy1; act_t* dy2; act_t* dy3; LayD yl;
+  MMH_HD void prep(int g, Ctx& c) const {
     const int C = cm.sl.C;
-    const PixIter p = decode_ext(i, groups, cm.sl.H, cm.sl.W, 0, 0);
-    float d1[8], xhat[8], d2[8], d3[8], o[8];
-    cm.load(p.b, p.h, p.w, p.g, d1, xhat, d2, d3);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = p.g * 8 + j;
-      o[j] = cm.coef[c] * (d1[j] - k[c] - xhat[j] * k[C + c]);
+      const int ch = g * 8 + j;
+      const float a = cm.coef[ch], mean = cm.save[ch], rstd = cm.save[C + ch];
+      c.a[j] = a; c.b[j] = cm.coef[C + ch];
+      c.bx[j] = -a * k[C + ch] * rstd;
+      c.cc[j] = -a * k[ch] + a * k[C + ch] * rstd * mean;
     }
-    if (ex2.p != nullptr) fold_add8(ex2, p.b, p.h, p.w, p.g * 8, d2);
-    if (ex3.p != nullptr) fold_add8(ex3, p.b, p.h, p.w, p.g * 8, d3);
-    const int64_t off = lay_off(yl, p.b, p.h, p.w) + p.g * 8;
+  }
+  MMH_HD void operator()(uint32_t pix, int g, const Ctx& c) const {
+    float d1[8], v1[8], d2[8], d3[8], o[8];
+    int b, h, w;
+    cm.load(pix, g, c.a, c.b, d1, v1, d2, d3, b, h, w);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = c.a[j] * d1[j] + c.bx[j] * v1[j] + c.cc[j];
+    if (ex2.p != nullptr) fold_add8(ex2, b, h, w, g * 8, d2);
+    if (ex3.p != nullptr) fold_add8(ex3, b, h, w, g * 8, d3);
+    const int64_t off = lay_off(yl, b, h, w) + g * 8;
     st8_bf16(dy1 + off, o);
     st8_bf16(dy2 + off, d2);
     st8_bf16(dy3 + off, d3);
@@ -374,6 +401,10 @@ using namespace mmh;
 
 #define MMH_REQ_VEC(C) MMH_CHECK((C) > 0 && ((C) % 8) == 0, "channel count %d must be a multiple of 8", (int)(C))
 
+static int64_t ext_pixels(int B, int H, int W, int lo, int hi) {
+  return static_cast<int64_t>(B) * (H + lo + hi) * (W + lo + hi);
+}
+
 extern "C" int mmh_assemble_nchw(const float* src0, int32_t C0, const float* src1, int32_t C1, const float* scale,
                                  const float* shift, void* dst, const MmhLay* dl, int32_t pad_lo, int32_t pad_hi,
                                  int32_t reflect, void* stream) {
@@ -383,10 +414,9 @@ extern "C" int mmh_assemble_nchw(const float* src0, int32_t C0, const float* src
   MMH_CHECK(!reflect || (pad_lo < dl->H && pad_hi < dl->H && pad_lo < dl->W && pad_hi < dl->W), "halo too large");
   AssembleF f;
   f.src0 = src0; f.src1 = src1; f.scale = scale; f.shift = shift;
-  f.dst = static_cast<act_t*>(dst); f.dl = to_layd(*dl);
-  f.C0 = C0; f.C1 = src1 ? C1 : 0; f.lo = pad_lo; f.hi = pad_hi; f.reflect = reflect; f.groups = dl->C / 8;
-  const int64_t n = static_cast<int64_t>(dl->B) * (dl->H + pad_lo + pad_hi) * (dl->W + pad_lo + pad_hi) * f.groups;
-  return launch_map(f, n, stream);
+  f.dst = static_cast<act_t*>(dst); f.dl = to_layd(*dl); f.pd = make_pixdec(dl->H, dl->W, pad_lo, pad_hi);
+  f.C0 = C0; f.C1 = src1 ? C1 : 0; f.reflect = reflect;
+  return launch_pg(f, ext_pixels(dl->B, dl->H, dl->W, pad_lo, pad_hi), dl->C / 8, stream);
 }
 
 extern "C" int mmh_bn_stats(const void* x, int64_t rows, int32_t ld, int32_t C, float* sums, void* stream) {
@@ -415,12 +445,12 @@ extern "C" int mmh_norm_act(const MmhNormAct* p, void* stream) {
   f.src = static_cast<const act_t*>(p->src); f.sl = to_layd(p->sl); f.coef = p->coef;
   f.relu = p->relu; f.dropout = p->dropout; f.key = p->drop_key; f.resid = p->resid;
   f.dst = static_cast<act_t*>(p->dst); f.dl = to_layd(p->dl);
-  f.lo = p->dst ? p->pad_lo : 0; f.hi = p->dst ? p->pad_hi : 0; f.reflect = p->reflect;
-  f.dst_f32 = p->dst_f32; f.groups = p->sl.C / 8;
+  const int lo = p->dst ? p->pad_lo : 0, hi = p->dst ? p->pad_hi : 0;
+  f.reflect = p->reflect; f.dst_f32 = p->dst_f32;
+  f.pd = make_pixdec(f.sl.H, f.sl.W, lo, hi);
   MMH_CHECK(!p->dst || (p->dl.H == p->sl.H && p->dl.W == p->sl.W && p->dl.C == p->sl.C), "src/dst shape mismatch");
-  MMH_CHECK(!f.reflect || (f.lo < f.sl.H && f.hi < f.sl.H && f.lo < f.sl.W && f.hi < f.sl.W), "halo too large");
-  const int64_t n = static_cast<int64_t>(f.sl.B) * (f.sl.H + f.lo + f.hi) * (f.sl.W + f.lo + f.hi) * f.groups;
-  return launch_map(f, n, stream);
+  MMH_CHECK(!f.reflect || (lo < f.sl.H && hi < f.sl.H && lo < f.sl.W && hi < f.sl.W), "halo too large");
+  return launch_pg(f, ext_pixels(f.sl.B, f.sl.H, f.sl.W, lo, hi), p->sl.C / 8, stream);
 }
 
 extern "C" int mmh_gate_fwd(const MmhGateFwd* p, void* stream) {
@@ -433,9 +463,9 @@ extern "C" int mmh_gate_fwd(const MmhGateFwd* p, void* stream) {
   f.d1 = static_cast<act_t*>(p->d1); f.d1l = to_layd(p->d1l);
   f.d2 = static_cast<act_t*>(p->d2); f.d2l = to_layd(p->d2l);
   f.d3 = static_cast<act_t*>(p->d3); f.d3l = to_layd(p->d3l);
-  f.lo = p->pad_lo; f.hi = p->pad_hi; f.reflect = p->reflect; f.groups = p->sl.C / 8;
-  const int64_t n = static_cast<int64_t>(f.sl.B) * (f.sl.H + f.lo + f.hi) * (f.sl.W + f.lo + f.hi) * f.groups;
-  return launch_map(f, n, stream);
+  f.reflect = p->reflect;
+  f.pd = make_pixdec(f.sl.H, f.sl.W, p->pad_lo, p->pad_hi);
+  return launch_pg(f, ext_pixels(f.sl.B, f.sl.H, f.sl.W, p->pad_lo, p->pad_hi), p->sl.C / 8, stream);
 }
 
 extern "C" int mmh_grad_gather(const MmhGradGather* p, void* stream) {
@@ -446,14 +476,16 @@ extern "C" int mmh_grad_gather(const MmhGradGather* p, void* stream) {
   for (int s = 0; s < p->nsrc; ++s) f.src[s] = to_gsd(p->src[s]);
   f.trunk = p->trunk; f.mask = static_cast<const act_t*>(p->mask); f.ml = to_layd(p->ml);
   f.dst = p->dst; f.dl = to_layd(p->dl); f.dst_f32 = p->dst_f32;
-  f.H = p->H; f.W = p->W; f.C = p->C; f.groups = p->C / 8;
-  return launch_map(f, static_cast<int64_t>(p->B) * p->H * p->W * f.groups, stream);
+  f.H = p->H; f.W = p->W; f.C = p->C;
+  f.pd = make_pixdec(p->H, p->W, 0, 0);
+  return launch_pg(f, ext_pixels(p->B, p->H, p->W, 0, 0), p->C / 8, stream);
 }
 
-static BnBwdCommon bn_common(const MmhBnBwd* p) {
-  BnBwdCommon c;
+static BnBwdBase bn_common(const MmhBnBwd* p) {
+  BnBwdBase c;
   c.dz = p->dz; c.dz_f32 = p->dz_f32; c.relu = p->relu; c.dropout = p->dropout; c.key = p->drop_key;
   c.x = static_cast<const act_t*>(p->x); c.xl = to_layd(p->xl); c.coef = p->coef; c.save = p->save;
+  c.pd = make_pixdec(p->xl.H, p->xl.W, 0, 0);
   return c;
 }
 extern "C" int mmh_bn_bwd_reduce(const MmhBnBwd* p, void* stream) {
@@ -461,14 +493,14 @@ extern "C" int mmh_bn_bwd_reduce(const MmhBnBwd* p, void* stream) {
   MMH_REQ_VEC(p->xl.C);
   BnBwdReduceF f;
   f.cm = bn_common(p);
-  return launch_reduce_ch<2>(f, static_cast<int64_t>(p->xl.B) * p->xl.H * p->xl.W, p->xl.C / 8, p->xl.C, p->sums, stream);
+  return launch_reduce_ch<2>(f, ext_pixels(p->xl.B, p->xl.H, p->xl.W, 0, 0), p->xl.C / 8, p->xl.C, p->sums, stream);
 }
 extern "C" int mmh_bn_bwd_apply(const MmhBnBwd* p, void* stream) {
   MMH_CHECK(p && p->dz && p->x && p->coef && p->save && p->k && p->dy, "null argument");
   MMH_REQ_VEC(p->xl.C);
   BnBwdApplyF f;
-  f.cm = bn_common(p); f.k = p->k; f.dy = static_cast<act_t*>(p->dy); f.yl = to_layd(p->yl); f.groups = p->xl.C / 8;
-  return launch_map(f, static_cast<int64_t>(p->xl.B) * p->xl.H * p->xl.W * f.groups, stream);
+  f.cm = bn_common(p); f.k = p->k; f.dy = static_cast<act_t*>(p->dy); f.yl = to_layd(p->yl);
+  return launch_pg(f, ext_pixels(p->xl.B, p->xl.H, p->xl.W, 0, 0), p->xl.C / 8, stream);
 }
 extern "C" int mmh_bn_bwd_finalize(const float* sums_global, const float* sums_local, float count, float* k,
                                    float* dgamma, float* dbeta, int32_t C, void* stream) {
@@ -478,10 +510,11 @@ extern "C" int mmh_bn_bwd_finalize(const float* sums_global, const float* sums_l
   return launch_map(f, C, stream);
 }
 
-static GateBwdCommon gate_common(const MmhGateBwd* p) {
-  GateBwdCommon c;
+static GateBwdBase gate_common(const MmhGateBwd* p) {
+  GateBwdBase c;
   c.dout = p->dout; c.c1 = static_cast<const act_t*>(p->c1); c.x2o = static_cast<const act_t*>(p->x2o);
   c.x3o = static_cast<const act_t*>(p->x3o); c.sl = to_layd(p->sl); c.coef = p->coef; c.save = p->save;
+  c.pd = make_pixdec(p->sl.H, p->sl.W, 0, 0);
   return c;
 }
 extern "C" int mmh_gate_bwd_reduce(const MmhGateBwd* p, void* stream) {
@@ -489,7 +522,7 @@ extern "C" int mmh_gate_bwd_reduce(const MmhGateBwd* p, void* stream) {
   MMH_REQ_VEC(p->sl.C);
   GateBwdReduceF f;
   f.cm = gate_common(p);
-  return launch_reduce_ch<2>(f, static_cast<int64_t>(p->sl.B) * p->sl.H * p->sl.W, p->sl.C / 8, p->sl.C, p->sums, stream);
+  return launch_reduce_ch<2>(f, ext_pixels(p->sl.B, p->sl.H, p->sl.W, 0, 0), p->sl.C / 8, p->sl.C, p->sums, stream);
 }
 extern "C" int mmh_gate_bwd_apply(const MmhGateBwd* p, void* stream) {
   MMH_CHECK(p && p->dout && p->c1 && p->x2o && p->x3o && p->coef && p->save && p->k && p->dy1 && p->dy2 && p->dy3,
@@ -499,6 +532,6 @@ extern "C" int mmh_gate_bwd_apply(const MmhGateBwd* p, void* stream) {
   f.cm = gate_common(p); f.k = p->k;
   f.ex2 = to_gsd(p->ex2); f.ex3 = to_gsd(p->ex3);
   f.dy1 = static_cast<act_t*>(p->dy1); f.dy2 = static_cast<act_t*>(p->dy2); f.dy3 = static_cast<act_t*>(p->dy3);
-  f.yl = to_layd(p->yl); f.groups = p->sl.C / 8;
-  return launch_map(f, static_cast<int64_t>(p->sl.B) * p->sl.H * p->sl.W * f.groups, stream);
+  f.yl = to_layd(p->yl);
+  return launch_pg(f, ext_pixels(p->sl.B, p->sl.H, p->sl.W, 0, 0), p->sl.C / 8, stream);
 }

@@ -1,8 +1,15 @@
-// Launch framework of the bandwidth-bound kernels. Each kernel is a functor whose operator() handles one
-// work item (one pixel x one group of 8 channels = one 16-byte bf16 vector); the same functor body is
-// compiled for the GPU (grid-stride kernels, 16-byte vector accesses, block reductions through shared
-// memory + one atomic per block and channel) and -- with -DMMH_HOST_EMU, for CPU tests of the index
-// arithmetic only -- as plain loops.
+// Launch framework of the bandwidth-bound kernels. Each kernel is a functor; the same functor body is compiled
+// for the GPU and -- with -DMMH_HOST_EMU, for CPU tests of the index arithmetic only -- as plain loops.
+//
+//   launch_map            one item per call, grid-stride
+//   launch_pg             "pixel x channel-group": a thread keeps its group of 8 channels for its whole life, so the
+//                         per-channel parameters (BN coefficients, means, ...) are loaded into registers once
+//                         (F::Ctx / prep) and every item is two or three 16-byte vector accesses plus arithmetic
+//   launch_reduce_ch      same decomposition for per-channel reductions: registers -> shared memory ->
+//                         one atomic per (block, channel)
+//   launch_reduce_scalar  warp-shuffle + shared-memory reduction to one atomic per block
+//
+// Grids are sized in multiples of the SM count.
 #pragma once
 #include <stdint.h>
 
@@ -43,6 +50,49 @@ MMH_HD int reflect_idx(int i, int n) {
   if (i < 0) i = -i;
   if (i >= n) i = 2 * (n - 1) - i;
   return i;
+}
+
+// division by a launch-time constant (n < 2^31): q = umulhi(n, m) >> s
+struct FastDiv {
+  uint32_t d, m, s;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  if (d <= 1) { f.m = 0; f.s = 0; return f; }
+  uint32_t lg = 0;
+  while ((1u << lg) < d) ++lg;               // ceil(log2 d)
+  const uint32_t p = 31 + lg;
+  f.m = static_cast<uint32_t>(((1ull << p) + d - 1) / d);
+  f.s = p - 32;
+  return f;
+}
+MMH_HD uint32_t fdiv(uint32_t n, const FastDiv& f) {
+#if defined(__CUDA_ARCH__)
+  return f.d <= 1 ? n : (__umulhi(n, f.m) >> f.s);
+#else
+  return f.d <= 1 ? n : n / f.d;
+#endif
+}
+
+// pixel index over the window [-lo, H+hi) x [-lo, W+hi) of B images -> (b, h, w)
+struct PixDec {
+  FastDiv we, he;
+  int lo;
+};
+inline PixDec make_pixdec(int H, int W, int lo, int hi) {
+  PixDec p;
+  p.we = make_fastdiv(W + lo + hi);
+  p.he = make_fastdiv(H + lo + hi);
+  p.lo = lo;
+  return p;
+}
+MMH_HD void pix_decode(const PixDec& d, uint32_t pix, int& b, int& h, int& w) {
+  const uint32_t t = fdiv(pix, d.we);
+  w = static_cast<int>(pix - t * d.we.d) - d.lo;
+  const uint32_t u = fdiv(t, d.he);
+  h = static_cast<int>(t - u * d.he.d) - d.lo;
+  b = static_cast<int>(u);
 }
 
 // dropout keep bit of logical NCHW element (b, c, h, w): the same hash as oracle/patn_ref.py::dropout_mask
@@ -96,17 +146,36 @@ int launch_map(const F& f, int64_t n, void*) {
   for (int64_t i = 0; i < n; ++i) f(i);
   return 0;
 }
-// per-channel reduction: item (row r, group g) adds NV*8 values into out[v*C + g*8 + j]
+template <class F>
+int launch_pg(const F& f, int64_t n_pix, int groups, void*) {
+  MMH_CHECK(n_pix < (int64_t(1) << 31), "too many pixels for one launch");
+  for (int g = 0; g < groups; ++g) {
+    typename F::Ctx c;
+    f.prep(g, c);
+    for (uint32_t pix = 0; pix < static_cast<uint32_t>(n_pix); ++pix) f(pix, g, c);
+  }
+  return 0;
+}
+// per-channel reduction: item (pixel, group g) adds NV*8 values into out[v*C + g*8 + j]
 template <int NV, class F>
-int launch_reduce_ch(const F& f, int64_t rows, int groups, int C, float* out, void*) {
-  for (int64_t r = 0; r < rows; ++r)
-    for (int g = 0; g < groups; ++g) {
-      float acc[NV][8];
-      for (int v = 0; v < NV; ++v) zero8(acc[v]);
-      f(r, g, acc);
+int launch_reduce_ch(const F& f, int64_t n_pix, int groups, int C, float* out, void*) {
+  MMH_CHECK(n_pix < (int64_t(1) << 31), "too many pixels for one launch");
+  for (int g = 0; g < groups; ++g) {
+    typename F::Ctx c;
+    f.prep(g, c);
+    double acc[NV][8];
+    for (int v = 0; v < NV; ++v)
+      for (int j = 0; j < 8; ++j) acc[v][j] = 0.0;
+    for (uint32_t pix = 0; pix < static_cast<uint32_t>(n_pix); ++pix) {
+      float a[NV][8];
+      for (int v = 0; v < NV; ++v) zero8(a[v]);
+      f(pix, g, c, a);
       for (int v = 0; v < NV; ++v)
-        for (int j = 0; j < 8; ++j) out[v * C + g * 8 + j] += acc[v][j];
+        for (int j = 0; j < 8; ++j) acc[v][j] += a[v][j];
     }
+    for (int v = 0; v < NV; ++v)
+      for (int j = 0; j < 8; ++j) out[v * C + g * 8 + j] += static_cast<float>(acc[v][j]);
+  }
   return 0;
 }
 // scalar reduction: item i returns a float, sum added to *out
@@ -137,46 +206,75 @@ int launch_map(const F& f, int64_t n, void* stream) {
   return 0;
 }
 
-template <int NV, class F>
-__global__ void __launch_bounds__(256) reduce_ch_kernel(const F f, const int64_t rows, const int groups, const int C,
-                                                        float* __restrict__ out) {
-  extern __shared__ float red[];   // [rpb][groups][NV*8]
-  const int rpb = blockDim.x / groups;
+// threads per block: the largest multiple of `groups` <= 256 (a thread never changes its channel group)
+inline int pg_threads(int groups) { return (256 / groups) * groups; }
+
+template <class F>
+__global__ void __launch_bounds__(256) pg_kernel(const F f, const uint32_t n_pix, const int groups) {
+  const uint32_t ppb = blockDim.x / groups;                  // pixels per block and sweep
   const int g = threadIdx.x % groups;
-  const int lr = threadIdx.x / groups;
+  uint32_t pix = blockIdx.x * ppb + threadIdx.x / groups;
+  const uint32_t stride = gridDim.x * ppb;
+  typename F::Ctx c;
+  f.prep(g, c);
+  for (; pix < n_pix; pix += stride) f(pix, g, c);
+}
+template <class F>
+int launch_pg(const F& f, int64_t n_pix, int groups, void* stream) {
+  if (n_pix <= 0) return 0;
+  MMH_CHECK(groups >= 1 && groups <= 256, "channel groups=%d unsupported", groups);
+  MMH_CHECK(n_pix < (int64_t(1) << 31), "too many pixels for one launch");
+  const int threads = pg_threads(groups);
+  const int ppb = threads / groups;
+  const int64_t want = (n_pix + ppb - 1) / ppb;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+  const int blocks = static_cast<int>(want < cap ? want : cap);
+  pg_kernel<F><<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(f, static_cast<uint32_t>(n_pix), groups);
+  MMH_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int NV, class F>
+__global__ void __launch_bounds__(256) reduce_ch_kernel(const F f, const uint32_t n_pix, const int groups, const int C,
+                                                        float* __restrict__ out) {
+  extern __shared__ float red[];   // [ppb][groups][NV*8]
+  const uint32_t ppb = blockDim.x / groups;
+  const int g = threadIdx.x % groups;
+  const uint32_t lr = threadIdx.x / groups;
   float acc[NV][8];
 #pragma unroll
   for (int v = 0; v < NV; ++v) zero8(acc[v]);
-  if (lr < rpb) {
-    for (int64_t r = static_cast<int64_t>(blockIdx.x) * rpb + lr; r < rows; r += static_cast<int64_t>(gridDim.x) * rpb)
-      f(r, g, acc);
-  }
+  typename F::Ctx c;
+  f.prep(g, c);
+  for (uint32_t pix = blockIdx.x * ppb + lr; pix < n_pix; pix += gridDim.x * ppb) f(pix, g, c, acc);
   float* mine = red + (static_cast<size_t>(lr) * groups + g) * (NV * 8);
 #pragma unroll
   for (int v = 0; v < NV; ++v)
 #pragma unroll
     for (int j = 0; j < 8; ++j) mine[v * 8 + j] = acc[v][j];
   __syncthreads();
-  // column sums over the rpb row-lanes: thread t handles (g, v, j) combos round-robin
+  // column sums over the ppb pixel lanes: thread t handles (g, v, j) combos round-robin
   const int total = groups * NV * 8;
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
     const int gg = idx / (NV * 8), vj = idx % (NV * 8);
     float s = 0.f;
-    for (int l = 0; l < rpb; ++l) s += red[(static_cast<size_t>(l) * groups + gg) * (NV * 8) + vj];
+    for (uint32_t l = 0; l < ppb; ++l) s += red[(static_cast<size_t>(l) * groups + gg) * (NV * 8) + vj];
     atomicAdd(out + (vj / 8) * C + gg * 8 + (vj % 8), s);
   }
 }
 template <int NV, class F>
-int launch_reduce_ch(const F& f, int64_t rows, int groups, int C, float* out, void* stream) {
-  if (rows <= 0) return 0;
+int launch_reduce_ch(const F& f, int64_t n_pix, int groups, int C, float* out, void* stream) {
+  if (n_pix <= 0) return 0;
   MMH_CHECK(groups >= 1 && groups <= 256, "channel groups=%d unsupported", groups);
-  const int rpb = 256 / groups;
-  const int threads = rpb * groups;
+  MMH_CHECK(n_pix < (int64_t(1) << 31), "too many pixels for one launch");
+  const int threads = pg_threads(groups);
+  const int ppb = threads / groups;
   const size_t smem = static_cast<size_t>(threads) * NV * 8 * sizeof(float);
-  const int64_t want = (rows + rpb * 8 - 1) / (rpb * 8);
+  const int64_t want = (n_pix + ppb * 8 - 1) / (ppb * 8);
   const int64_t cap = static_cast<int64_t>(num_sms()) * 4;
   const int blocks = static_cast<int>(want < cap ? (want < 1 ? 1 : want) : cap);
-  reduce_ch_kernel<NV, F><<<blocks, threads, smem, static_cast<cudaStream_t>(stream)>>>(f, rows, groups, C, out);
+  reduce_ch_kernel<NV, F><<<blocks, threads, smem, static_cast<cudaStream_t>(stream)>>>(
+      f, static_cast<uint32_t>(n_pix), groups, C, out);
   MMH_CUDA(cudaGetLastError());
   return 0;
 }

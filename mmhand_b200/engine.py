@@ -153,7 +153,7 @@ class ConvL:
 
     def run_fwd(self):
         for p in self.fwd:
-            self.eng.ops.run_conv(p)
+            self.eng.ops.run_conv(p, (self.name, "fwd"))
 
     def run_bwd(self, want_wgrad=True, want_dx=True):
         """Consumes self.dy. Weight gradient accumulates into weight.grad; data gradient lands in self.dx."""
@@ -161,7 +161,7 @@ class ConvL:
         if want_wgrad and self.has_wgrad:
             ops.memset0(self.dw)
             for p in self.wgrad:
-                ops.run_wgrad(p)
+                ops.run_wgrad(p, (self.name, "wgrad"))
             sn, sc, stt = self._strides()
             ops.unpack_wgrad(self.dw, self.weight.grad, sn, sc, stt, self.Cout, self.Cin, self.T, True)
             if self.bias is not None:
@@ -170,7 +170,7 @@ class ConvL:
                 ops.unpack_wgrad(self.dbias, self.bias.grad, 1, 0, 0, self.Cout, 1, 1, True)
         if want_dx and self.need_dx:
             for p in self.dgrad:
-                ops.run_conv(p)
+                ops.run_conv(p, (self.name, "dgrad"))
 
     def dx_source(self):
         g = self.g

@@ -155,15 +155,15 @@ class Ops:
         return None
 
     # ------------------------------------------------------------------ convolutions
-    def run_conv(self, plan):
+    def run_conv(self, plan, tag=None):
         if self.conv_hook is not None and self.tape is None:
-            self.conv_hook("conv", plan, lambda: self._run(self.lib.mmh_conv_run, (plan.handle, self.st())))
+            self.conv_hook("conv", tag, plan, lambda: self._run(self.lib.mmh_conv_run, (plan.handle, self.st())))
         else:
             self._run(self.lib.mmh_conv_run, (plan.handle, self.st()), keep=plan)
 
-    def run_wgrad(self, plan):
+    def run_wgrad(self, plan, tag=None):
         if self.conv_hook is not None and self.tape is None:
-            self.conv_hook("wgrad", plan, lambda: self._run(self.lib.mmh_wgrad_run, (plan.handle, self.st())))
+            self.conv_hook("wgrad", tag, plan, lambda: self._run(self.lib.mmh_wgrad_run, (plan.handle, self.st())))
         else:
             self._run(self.lib.mmh_wgrad_run, (plan.handle, self.st()), keep=plan)
 
