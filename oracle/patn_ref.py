@@ -86,21 +86,40 @@ def _rpad(x, p):
     return F.pad(x, (p, p, p, p), mode="reflect")
 
 
+# Optional storage-rounding hook (tests only): when set to e.g. ``lambda t: t.bfloat16().float()`` the oracle rounds
+# conv operands (activations, weights) and raw conv outputs exactly where the CUDA path stores bf16,
+# keeping fp32 accumulation, statistics and residual trunks. None = the reference's plain fp32 arithmetic.
+QUANT = None
+
+
+def _q(t):
+    return t if QUANT is None else QUANT(t)
+
+
+def _conv(x, w, bias=None, stride=1, padding=0, q_out=True):
+    y = F.conv2d(_q(x), _q(w), bias, stride=stride, padding=padding)
+    return _q(y) if q_out else y
+
+
+def _convT(x, w):
+    return _q(F.conv_transpose2d(_q(x), _q(w), stride=2, padding=1, output_padding=1))
+
+
 def _down_stream(sd, p, x, train):
     """pad3-conv7-BN-ReLU, 2 x [conv3 s2 p1 - BN - ReLU]  (Generator.py:158-223, Discriminator.py:79-99)."""
-    x = F.relu(_bn(sd, p + ".2", F.conv2d(_rpad(x, 3), sd[p + ".1.weight"]), train))
-    x = F.relu(_bn(sd, p + ".5", F.conv2d(x, sd[p + ".4.weight"], stride=2, padding=1), train))
-    x = F.relu(_bn(sd, p + ".8", F.conv2d(x, sd[p + ".7.weight"], stride=2, padding=1), train))
+    x = F.relu(_bn(sd, p + ".2", _conv(_rpad(x, 3), sd[p + ".1.weight"]), train))
+    x = F.relu(_bn(sd, p + ".5", _conv(x, sd[p + ".4.weight"], stride=2, padding=1), train))
+    x = F.relu(_bn(sd, p + ".8", _conv(x, sd[p + ".7.weight"], stride=2, padding=1), train))
     return x
 
 
 def _conv_block(sd, p, x, train, use_dropout, drop, final_bn):
     """pad,conv,BN,ReLU,[drop],pad,conv,[BN]  (Generator.py:40-113, Discriminator.py:14-51)."""
     j = 6 if use_dropout else 5
-    h = F.relu(_bn(sd, p + ".2", F.conv2d(_rpad(x, 1), sd[p + ".1.weight"]), train))
+    h = F.relu(_bn(sd, p + ".2", _conv(_rpad(x, 1), sd[p + ".1.weight"]), train))
     if use_dropout:
         h = drop.apply(h) if train else h
-    h = F.conv2d(_rpad(h, 1), sd[p + ".%d.weight" % j])
+    h = _conv(_rpad(h, 1), sd[p + ".%d.weight" % j])
     if final_bn:
         h = _bn(sd, p + ".%d" % (j + 1), h, train)
     return h
@@ -126,11 +145,11 @@ def generator_forward(sd, inputs, train=False, use_dropout=True, n_blocks=9, dro
         if taps is not None:
             taps["att%d" % i] = out
     u = "model.stream1_up"
-    h = F.conv_transpose2d(x1, sd[u + ".0.weight"], stride=2, padding=1, output_padding=1)
+    h = _convT(x1, sd[u + ".0.weight"])
     h = F.relu(_bn(sd, u + ".1", h, train))
-    h = F.conv_transpose2d(h, sd[u + ".3.weight"], stride=2, padding=1, output_padding=1)
+    h = _convT(h, sd[u + ".3.weight"])
     h = F.relu(_bn(sd, u + ".4", h, train))
-    h = F.conv2d(_rpad(h, 3), sd[u + ".7.weight"], sd[u + ".7.bias"])
+    h = _conv(_rpad(h, 3), sd[u + ".7.weight"], sd[u + ".7.bias"], q_out=False)
     return torch.tanh(h)
 
 
