@@ -1,0 +1,8 @@
+// Internal: the two generations of the shifted-row convolution kernel behind mmh_conv_plan_*.
+#pragma once
+#include "../../include/mmhand_sm100.h"
+
+struct MmhConv2;   // tc_conv2.cu: activation windows in shared memory, optional cta_group::2 pairs
+int mmh_conv2_create(const MmhConvDesc* d, MmhConv2** out_plan);
+void mmh_conv2_destroy(MmhConv2* plan);
+int mmh_conv2_run(const MmhConv2* plan, void* stream);

@@ -17,11 +17,13 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
 
 #include "../../include/mmhand_sm100.h"
+#include "conv_plan.h"
 #include "host_common.h"
 #include "ptx.cuh"
 #include "tmap.h"
@@ -223,6 +225,8 @@ struct MmhConvPlan {
   mmh::ConvKParams kp;
   int grid;
   size_t smem;
+  MmhConv2* v2 = nullptr;   // generation-2 plan (default); MMH_CONV_IMPL=1 selects the first-generation kernel
+  ~MmhConvPlan() { if (v2) mmh_conv2_destroy(v2); }
 };
 
 using namespace mmh;
@@ -241,6 +245,14 @@ extern "C" int mmh_conv_plan_create(const MmhConvDesc* d, MmhConvPlan** out_plan
                 (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
             "operand pointers must be 16-byte aligned");
   auto* plan = new MmhConvPlan();
+  {
+    const char* impl = getenv("MMH_CONV_IMPL");
+    if (impl == nullptr || atoi(impl) != 1) {
+      if (mmh_conv2_create(d, &plan->v2)) { delete plan; return 1; }
+      *out_plan = plan;
+      return 0;
+    }
+  }
   ConvKParams& k = plan->kp;
   memset(&k, 0, sizeof(k));
   k.T = d->T;
@@ -314,6 +326,7 @@ extern "C" int mmh_conv_plan_destroy(MmhConvPlan* plan) {
 
 extern "C" int mmh_conv_run(const MmhConvPlan* plan, void* stream) {
   MMH_CHECK(plan, "null plan");
+  if (plan->v2) return mmh_conv2_run(plan->v2, stream);
   conv_sgemm_kernel<<<plan->grid, kThreads, plan->smem, static_cast<cudaStream_t>(stream)>>>(plan->tmA, plan->tmW,
                                                                                            plan->kp);
   MMH_CUDA(cudaGetLastError());

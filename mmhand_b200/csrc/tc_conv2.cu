@@ -1,0 +1,474 @@
+// Shifted-row implicit-GEMM convolution on tcgen05, generation 2: activation *windows* in shared memory.
+//
+//   out[map(q)][n] = act(bias[n] + sum_t sum_c a[q + shift[t]][c] * w[t][n][c])
+//
+// The taps of a convolution read the same activation rows at different row offsets. Taps whose shifts lie
+// close together (the 9 taps of a 3x3 on a 64-wide grid, the 7 column taps of one kernel row of a 7x7) form
+// a *group*: per (tile, group, 64-channel chunk) ONE window of 128 + span rows is brought in by TMA and every
+// tap of the group multiplies straight out of it -- its UMMA descriptor simply starts `rel` rows into the
+// window (tcgen05 descriptors are plain address arithmetic on the swizzled layout; the XOR pattern is a
+// function of the absolute shared-memory address, so any 16-byte-aligned row start is legal; verified by
+// tools/exp/desc_shift*.cu). The weight tiles stream through a second ring. L2 -> SM traffic per
+// 128 x 256 x 64 x 9-tap step drops from 432 KB to 321 KB; with NCTA = 2 (cta_group::2 pairs, each CTA
+// loading its own 128-row window and half of every weight tile) to 177 KB, which lifts the kernel off the
+// L2 bandwidth limit the first generation sat on (profiles/r01_conv_v1_ncu.txt).
+//
+// Warp roles per CTA (192 threads): warp 0 TMA producer (lane 0), warp 1 MMA issuer (lane 0 of the pair's
+// leader CTA) + TMEM allocation, warps 2..5 epilogue (TMEM -> registers -> bias/activation -> global).
+// Two accumulator stages of 256 TMEM columns: the epilogue of tile i overlaps the main loop of tile i+1.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/mmhand_sm100.h"
+#include "conv_plan.h"
+#include "host_common.h"
+#include "ptx.cuh"
+#include "tmap.h"
+
+namespace mmh {
+
+constexpr int kC2Threads = 192;
+constexpr int kC2MaxGroups = 16;
+constexpr int kC2MaxA = 4;
+constexpr int kC2MaxB = 8;
+constexpr uint32_t kC2TmemCols = 512;
+constexpr uint32_t kC2AccStride = 256;
+
+struct Conv2Params {
+  int32_t n_groups, cpt, KC, ksteps;
+  int32_t N, BN, tiles_n, tiles_m, M;
+  int32_t Hg, Wg, Hv, Wv;
+  int32_t out_f32, out_ld, out_wg, out_sh, out_sw, out_h0, out_w0, zero_invalid, act, n_store;
+  int64_t out_img_rows;
+  uint32_t row_bytes, swz, sbo;
+  uint32_t a_box_rows, a_boxes, a_box_bytes, a_slot_bytes, nA;
+  uint32_t b_rows, b_tile_bytes, b_tile_stride, b_batch, b_slot_bytes, nB;
+  uint32_t b_ring_off, bar_off;
+  void* out;
+  const float* bias;
+  int32_t g_first[kC2MaxGroups + 1];
+  int32_t g_min[kC2MaxGroups];
+  int32_t rel[MMH_MAX_TAPS];      // row offset of the tap inside its group's window
+  int32_t w_slot[MMH_MAX_TAPS];
+};
+
+// ---------------------------------------------------------------- pair (cta_group::2) helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion is signalled on an mbarrier that may live in the peer CTA of the pair.
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int32_t c0,
+                                                 int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int NCTA>
+__global__ void __launch_bounds__(kC2Threads, 1)
+conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+             const __grid_constant__ Conv2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + p.b_ring_off;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.bar_off);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = bars + kC2MaxA;
+  uint64_t* fullB = bars + 2 * kC2MaxA;
+  uint64_t* emptyB = bars + 2 * kC2MaxA + kC2MaxB;
+  uint64_t* tmem_full = bars + 2 * kC2MaxA + 2 * kC2MaxB;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta = NCTA == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    for (uint32_t s = 0; s < p.nA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+    for (uint32_t s = 0; s < p.nB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4 * NCTA); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    if (NCTA == 2) { tmem_alloc2(tmem_slot, kC2TmemCols); tmem_relinquish2(); }
+    else { tmem_alloc(tmem_slot, kC2TmemCols); tmem_relinquish(); }
+  }
+  tc_fence_before();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_tiles = p.tiles_m * p.tiles_n;
+  const int first_tile = blockIdx.x / NCTA;
+  const int tile_step = gridDim.x / NCTA;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: windows into the A ring, weight tiles into the B ring, in consumption order
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      for (int tile = first_tile; tile < n_tiles; tile += tile_step) {
+        const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+        const int m0 = (tm * NCTA + static_cast<int>(cta)) * 128;
+        const int n0 = tn * p.BN + static_cast<int>(cta * p.b_rows);
+        for (int g = 0; g < p.n_groups; ++g) {
+          const int t_begin = p.g_first[g], t_end = p.g_first[g + 1];
+          const int row0 = m0 + p.g_min[g];
+          for (int kc = 0; kc < p.cpt; ++kc) {
+            const int ch = kc * p.KC;
+            mbar_wait(&emptyA[sa], pa ^ 1);
+            uint8_t* dst = a_ring + static_cast<size_t>(sa) * p.a_slot_bytes;
+            if (NCTA == 2) {
+              const uint32_t bar = mapa_shared(smem_u32(&fullA[sa]), 0);
+              if (leader) mbar_expect_tx(&fullA[sa], 2 * p.a_boxes * p.a_box_bytes);
+              for (uint32_t b = 0; b < p.a_boxes; ++b)
+                tma_load_2d_pair(&tmA, bar, dst + b * p.a_box_bytes, ch, row0 + static_cast<int>(b * p.a_box_rows));
+            } else {
+              mbar_expect_tx(&fullA[sa], p.a_boxes * p.a_box_bytes);
+              for (uint32_t b = 0; b < p.a_boxes; ++b)
+                tma_load_2d(&tmA, &fullA[sa], dst + b * p.a_box_bytes, ch, row0 + static_cast<int>(b * p.a_box_rows));
+            }
+            if (++sa == p.nA) { sa = 0; pa ^= 1; }
+            for (int t0 = t_begin; t0 < t_end; t0 += p.b_batch) {
+              const int nb = min(static_cast<int>(p.b_batch), t_end - t0);
+              mbar_wait(&emptyB[sb], pb ^ 1);
+              uint8_t* bd = b_ring + static_cast<size_t>(sb) * p.b_slot_bytes;
+              if (NCTA == 2) {
+                const uint32_t bar = mapa_shared(smem_u32(&fullB[sb]), 0);
+                if (leader) mbar_expect_tx(&fullB[sb], 2 * nb * p.b_tile_bytes);
+                for (int j = 0; j < nb; ++j)
+                  tma_load_2d_pair(&tmW, bar, bd + j * p.b_tile_stride, ch, p.w_slot[t0 + j] * p.N + n0);
+              } else {
+                mbar_expect_tx(&fullB[sb], nb * p.b_tile_bytes);
+                for (int j = 0; j < nb; ++j)
+                  tma_load_2d(&tmW, &fullB[sb], bd + j * p.b_tile_stride, ch, p.w_slot[t0 + j] * p.N + n0);
+              }
+              if (++sb == p.nB) { sb = 0; pb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ===== MMA issuer
+      const uint32_t idesc = make_idesc_bf16(128 * NCTA, p.BN, 0, 0);
+      const uint64_t desc_hi = make_smem_desc(0, 16, p.sbo, p.swz);
+      const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_ring);
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, acc_phase = 0;
+      for (int tile = first_tile; tile < n_tiles; tile += tile_step) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kC2AccStride;
+        uint32_t accum = 0;
+        for (int g = 0; g < p.n_groups; ++g) {
+          const int t_begin = p.g_first[g], t_end = p.g_first[g + 1];
+          for (int kc = 0; kc < p.cpt; ++kc) {
+            mbar_wait(&fullA[sa], pa);
+            tc_fence_after();
+            const uint32_t wa = a_base + sa * p.a_slot_bytes;
+            for (int t0 = t_begin; t0 < t_end; t0 += p.b_batch) {
+              const int nb = min(static_cast<int>(p.b_batch), t_end - t0);
+              mbar_wait(&fullB[sb], pb);
+              tc_fence_after();
+              const uint32_t wb = b_base + sb * p.b_slot_bytes;
+              for (int j = 0; j < nb; ++j) {
+                const uint32_t ta = wa + static_cast<uint32_t>(p.rel[t0 + j]) * p.row_bytes;
+                const uint32_t tb = wb + j * p.b_tile_stride;
+                for (int k = 0; k < p.ksteps; ++k) {
+                  const uint64_t ad = desc_hi | static_cast<uint64_t>(((ta + k * 32) >> 4) & 0x3FFF);
+                  const uint64_t bd = desc_hi | static_cast<uint64_t>(((tb + k * 32) >> 4) & 0x3FFF);
+                  if (NCTA == 2) umma_bf16_pair(d_tmem, ad, bd, idesc, accum);
+                  else umma_bf16(d_tmem, ad, bd, idesc, accum);
+                  accum = 1;
+                }
+              }
+              if (NCTA == 2) umma_commit_pair(&emptyB[sb]); else umma_commit(&emptyB[sb]);
+              if (++sb == p.nB) { sb = 0; pb ^= 1; }
+            }
+            if (NCTA == 2) umma_commit_pair(&emptyA[sa]); else umma_commit(&emptyA[sa]);
+            if (++sa == p.nA) { sa = 0; pa ^= 1; }
+          }
+        }
+        if (NCTA == 2) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue warps: TMEM lane quadrant = warp id % 4
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int hw = p.Hg * p.Wg;
+    const int nchunks = p.BN / 16;
+    const uint32_t empty_remote = NCTA == 2 ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : 0u;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = first_tile; tile < n_tiles; tile += tile_step) {
+      const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+      const int q = (tm * NCTA + static_cast<int>(cta)) * 128 + row;
+      const int n0 = tn * p.BN;
+      const int img = q / hw;
+      const int rem = q - img * hw;
+      const int h = rem / p.Wg;
+      const int x = rem - h * p.Wg;
+      const bool in_range = q < p.M;
+      const bool valid = in_range && h < p.Hv && x < p.Wv;
+      const bool do_store = valid || (in_range && p.zero_invalid);
+      const int64_t orow = static_cast<int64_t>(img) * p.out_img_rows +
+                           static_cast<int64_t>(h * p.out_sh + p.out_h0) * p.out_wg + (x * p.out_sw + p.out_w0);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + acc * kC2AccStride + (static_cast<uint32_t>(quad * 32) << 16);
+      for (int j = 0; j < nchunks; ++j) {
+        uint32_t v[16];
+        tmem_ld16(t_addr + j * 16, v);
+        tmem_ld_wait();
+        const int nc = n0 + j * 16;
+        if (do_store && nc < p.n_store) {
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float val = valid ? __uint_as_float(v[i]) : 0.f;
+            if (valid) {
+              if (p.bias != nullptr) val += __ldg(p.bias + nc + i);
+              if (p.act == 1) val = fmaxf(val, 0.f);
+              else if (p.act == 2) val = tanhf(val);
+            }
+            f[i] = val;
+          }
+          if (p.out_f32) {
+            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.out_ld + nc);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + orow * p.out_ld + nc);
+            dst[0] = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+            dst[1] = make_uint4(pack2(f[8], f[9]), pack2(f[10], f[11]), pack2(f[12], f[13]), pack2(f[14], f[15]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (NCTA == 2) mbar_arrive_cluster(empty_remote + acc * 8);
+        else mbar_arrive(&tmem_empty[acc]);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    if (NCTA == 2) tmem_dealloc2(tmem_base, kC2TmemCols);
+    else tmem_dealloc(tmem_base, kC2TmemCols);
+  }
+}
+
+}  // namespace mmh
+
+// ------------------------------------------------------------------------------------------------
+using namespace mmh;
+
+struct MmhConv2 {
+  CUtensorMap tmA, tmW;
+  Conv2Params kp;
+  int grid, ncta;
+  size_t smem;
+};
+
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
+int mmh_conv2_create(const MmhConvDesc* d, MmhConv2** out_plan) {
+  auto* plan = new MmhConv2();
+  Conv2Params& k = plan->kp;
+  memset(&k, 0, sizeof(k));
+  auto fail = [&]() { delete plan; return 1; };
+  k.KC = (d->C % 64) == 0 ? 64 : ((d->C % 32) == 0 ? 32 : 16);
+  k.cpt = d->C / k.KC;
+  k.ksteps = k.KC / 16;
+  k.row_bytes = k.KC * 2;
+  k.swz = k.KC == 64 ? 2u : (k.KC == 32 ? 4u : 6u);
+  k.sbo = 8 * k.row_bytes;
+  k.N = d->N;
+  if (d->N <= 256) {
+    k.BN = d->N;
+  } else {
+    if ((d->N % 128) != 0) { set_error("N=%d unsupported", d->N); return fail(); }
+    k.BN = (d->N % 256) == 0 ? 256 : 128;
+  }
+  k.tiles_n = d->N / k.BN;
+  k.M = static_cast<int32_t>(d->M);
+  // pairs: worth it when the weight tile dominates the traffic and there are enough row tiles to fill 74 pairs
+  int ncta = env_int("MMH_CONV_NCTA", 0);
+  if (ncta == 0) ncta = (k.BN >= 128 && (k.BN % 32) == 0 && d->M >= 148 * 128) ? 2 : 1;
+  if (ncta == 2 && (k.BN % 32) != 0) ncta = 1;
+  plan->ncta = ncta;
+  k.tiles_m = (k.M + 128 * ncta - 1) / (128 * ncta);
+  k.Hg = d->Hg; k.Wg = d->Wg; k.Hv = d->Hv; k.Wv = d->Wv;
+  k.out_f32 = d->out_f32; k.out_ld = d->out_ld; k.out_wg = d->out_wg;
+  k.out_sh = d->out_sh; k.out_sw = d->out_sw; k.out_h0 = d->out_h0; k.out_w0 = d->out_w0;
+  k.zero_invalid = d->zero_invalid; k.act = d->act;
+  k.n_store = d->n_store > 0 ? d->n_store : d->N;
+  k.out_img_rows = d->out_img_rows;
+  k.out = d->out;
+  k.bias = d->bias;
+
+  // ---- tap groups: sort by shift, start a new group at a gap of >= 128 rows or when the window would
+  // outgrow its slot
+  const int w_taps = d->w_taps > 0 ? d->w_taps : d->T;
+  std::vector<std::pair<int, int>> taps;   // (shift, slot)
+  for (int t = 0; t < d->T; ++t) {
+    const int slot = d->w_taps > 0 ? d->w_slot[t] : t;
+    if (slot < 0 || slot >= w_taps) { set_error("w_slot[%d] out of range", t); return fail(); }
+    taps.emplace_back(d->shift[t], slot);
+  }
+  std::stable_sort(taps.begin(), taps.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) {
+    return a.first < b.first;
+  });
+  const int cap_rows = static_cast<int>(40960 / k.row_bytes);
+  int ng = 0, span_max = 0, gtaps_max = 0;
+  for (int t = 0; t < d->T; ++t) {
+    const bool fresh = t == 0 || taps[t].first - taps[t - 1].first >= 128 ||
+                       taps[t].first - k.g_min[ng - 1] + 128 > cap_rows;
+    if (fresh) {
+      if (ng == kC2MaxGroups) { set_error("too many tap groups"); return fail(); }
+      k.g_first[ng] = t;
+      k.g_min[ng] = taps[t].first;
+      ++ng;
+    }
+    k.rel[t] = taps[t].first - k.g_min[ng - 1];
+    k.w_slot[t] = taps[t].second;
+    span_max = std::max(span_max, k.rel[t]);
+  }
+  k.g_first[ng] = d->T;
+  k.n_groups = ng;
+  for (int g = 0; g < ng; ++g) gtaps_max = std::max(gtaps_max, k.g_first[g + 1] - k.g_first[g]);
+
+  const int need_rows = 128 + span_max;
+  k.a_boxes = (need_rows + 255) / 256;
+  k.a_box_rows = ((need_rows + k.a_boxes - 1) / k.a_boxes + 7) / 8 * 8;
+  k.a_box_bytes = k.a_box_rows * k.row_bytes;
+  k.a_slot_bytes = (k.a_boxes * k.a_box_bytes + 1023u) & ~1023u;
+  k.b_rows = k.BN / ncta;
+  k.b_tile_bytes = k.b_rows * k.row_bytes;
+  k.b_tile_stride = (k.b_tile_bytes + 1023u) & ~1023u;
+  int batch = static_cast<int>(32768 / k.b_tile_stride);
+  batch = std::max(1, std::min(batch, gtaps_max));
+  batch = env_int("MMH_CONV_BBATCH", batch);
+  k.b_batch = batch;
+  k.b_slot_bytes = k.b_batch * k.b_tile_stride;
+  const uint32_t budget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/;
+  k.nA = env_int("MMH_CONV_NA", k.a_slot_bytes <= 16384 ? 4 : 2);
+  if (k.nA > kC2MaxA) k.nA = kC2MaxA;
+  if (k.nA * k.a_slot_bytes + 2 * k.b_slot_bytes > budget) { set_error("conv tile does not fit in shared memory"); return fail(); }
+  k.nB = (budget - k.nA * k.a_slot_bytes) / k.b_slot_bytes;
+  if (k.nB > kC2MaxB) k.nB = kC2MaxB;
+  k.b_ring_off = k.nA * k.a_slot_bytes;
+  k.bar_off = k.b_ring_off + k.nB * k.b_slot_bytes;
+  plan->smem = k.bar_off + 512 + 1024;
+
+  const CUtensorMapSwizzle swz = k.KC == 64   ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : k.KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                              : CU_TENSOR_MAP_SWIZZLE_32B;
+  if (make_tmap_2d_bf16(&plan->tmA, d->a, d->C, d->a_rows, d->a_ld, k.KC, k.a_box_rows, swz)) return fail();
+  if (make_tmap_2d_bf16(&plan->tmW, d->w, d->C, static_cast<int64_t>(w_taps) * d->N, d->C, k.KC, k.b_rows, swz))
+    return fail();
+  const int tiles = k.tiles_m * k.tiles_n;
+  const int units = num_sms() / ncta;
+  plan->grid = (tiles < units ? tiles : units) * ncta;
+  cudaError_t e = ncta == 2 ? cudaFuncSetAttribute(conv2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                            : cudaFuncSetAttribute(conv2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv2_kernel): %s", cudaGetErrorString(e)); return fail(); }
+  *out_plan = plan;
+  return 0;
+}
+
+void mmh_conv2_destroy(MmhConv2* plan) { delete plan; }
+
+int mmh_conv2_run(const MmhConv2* plan, void* stream) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(plan->grid, 1, 1);
+  cfg.blockDim = dim3(kC2Threads, 1, 1);
+  cfg.dynamicSmemBytes = plan->smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  if (plan->ncta == 2) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MMH_CUDA(cudaLaunchKernelEx(&cfg, conv2_kernel<2>, plan->tmA, plan->tmW, plan->kp));
+  } else {
+    MMH_CUDA(cudaLaunchKernelEx(&cfg, conv2_kernel<1>, plan->tmA, plan->tmW, plan->kp));
+  }
+  return 0;
+}

@@ -91,7 +91,7 @@ class ConvL:
         self.need_dx = need_dx
         self.T = geom.k * geom.k
         # few-channel k x k stems: fold the k column taps into the contraction (128-byte TMA rows instead of 32)
-        self.fold = geom.kind == 's1' and geom.k >= 5 and self.Cin_p <= 48 and x_buf is None
+        self.fold = False   # superseded: the window kernel reuses one activation window per kernel row (tc_conv2.cu)
         if x_buf is not None:
             self.x = x_buf
         else:

@@ -234,7 +234,9 @@ def case_conv_wgrad(kind='s1', B=2, H=16, W=16, Cin=64, Cout=64, k=3, mode='refl
 
 
 def case_perf(B=16, H=64, W=64, Cin=256, Cout=256, iters=20):
-    """Device time of the dominant 3x3 layer (fprop, dgrad, wgrad)."""
+    """Device time of the dominant 3x3 layer (fprop, dgrad, wgrad). MMH_PERF_ITERS overrides iters (ncu runs)."""
+    iters = int(os.environ.get("MMH_PERF_ITERS", iters))
+    warm = 1 if iters == 1 else 3
     lib = _lib()
     Cin_p, Cout_p = chan_pad(Cin), chan_pad(Cout)
     g = geom_s1(B, H, W, 3, 'reflect', Cin_p, Cout_p)
@@ -249,7 +251,7 @@ def case_perf(B=16, H=64, W=64, Cin=256, Cout=256, iters=20):
     for name, plans in (("fprop", convops.fwd_plans(lib, g, a_buf, wp, out, Cin_p, Cout_p)),
                         ("dgrad", convops.dgrad_plans(lib, g, out, wd, dx, Cin_p, Cout_p)),
                         ("wgrad", convops.wgrad_plans(lib, g, a_buf, out, dw, Cin_p, Cout_p, Cin, Cout))):
-        for _ in range(3):
+        for _ in range(warm):
             for p_ in plans:
                 p_.run(_stream())
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -301,4 +303,5 @@ CASES = {
     "wgrad_s2": lambda: case_conv_wgrad('s2', 2, 32, 32, 64, 128),
     "wgrad_up": lambda: case_conv_wgrad('up', 2, 16, 16, 256, 128),
     "perf": lambda: case_perf(),
+    "perf512": lambda: case_perf(16, 64, 64, 512, 512),
 }
