@@ -6,3 +6,8 @@ struct MmhConv2;   // tc_conv2.cu: activation windows in shared memory, optional
 int mmh_conv2_create(const MmhConvDesc* d, MmhConv2** out_plan);
 void mmh_conv2_destroy(MmhConv2* plan);
 int mmh_conv2_run(const MmhConv2* plan, void* stream);
+
+struct MmhWgrad2;  // tc_wgrad2.cu: windows shared by the taps, pairs, taps-on-M mode for the stems
+int mmh_wgrad2_create(const MmhWgradDesc* d, MmhWgrad2** out_plan);
+void mmh_wgrad2_destroy(MmhWgrad2* plan);
+int mmh_wgrad2_run(const MmhWgrad2* plan, void* stream);

@@ -14,9 +14,11 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/mmhand_sm100.h"
+#include "conv_plan.h"
 #include "host_common.h"
 #include "ptx.cuh"
 #include "tmap.h"
@@ -172,6 +174,8 @@ struct MmhWgradPlan {
   mmh::WgradKParams kp;
   int grid;
   size_t smem;
+  MmhWgrad2* v2 = nullptr;   // generation-2 plan (default); MMH_WGRAD_IMPL=1 selects the first-generation kernel
+  ~MmhWgradPlan() { if (v2) mmh_wgrad2_destroy(v2); }
 };
 
 using namespace mmh;
@@ -195,6 +199,14 @@ extern "C" int mmh_wgrad_plan_create(const MmhWgradDesc* d, MmhWgradPlan** out_p
   MMH_CHECK((d->a_ld % 8) == 0 && (d->dy_ld % 8) == 0, "leading dimensions must be multiples of 8");
   MMH_CHECK(d->M > 0 && d->M < (int64_t(1) << 31) - 256, "M out of range");
   auto* plan = new MmhWgradPlan();
+  {
+    const char* impl = getenv("MMH_WGRAD_IMPL");
+    if (impl == nullptr || atoi(impl) != 1) {
+      if (mmh_wgrad2_create(d, &plan->v2)) { delete plan; return 1; }
+      *out_plan = plan;
+      return 0;
+    }
+  }
   WgradKParams& k = plan->kp;
   memset(&k, 0, sizeof(k));
   k.T = d->T;
@@ -276,6 +288,7 @@ extern "C" int mmh_wgrad_plan_destroy(MmhWgradPlan* plan) {
 
 extern "C" int mmh_wgrad_run(const MmhWgradPlan* plan, void* stream) {
   MMH_CHECK(plan, "null plan");
+  if (plan->v2) return mmh_wgrad2_run(plan->v2, stream);
   wgrad_kernel<<<plan->grid, kWgThreads, plan->smem, static_cast<cudaStream_t>(stream)>>>(plan->tmDy, plan->tmA,
                                                                                          plan->kp);
   MMH_CUDA(cudaGetLastError());
