@@ -15,9 +15,11 @@ struct NoCtx {};
 
 // ------------------------------------------------------------------------------------------------ assemble
 struct AssembleF {
+  static constexpr int kUnroll = 2;
   struct Ctx { float sc[8], sh[8]; };
+  struct In { float v[8]; };
   const float* src0; const float* src1; const float* scale; const float* shift;
-  act_t* dst; LayD dl; PixDec pd;
+  act_t* dst; LayD dl;
   int C0, C1, reflect;
   MMH_HD void prep(int g, Ctx& c) const {
 #pragma unroll
@@ -28,35 +30,41 @@ struct AssembleF {
       c.sh[j] = on ? shift[ch] : 0.f;
     }
   }
-  MMH_HD void operator()(uint32_t pix, int g, const Ctx& c) const {
-    int b, h, w;
-    pix_decode(pd, pix, b, h, w);
+  MMH_HD void load(int b, int h, int w, int g, const Ctx&, In& in) const {
     const bool inside = h >= 0 && h < dl.H && w >= 0 && w < dl.W;
-    float v[8];
-    zero8(v);
+    zero8(in.v);
     if (inside || reflect) {
       const int hs = reflect_idx(h, dl.H), ws = reflect_idx(w, dl.W);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int ch = g * 8 + j;
-        float x = 0.f;
-        if (ch < C0) x = src0[((static_cast<int64_t>(b) * C0 + ch) * dl.H + hs) * dl.W + ws];
-        else if (ch < C0 + C1) x = src1[((static_cast<int64_t>(b) * C1 + (ch - C0)) * dl.H + hs) * dl.W + ws];
-        v[j] = ch < C0 + C1 ? x * c.sc[j] + c.sh[j] : 0.f;
+        if (ch < C0) in.v[j] = src0[((static_cast<int64_t>(b) * C0 + ch) * dl.H + hs) * dl.W + ws];
+        else if (ch < C0 + C1) in.v[j] = src1[((static_cast<int64_t>(b) * C1 + (ch - C0)) * dl.H + hs) * dl.W + ws];
       }
     }
+  }
+  MMH_HD void finish(const In& in, int b, int h, int w, int g, const Ctx& c) const {
+    const bool live = reflect || (h >= 0 && h < dl.H && w >= 0 && w < dl.W);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (live && g * 8 + j < C0 + C1) ? in.v[j] * c.sc[j] + c.sh[j] : 0.f;
     st8_bf16(dst + lay_off(dl, b, h, w) + g * 8, v);
   }
 };
 
 // ------------------------------------------------------------------------------------------------ BN stats
 struct BnStatsF {
+  static constexpr int kUnroll = 4;
   typedef NoCtx Ctx;
+  struct In { ActX8 x; };
   const act_t* x; int ld;
   MMH_HD void prep(int, Ctx&) const {}
-  MMH_HD void operator()(uint32_t r, int g, const Ctx&, float (&acc)[2][8]) const {
+  MMH_HD void load(int, int, int r, int g, const Ctx&, In& in) const {
+    ld_raw(x + static_cast<int64_t>(r) * ld + g * 8, in.x);
+  }
+  MMH_HD void accum(const In& in, int, int, int, int, const Ctx&, float (&acc)[2][8]) const {
     float v[8];
-    ld8_bf16(x + static_cast<int64_t>(r) * ld + g * 8, v);
+    cvt8(in.x, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[0][j] += v[j]; acc[1][j] += v[j] * v[j]; }
   }
@@ -91,9 +99,11 @@ struct BnFinalizeF {
 
 // ------------------------------------------------------------------------------------------------ norm + act + pad
 struct NormActF {
+  static constexpr int kUnroll = 4;
   struct Ctx { float a[8], b[8]; };
+  struct In { ActX8 x; F32x8 r; };
   const act_t* src; LayD sl; const float* coef; int relu, dropout; uint32_t key;
-  const float* resid; act_t* dst; LayD dl; PixDec pd; int reflect; float* dst_f32;
+  const float* resid; act_t* dst; LayD dl; int reflect; float* dst_f32;
   MMH_HD void prep(int g, Ctx& c) const {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -101,16 +111,22 @@ struct NormActF {
       c.b[j] = coef != nullptr ? coef[sl.C + g * 8 + j] : 0.f;
     }
   }
-  MMH_HD void operator()(uint32_t pix, int g, const Ctx& c) const {
+  MMH_HD bool live(int h, int w) const { return reflect || (h >= 0 && h < sl.H && w >= 0 && w < sl.W); }
+  MMH_HD void load(int b, int h, int w, int g, const Ctx&, In& in) const {
+    if (live(h, w)) {
+      const int hs = reflect_idx(h, sl.H), ws = reflect_idx(w, sl.W);
+      ld_raw(src + lay_off(sl, b, hs, ws) + g * 8, in.x);
+      if (resid != nullptr) ld_raw(resid + static_cast<int64_t>((b * sl.H + hs) * sl.W + ws) * sl.C + g * 8, in.r);
+    }
+  }
+  MMH_HD void finish(const In& in, int b, int h, int w, int g, const Ctx& c) const {
     const int H = sl.H, W = sl.W, C = sl.C;
-    int b, h, w;
-    pix_decode(pd, pix, b, h, w);
     const bool inside = h >= 0 && h < H && w >= 0 && w < W;
     float y[8];
     zero8(y);
-    if (inside || reflect) {
+    if (live(h, w)) {
       const int hs = reflect_idx(h, H), ws = reflect_idx(w, W);
-      ld8_bf16(src + lay_off(sl, b, hs, ws) + g * 8, y);
+      cvt8(in.x, y);
 #pragma unroll
       for (int j = 0; j < 8; ++j) y[j] = c.a[j] * y[j] + c.b[j];
       if (relu) {
@@ -118,47 +134,57 @@ struct NormActF {
         for (int j = 0; j < 8; ++j) y[j] = y[j] > 0.f ? y[j] : 0.f;
       }
       if (dropout) {
+        const uint32_t bits = drop_bits(key, b, hs, ws, g, C, H, W);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] *= drop_keep2(key, b, g * 8 + j, hs, ws, C, H, W);
+        for (int j = 0; j < 8; ++j) y[j] = ((bits >> j) & 1u) ? 2.0f * y[j] : 0.f;
       }
       if (resid != nullptr) {
         float r[8];
-        ld8_f32(resid + ((static_cast<int64_t>(b) * H + hs) * W + ws) * C + g * 8, r);
+        cvt8(in.r, r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) y[j] += r[j];
       }
     }
     if (dst != nullptr) st8_bf16(dst + lay_off(dl, b, h, w) + g * 8, y);
-    if (inside && dst_f32 != nullptr) st8_f32(dst_f32 + ((static_cast<int64_t>(b) * H + h) * W + w) * C + g * 8, y);
+    if (inside && dst_f32 != nullptr) st8_f32(dst_f32 + static_cast<int64_t>((b * H + h) * W + w) * C + g * 8, y);
   }
 };
 
 // ------------------------------------------------------------------------------------------------ PAT gate
 struct GateFwdF {
+  static constexpr int kUnroll = 2;
   struct Ctx { float a[8], b[8]; };
+  struct In { ActX8 c1, x2, x3; F32x8 t; };
   const act_t* c1; const act_t* x2o; const act_t* x3o; LayD sl; const float* coef;
   const float* trunk_in; float* trunk_out;
   act_t* d1; LayD d1l; act_t* d2; LayD d2l; act_t* d3; LayD d3l;
-  PixDec pd; int reflect;
+  int reflect;
   MMH_HD void prep(int g, Ctx& c) const {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { c.a[j] = coef[g * 8 + j]; c.b[j] = coef[sl.C + g * 8 + j]; }
   }
-  MMH_HD void operator()(uint32_t pix, int g, const Ctx& c) const {
+  MMH_HD bool live(int h, int w) const { return reflect || (h >= 0 && h < sl.H && w >= 0 && w < sl.W); }
+  MMH_HD void load(int b, int h, int w, int g, const Ctx&, In& in) const {
+    if (live(h, w)) {
+      const int hs = reflect_idx(h, sl.H), ws = reflect_idx(w, sl.W);
+      const int64_t so = lay_off(sl, b, hs, ws) + g * 8;
+      ld_raw(c1 + so, in.c1);
+      ld_raw(x2o + so, in.x2);
+      ld_raw(x3o + so, in.x3);
+      ld_raw(trunk_in + static_cast<int64_t>((b * sl.H + hs) * sl.W + ws) * sl.C + g * 8, in.t);
+    }
+  }
+  MMH_HD void finish(const In& in, int b, int h, int w, int g, const Ctx& c) const {
     const int H = sl.H, W = sl.W, C = sl.C;
-    int b, h, w;
-    pix_decode(pd, pix, b, h, w);
     const bool inside = h >= 0 && h < H && w >= 0 && w < W;
     float out[8], a2[8], a3[8];
     zero8(out); zero8(a2); zero8(a3);
-    if (inside || reflect) {
-      const int hs = reflect_idx(h, H), ws = reflect_idx(w, W);
-      const int64_t so = lay_off(sl, b, hs, ws) + g * 8;
+    if (live(h, w)) {
       float v1[8], t[8];
-      ld8_bf16(c1 + so, v1);
-      ld8_bf16(x2o + so, a2);
-      ld8_bf16(x3o + so, a3);
-      ld8_f32(trunk_in + ((static_cast<int64_t>(b) * H + hs) * W + ws) * C + g * 8, t);
+      cvt8(in.c1, v1);
+      cvt8(in.x2, a2);
+      cvt8(in.x3, a3);
+      cvt8(in.t, t);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float bn = c.a[j] * v1[j] + c.b[j];
@@ -176,7 +202,7 @@ struct GateFwdF {
       st8_bf16(d3 + o, a2);
       st8_bf16(d3 + o + C, out);
     }
-    if (inside) st8_f32(trunk_out + ((static_cast<int64_t>(b) * H + h) * W + w) * C + g * 8, out);
+    if (inside) st8_f32(trunk_out + static_cast<int64_t>((b * H + h) * W + w) * C + g * 8, out);
   }
 };
 
@@ -215,20 +241,25 @@ MMH_HD void fold_add8(const GradSrcD& s, int b, int h, int w, int cg, float (&ac
 }
 
 struct GradGatherF {
+  static constexpr int kUnroll = 2;
   typedef NoCtx Ctx;
+  struct In { float acc[8]; ActX8 m; };
   int nsrc; GradSrcD src[4]; const float* trunk; const act_t* mask; LayD ml;
-  void* dst; LayD dl; PixDec pd; int dst_f32, H, W, C;
+  void* dst; LayD dl; int dst_f32, H, W, C;
   MMH_HD void prep(int, Ctx&) const {}
-  MMH_HD void operator()(uint32_t pix, int g, const Ctx&) const {
-    int b, h, w;
-    pix_decode(pd, pix, b, h, w);
+  MMH_HD void load(int b, int h, int w, int g, const Ctx&, In& in) const {
+    const int64_t plain = static_cast<int64_t>((b * H + h) * W + w) * C + g * 8;
+    if (trunk != nullptr) ld8_f32(trunk + plain, in.acc); else zero8(in.acc);
+    for (int s = 0; s < nsrc; ++s) fold_add8(src[s], b, h, w, g * 8, in.acc);
+    if (mask != nullptr) ld_raw(mask + lay_off(ml, b, h, w) + g * 8, in.m);
+  }
+  MMH_HD void finish(const In& in, int b, int h, int w, int g, const Ctx&) const {
     float acc[8];
-    const int64_t plain = static_cast<int64_t>(pix) * C + g * 8;
-    if (trunk != nullptr) ld8_f32(trunk + plain, acc); else zero8(acc);
-    for (int s = 0; s < nsrc; ++s) fold_add8(src[s], b, h, w, g * 8, acc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = in.acc[j];
     if (mask != nullptr) {
       float m[8];
-      ld8_bf16(mask + lay_off(ml, b, h, w) + g * 8, m);
+      cvt8(in.m, m);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = m[j] > 0.f ? acc[j] : 0.f;
     }
@@ -240,31 +271,37 @@ struct GradGatherF {
 
 // ------------------------------------------------------------------------------------------------ BN backward
 // dy = a*(dz_eff - k0 - xhat*k1) with xhat = (x - mean)*rstd is evaluated as  a*dz_eff + bx*x + cc
+struct BnBwdIn { union { F32x8 f; ActX8 h; } dz; ActX8 x; };
 struct BnBwdBase {
   const void* dz; int dz_f32, relu, dropout; uint32_t key;
-  const act_t* x; LayD xl; const float* coef; const float* save; PixDec pd;
+  const act_t* x; LayD xl; const float* coef; const float* save;
+  MMH_HD void load(int b, int h, int w, int g, BnBwdIn& in) const {
+    const int64_t plain = static_cast<int64_t>((b * xl.H + h) * xl.W + w) * xl.C + g * 8;
+    if (dz_f32) ld_raw(static_cast<const float*>(dz) + plain, in.dz.f);
+    else ld_raw(static_cast<const act_t*>(dz) + plain, in.dz.h);
+    ld_raw(x + lay_off(xl, b, h, w) + g * 8, in.x);
+  }
   // effective upstream gradient (after the recomputed ReLU / dropout masks) and raw activation of one vector
-  MMH_HD void load(uint32_t pix, int g, const float (&a)[8], const float (&bb)[8], float (&dze)[8], float (&xv)[8]) const {
-    const int H = xl.H, W = xl.W, C = xl.C;
-    int b, h, w;
-    pix_decode(pd, pix, b, h, w);
-    const int64_t plain = static_cast<int64_t>(pix) * C + g * 8;
-    if (dz_f32) ld8_f32(static_cast<const float*>(dz) + plain, dze);
-    else ld8_bf16(static_cast<const act_t*>(dz) + plain, dze);
-    ld8_bf16(x + lay_off(xl, b, h, w) + g * 8, xv);
+  MMH_HD void eff(const BnBwdIn& in, int b, int h, int w, int g, const float (&a)[8], const float (&bb)[8],
+                  float (&dze)[8], float (&xv)[8]) const {
+    if (dz_f32) cvt8(in.dz.f, dze); else cvt8(in.dz.h, dze);
+    cvt8(in.x, xv);
     if (relu) {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (!(a[j] * xv[j] + bb[j] > 0.f)) dze[j] = 0.f;
     }
     if (dropout) {
+      const uint32_t bits = drop_bits(key, b, h, w, g, xl.C, xl.H, xl.W);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dze[j] *= drop_keep2(key, b, g * 8 + j, h, w, C, H, W);
+      for (int j = 0; j < 8; ++j) dze[j] = ((bits >> j) & 1u) ? 2.0f * dze[j] : 0.f;
     }
   }
 };
 struct BnBwdReduceF {
+  static constexpr int kUnroll = 4;
   struct Ctx { float a[8], b[8], mean[8], rstd[8]; };
+  typedef BnBwdIn In;
   BnBwdBase cm;
   MMH_HD void prep(int g, Ctx& c) const {
     const int C = cm.xl.C;
@@ -274,9 +311,10 @@ struct BnBwdReduceF {
       c.mean[j] = cm.save[g * 8 + j]; c.rstd[j] = cm.save[C + g * 8 + j];
     }
   }
-  MMH_HD void operator()(uint32_t pix, int g, const Ctx& c, float (&acc)[2][8]) const {
+  MMH_HD void load(int b, int h, int w, int g, const Ctx&, In& in) const { cm.load(b, h, w, g, in); }
+  MMH_HD void accum(const In& in, int b, int h, int w, int g, const Ctx& c, float (&acc)[2][8]) const {
     float dze[8], xv[8];
-    cm.load(pix, g, c.a, c.b, dze, xv);
+    cm.eff(in, b, h, w, g, c.a, c.b, dze, xv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       acc[0][j] += dze[j];
@@ -285,7 +323,9 @@ struct BnBwdReduceF {
   }
 };
 struct BnBwdApplyF {
+  static constexpr int kUnroll = 4;
   struct Ctx { float a[8], b[8], bx[8], cc[8]; };
+  typedef BnBwdIn In;
   BnBwdBase cm; const float* k; act_t* dy; LayD yl;
   MMH_HD void prep(int g, Ctx& c) const {
     const int C = cm.xl.C;
@@ -298,13 +338,12 @@ struct BnBwdApplyF {
       c.cc[j] = -a * k[ch] + a * k[C + ch] * rstd * mean;
     }
   }
-  MMH_HD void operator()(uint32_t pix, int g, const Ctx& c) const {
+  MMH_HD void load(int b, int h, int w, int g, const Ctx&, In& in) const { cm.load(b, h, w, g, in); }
+  MMH_HD void finish(const In& in, int b, int h, int w, int g, const Ctx& c) const {
     float dze[8], xv[8], o[8];
-    cm.load(pix, g, c.a, c.b, dze, xv);
+    cm.eff(in, b, h, w, g, c.a, c.b, dze, xv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = c.a[j] * dze[j] + c.bx[j] * xv[j] + c.cc[j];
-    int b, h, w;
-    pix_decode(cm.pd, pix, b, h, w);
     st8_bf16(dy + lay_off(yl, b, h, w) + g * 8, o);
   }
 };
@@ -319,19 +358,24 @@ struct BnBwdFinalizeF {
 };
 
 // ------------------------------------------------------------------------------------------------ gate backward
+struct GateBwdIn { F32x8 dv; ActX8 c1, x2, x3; float e2[8], e3[8]; };
 struct GateBwdBase {
   const float* dout; const act_t* c1; const act_t* x2o; const act_t* x3o; LayD sl;
-  const float* coef; const float* save; PixDec pd;
-  MMH_HD void load(uint32_t pix, int g, const float (&a)[8], const float (&bb)[8], float (&d1)[8], float (&v1)[8],
-                   float (&d2)[8], float (&d3)[8], int& b, int& h, int& w) const {
-    const int C = sl.C;
-    pix_decode(pd, pix, b, h, w);
-    float dv[8], v2[8], v3[8];
-    ld8_f32(dout + static_cast<int64_t>(pix) * C + g * 8, dv);
+  const float* coef; const float* save;
+  MMH_HD void load(int b, int h, int w, int g, GateBwdIn& in) const {
+    ld_raw(dout + static_cast<int64_t>((b * sl.H + h) * sl.W + w) * sl.C + g * 8, in.dv);
     const int64_t so = lay_off(sl, b, h, w) + g * 8;
-    ld8_bf16(c1 + so, v1);
-    ld8_bf16(x2o + so, v2);
-    ld8_bf16(x3o + so, v3);
+    ld_raw(c1 + so, in.c1);
+    ld_raw(x2o + so, in.x2);
+    ld_raw(x3o + so, in.x3);
+  }
+  MMH_HD void eff(const GateBwdIn& in, const float (&a)[8], const float (&bb)[8], float (&d1)[8], float (&v1)[8],
+                  float (&d2)[8], float (&d3)[8]) const {
+    float dv[8], v2[8], v3[8];
+    cvt8(in.dv, dv);
+    cvt8(in.c1, v1);
+    cvt8(in.x2, v2);
+    cvt8(in.x3, v3);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float s2 = sigmoidf_(v2[j]), s3 = sigmoidf_(v3[j]);
@@ -343,7 +387,9 @@ struct GateBwdBase {
   }
 };
 struct GateBwdReduceF {
+  static constexpr int kUnroll = 2;
   struct Ctx { float a[8], b[8], mean[8], rstd[8]; };
+  typedef GateBwdIn In;
   GateBwdBase cm;
   MMH_HD void prep(int g, Ctx& c) const {
     const int C = cm.sl.C;
@@ -353,10 +399,10 @@ struct GateBwdReduceF {
       c.mean[j] = cm.save[g * 8 + j]; c.rstd[j] = cm.save[C + g * 8 + j];
     }
   }
-  MMH_HD void operator()(uint32_t pix, int g, const Ctx& c, float (&acc)[2][8]) const {
+  MMH_HD void load(int b, int h, int w, int g, const Ctx&, In& in) const { cm.load(b, h, w, g, in); }
+  MMH_HD void accum(const In& in, int, int, int, int, const Ctx& c, float (&acc)[2][8]) const {
     float d1[8], v1[8], d2[8], d3[8];
-    int b, h, w;
-    cm.load(pix, g, c.a, c.b, d1, v1, d2, d3, b, h, w);
+    cm.eff(in, c.a, c.b, d1, v1, d2, d3);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       acc[0][j] += d1[j];
@@ -365,7 +411,9 @@ struct GateBwdReduceF {
   }
 };
 struct GateBwdApplyF {
+  static constexpr int kUnroll = 2;
   struct Ctx { float a[8], b[8], bx[8], cc[8]; };
+  typedef GateBwdIn In;
   GateBwdBase cm; const float* k; GradSrcD ex2, ex3;
   act_t* dy1; act_t* dy2; act_t* dy3; LayD yl;
   MMH_HD void prep(int g, Ctx& c) const {
@@ -379,14 +427,22 @@ struct GateBwdApplyF {
       c.cc[j] = -a * k[ch] + a * k[C + ch] * rstd * mean;
     }
   }
-  MMH_HD void operator()(uint32_t pix, int g, const Ctx& c) const {
+  MMH_HD void load(int b, int h, int w, int g, const Ctx&, In& in) const {
+    cm.load(b, h, w, g, in);
+    zero8(in.e2);
+    zero8(in.e3);
+    if (ex2.p != nullptr) fold_add8(ex2, b, h, w, g * 8, in.e2);
+    if (ex3.p != nullptr) fold_add8(ex3, b, h, w, g * 8, in.e3);
+  }
+  MMH_HD void finish(const In& in, int b, int h, int w, int g, const Ctx& c) const {
     float d1[8], v1[8], d2[8], d3[8], o[8];
-    int b, h, w;
-    cm.load(pix, g, c.a, c.b, d1, v1, d2, d3, b, h, w);
+    cm.eff(in, c.a, c.b, d1, v1, d2, d3);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = c.a[j] * d1[j] + c.bx[j] * v1[j] + c.cc[j];
-    if (ex2.p != nullptr) fold_add8(ex2, b, h, w, g * 8, d2);
-    if (ex3.p != nullptr) fold_add8(ex3, b, h, w, g * 8, d3);
+    for (int j = 0; j < 8; ++j) {
+      o[j] = c.a[j] * d1[j] + c.bx[j] * v1[j] + c.cc[j];
+      d2[j] += in.e2[j];
+      d3[j] += in.e3[j];
+    }
     const int64_t off = lay_off(yl, b, h, w) + g * 8;
     st8_bf16(dy1 + off, o);
     st8_bf16(dy2 + off, d2);
@@ -401,9 +457,6 @@ using namespace mmh;
 
 #define MMH_REQ_VEC(C) MMH_CHECK((C) > 0 && ((C) % 8) == 0, "channel count %d must be a multiple of 8", (int)(C))
 
-static int64_t ext_pixels(int B, int H, int W, int lo, int hi) {
-  return static_cast<int64_t>(B) * (H + lo + hi) * (W + lo + hi);
-}
 
 extern "C" int mmh_assemble_nchw(const float* src0, int32_t C0, const float* src1, int32_t C1, const float* scale,
                                  const float* shift, void* dst, const MmhLay* dl, int32_t pad_lo, int32_t pad_hi,
@@ -414,9 +467,9 @@ extern "C" int mmh_assemble_nchw(const float* src0, int32_t C0, const float* src
   MMH_CHECK(!reflect || (pad_lo < dl->H && pad_hi < dl->H && pad_lo < dl->W && pad_hi < dl->W), "halo too large");
   AssembleF f;
   f.src0 = src0; f.src1 = src1; f.scale = scale; f.shift = shift;
-  f.dst = static_cast<act_t*>(dst); f.dl = to_layd(*dl); f.pd = make_pixdec(dl->H, dl->W, pad_lo, pad_hi);
+  f.dst = static_cast<act_t*>(dst); f.dl = to_layd(*dl);
   f.C0 = C0; f.C1 = src1 ? C1 : 0; f.reflect = reflect;
-  return launch_pg(f, ext_pixels(dl->B, dl->H, dl->W, pad_lo, pad_hi), dl->C / 8, stream);
+  return launch_pg(f, make_rowgeom(dl->B, dl->H, dl->W, pad_lo, pad_hi), dl->C / 8, stream);
 }
 
 extern "C" int mmh_bn_stats(const void* x, int64_t rows, int32_t ld, int32_t C, float* sums, void* stream) {
@@ -424,7 +477,8 @@ extern "C" int mmh_bn_stats(const void* x, int64_t rows, int32_t ld, int32_t C, 
   MMH_REQ_VEC(C);
   BnStatsF f;
   f.x = static_cast<const act_t*>(x); f.ld = ld;
-  return launch_reduce_ch<2>(f, rows, C / 8, C, sums, stream);
+  MMH_CHECK(rows < (int64_t(1) << 31), "too many rows");
+  return launch_reduce_ch<2>(f, make_flatgeom(rows), C / 8, C, sums, stream);
 }
 
 extern "C" int mmh_bn_finalize(const float* sums, float count, const float* gamma, const float* beta,
@@ -447,10 +501,9 @@ extern "C" int mmh_norm_act(const MmhNormAct* p, void* stream) {
   f.dst = static_cast<act_t*>(p->dst); f.dl = to_layd(p->dl);
   const int lo = p->dst ? p->pad_lo : 0, hi = p->dst ? p->pad_hi : 0;
   f.reflect = p->reflect; f.dst_f32 = p->dst_f32;
-  f.pd = make_pixdec(f.sl.H, f.sl.W, lo, hi);
   MMH_CHECK(!p->dst || (p->dl.H == p->sl.H && p->dl.W == p->sl.W && p->dl.C == p->sl.C), "src/dst shape mismatch");
   MMH_CHECK(!f.reflect || (lo < f.sl.H && hi < f.sl.H && lo < f.sl.W && hi < f.sl.W), "halo too large");
-  return launch_pg(f, ext_pixels(f.sl.B, f.sl.H, f.sl.W, lo, hi), p->sl.C / 8, stream);
+  return launch_pg(f, make_rowgeom(f.sl.B, f.sl.H, f.sl.W, lo, hi), p->sl.C / 8, stream);
 }
 
 extern "C" int mmh_gate_fwd(const MmhGateFwd* p, void* stream) {
@@ -464,8 +517,7 @@ extern "C" int mmh_gate_fwd(const MmhGateFwd* p, void* stream) {
   f.d2 = static_cast<act_t*>(p->d2); f.d2l = to_layd(p->d2l);
   f.d3 = static_cast<act_t*>(p->d3); f.d3l = to_layd(p->d3l);
   f.reflect = p->reflect;
-  f.pd = make_pixdec(f.sl.H, f.sl.W, p->pad_lo, p->pad_hi);
-  return launch_pg(f, ext_pixels(f.sl.B, f.sl.H, f.sl.W, p->pad_lo, p->pad_hi), p->sl.C / 8, stream);
+  return launch_pg(f, make_rowgeom(f.sl.B, f.sl.H, f.sl.W, p->pad_lo, p->pad_hi), p->sl.C / 8, stream);
 }
 
 extern "C" int mmh_grad_gather(const MmhGradGather* p, void* stream) {
@@ -477,15 +529,13 @@ extern "C" int mmh_grad_gather(const MmhGradGather* p, void* stream) {
   f.trunk = p->trunk; f.mask = static_cast<const act_t*>(p->mask); f.ml = to_layd(p->ml);
   f.dst = p->dst; f.dl = to_layd(p->dl); f.dst_f32 = p->dst_f32;
   f.H = p->H; f.W = p->W; f.C = p->C;
-  f.pd = make_pixdec(p->H, p->W, 0, 0);
-  return launch_pg(f, ext_pixels(p->B, p->H, p->W, 0, 0), p->C / 8, stream);
+  return launch_pg(f, make_rowgeom(p->B, p->H, p->W, 0, 0), p->C / 8, stream);
 }
 
 static BnBwdBase bn_common(const MmhBnBwd* p) {
   BnBwdBase c;
   c.dz = p->dz; c.dz_f32 = p->dz_f32; c.relu = p->relu; c.dropout = p->dropout; c.key = p->drop_key;
   c.x = static_cast<const act_t*>(p->x); c.xl = to_layd(p->xl); c.coef = p->coef; c.save = p->save;
-  c.pd = make_pixdec(p->xl.H, p->xl.W, 0, 0);
   return c;
 }
 extern "C" int mmh_bn_bwd_reduce(const MmhBnBwd* p, void* stream) {
@@ -493,14 +543,14 @@ extern "C" int mmh_bn_bwd_reduce(const MmhBnBwd* p, void* stream) {
   MMH_REQ_VEC(p->xl.C);
   BnBwdReduceF f;
   f.cm = bn_common(p);
-  return launch_reduce_ch<2>(f, ext_pixels(p->xl.B, p->xl.H, p->xl.W, 0, 0), p->xl.C / 8, p->xl.C, p->sums, stream);
+  return launch_reduce_ch<2>(f, make_rowgeom(p->xl.B, p->xl.H, p->xl.W, 0, 0), p->xl.C / 8, p->xl.C, p->sums, stream);
 }
 extern "C" int mmh_bn_bwd_apply(const MmhBnBwd* p, void* stream) {
   MMH_CHECK(p && p->dz && p->x && p->coef && p->save && p->k && p->dy, "null argument");
   MMH_REQ_VEC(p->xl.C);
   BnBwdApplyF f;
   f.cm = bn_common(p); f.k = p->k; f.dy = static_cast<act_t*>(p->dy); f.yl = to_layd(p->yl);
-  return launch_pg(f, ext_pixels(p->xl.B, p->xl.H, p->xl.W, 0, 0), p->xl.C / 8, stream);
+  return launch_pg(f, make_rowgeom(p->xl.B, p->xl.H, p->xl.W, 0, 0), p->xl.C / 8, stream);
 }
 extern "C" int mmh_bn_bwd_finalize(const float* sums_global, const float* sums_local, float count, float* k,
                                    float* dgamma, float* dbeta, int32_t C, void* stream) {
@@ -514,7 +564,6 @@ static GateBwdBase gate_common(const MmhGateBwd* p) {
   GateBwdBase c;
   c.dout = p->dout; c.c1 = static_cast<const act_t*>(p->c1); c.x2o = static_cast<const act_t*>(p->x2o);
   c.x3o = static_cast<const act_t*>(p->x3o); c.sl = to_layd(p->sl); c.coef = p->coef; c.save = p->save;
-  c.pd = make_pixdec(p->sl.H, p->sl.W, 0, 0);
   return c;
 }
 extern "C" int mmh_gate_bwd_reduce(const MmhGateBwd* p, void* stream) {
@@ -522,7 +571,7 @@ extern "C" int mmh_gate_bwd_reduce(const MmhGateBwd* p, void* stream) {
   MMH_REQ_VEC(p->sl.C);
   GateBwdReduceF f;
   f.cm = gate_common(p);
-  return launch_reduce_ch<2>(f, ext_pixels(p->sl.B, p->sl.H, p->sl.W, 0, 0), p->sl.C / 8, p->sl.C, p->sums, stream);
+  return launch_reduce_ch<2>(f, make_rowgeom(p->sl.B, p->sl.H, p->sl.W, 0, 0), p->sl.C / 8, p->sl.C, p->sums, stream);
 }
 extern "C" int mmh_gate_bwd_apply(const MmhGateBwd* p, void* stream) {
   MMH_CHECK(p && p->dout && p->c1 && p->x2o && p->x3o && p->coef && p->save && p->k && p->dy1 && p->dy2 && p->dy3,
@@ -533,5 +582,5 @@ extern "C" int mmh_gate_bwd_apply(const MmhGateBwd* p, void* stream) {
   f.ex2 = to_gsd(p->ex2); f.ex3 = to_gsd(p->ex3);
   f.dy1 = static_cast<act_t*>(p->dy1); f.dy2 = static_cast<act_t*>(p->dy2); f.dy3 = static_cast<act_t*>(p->dy3);
   f.yl = to_layd(p->yl);
-  return launch_pg(f, ext_pixels(p->sl.B, p->sl.H, p->sl.W, 0, 0), p->sl.C / 8, stream);
+  return launch_pg(f, make_rowgeom(p->sl.B, p->sl.H, p->sl.W, 0, 0), p->sl.C / 8, stream);
 }

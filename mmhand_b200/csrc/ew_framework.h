@@ -4,7 +4,10 @@
 //   launch_map            one item per call, grid-stride
 //   launch_pg             "pixel x channel-group": a thread keeps its group of 8 channels for its whole life, so the
 //                         per-channel parameters (BN coefficients, means, ...) are loaded into registers once
-//                         (F::Ctx / prep) and every item is two or three 16-byte vector accesses plus arithmetic
+//                         (F::Ctx / prep) and every item is two or three 16-byte vector accesses plus arithmetic.
+//                         Functors are two-phase -- load(pix, g, ctx, In&) then finish(In, g, ctx) -- and the kernel
+//                         issues the loads of kPgUnroll items before finishing any of them: with one 16-byte load in
+//                         flight per thread HBM sits at ~30 % (measured), with four it is bandwidth-bound
 //   launch_reduce_ch      same decomposition for per-channel reductions: registers -> shared memory ->
 //                         one atomic per (block, channel)
 //   launch_reduce_scalar  warp-shuffle + shared-memory reduction to one atomic per block
@@ -12,6 +15,10 @@
 // Grids are sized in multiples of the SM count.
 #pragma once
 #include <stdint.h>
+
+#ifndef MMH_HOST_EMU
+#include <cuda_bf16.h>
+#endif
 
 #include "../../include/mmhand_sm100.h"
 #include "ew_common.h"
@@ -22,27 +29,27 @@ namespace mmh {
 // ------------------------------------------------------------------ layout arithmetic
 struct LayD {
   int B, H, W, Hg, Wg, h0, w0, phase, ld, c0, C;
-  int64_t plane_rows;
+  int plane_rows;     // rows of one parity plane; every grid has < 2^31 rows (checked by the launchers)
 };
 
 inline LayD to_layd(const MmhLay& l) {
   LayD d;
   d.B = l.B; d.H = l.H; d.W = l.W; d.Hg = l.Hg; d.Wg = l.Wg; d.h0 = l.h0; d.w0 = l.w0;
   d.phase = l.phase; d.ld = l.ld; d.c0 = l.c0; d.C = l.C;
-  d.plane_rows = static_cast<int64_t>(l.B) * l.Hg * l.Wg;
+  d.plane_rows = l.B * l.Hg * l.Wg;
   return d;
 }
 
 // element offset of channel c0 of logical pixel (b, h, w); h, w may lie in the halo
 MMH_HD int64_t lay_off(const LayD& l, int b, int h, int w) {
   const int hp = h + l.h0, wp = w + l.w0;
-  int64_t row;
+  int row;            // 32-bit row arithmetic, one widening multiply at the end
   if (!l.phase) {
-    row = (static_cast<int64_t>(b) * l.Hg + hp) * l.Wg + wp;
+    row = (b * l.Hg + hp) * l.Wg + wp;
   } else {
-    row = ((hp & 1) * 2 + (wp & 1)) * l.plane_rows + (static_cast<int64_t>(b) * l.Hg + (hp >> 1)) * l.Wg + (wp >> 1);
+    row = ((hp & 1) * 2 + (wp & 1)) * l.plane_rows + (b * l.Hg + (hp >> 1)) * l.Wg + (wp >> 1);
   }
-  return row * l.ld + l.c0;
+  return static_cast<int64_t>(row) * l.ld + l.c0;
 }
 
 // reflect index i in [-p, n+p) into [0, n) (torch ReflectionPad2d: no edge repeat)
@@ -75,34 +82,37 @@ MMH_HD uint32_t fdiv(uint32_t n, const FastDiv& f) {
 #endif
 }
 
-// pixel index over the window [-lo, H+hi) x [-lo, W+hi) of B images -> (b, h, w)
-struct PixDec {
-  FastDiv we, he;
+// Iteration space of the pixel kernels: B images x rows [-lo, H+hi) x columns [-lo, W+hi). A block works on a
+// run of consecutive columns of ONE row, so that image and row are block-uniform and cost nothing per item.
+struct RowGeom {
+  int n_rows;     // B * (H + lo + hi)   (1 for flat row lists)
+  int h_ext;      // H + lo + hi
+  int n_cols;     // W + lo + hi         (number of rows for flat row lists)
   int lo;
 };
-inline PixDec make_pixdec(int H, int W, int lo, int hi) {
-  PixDec p;
-  p.we = make_fastdiv(W + lo + hi);
-  p.he = make_fastdiv(H + lo + hi);
-  p.lo = lo;
-  return p;
+inline RowGeom make_rowgeom(int B, int H, int W, int lo, int hi) {
+  RowGeom r;
+  r.n_rows = B * (H + lo + hi);
+  r.h_ext = H + lo + hi;
+  r.n_cols = W + lo + hi;
+  r.lo = lo;
+  return r;
 }
-MMH_HD void pix_decode(const PixDec& d, uint32_t pix, int& b, int& h, int& w) {
-  const uint32_t t = fdiv(pix, d.we);
-  w = static_cast<int>(pix - t * d.we.d) - d.lo;
-  const uint32_t u = fdiv(t, d.he);
-  h = static_cast<int>(t - u * d.he.d) - d.lo;
-  b = static_cast<int>(u);
+inline RowGeom make_flatgeom(int64_t rows) {
+  RowGeom r;
+  r.n_rows = 1; r.h_ext = 1; r.n_cols = static_cast<int>(rows); r.lo = 0;
+  return r;
 }
 
-// dropout keep bit of logical NCHW element (b, c, h, w): the same hash as oracle/patn_ref.py::dropout_mask
+// dropout keep bits of logical NCHW elements: the same hash as oracle/patn_ref.py::dropout_mask
 MMH_HD uint32_t mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
   return x;
 }
-MMH_HD float drop_keep2(uint32_t key, int b, int c, int h, int w, int C, int H, int W) {
-  const uint32_t idx = ((static_cast<uint32_t>(b) * C + c) * H + h) * W + w;
-  return (mix32(idx * 0x9E3779B1u + key) & 1u) ? 2.0f : 0.0f;
+// One hash per (pixel, group of 8 channels): bit j of the word decides channel 8*g + j.
+MMH_HD uint32_t drop_bits(uint32_t key, int b, int h, int w, int g, int C, int H, int W) {
+  const uint32_t word = ((static_cast<uint32_t>(b) * H + h) * W + w) * static_cast<uint32_t>((C + 7) / 8) + g;
+  return mix32(word * 0x9E3779B1u + key);
 }
 
 // ------------------------------------------------------------------ 8-wide vector access
@@ -115,6 +125,17 @@ MMH_HD void ld8_bf16(const act_t* p, float (&f)[8]) {
   for (int i = 0; i < 8; ++i) f[i] = act2f(u.v[i]);
 }
 MMH_HD void st8_bf16(act_t* p, const float (&f)[8]) {
+#if defined(__CUDA_ARCH__) && !defined(MMH_EMU_F32)
+  // cvt.rn.bf16x2.f32: same round-to-nearest-even as f2bf
+  uint4 q;
+  __nv_bfloat162 t;
+  t = __floats2bfloat162_rn(f[0], f[1]); q.x = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(f[2], f[3]); q.y = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(f[4], f[5]); q.z = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(f[6], f[7]); q.w = *reinterpret_cast<uint32_t*>(&t);
+  *reinterpret_cast<uint4*>(p) = q;
+  return;
+#endif
   ActX8 u;
 #pragma unroll
   for (int i = 0; i < 8; ++i) u.v[i] = f2act(f[i]);
@@ -133,6 +154,20 @@ MMH_HD void st8_f32(float* p, const float (&f)[8]) {
   *reinterpret_cast<F32x4*>(p) = a;
   *reinterpret_cast<F32x4*>(p + 4) = b;
 }
+struct F32x8 { F32x4 a, b; };
+MMH_HD void ld_raw(const act_t* p, ActX8& u) { u = *reinterpret_cast<const ActX8*>(p); }
+MMH_HD void ld_raw(const float* p, F32x8& u) {
+  u.a = *reinterpret_cast<const F32x4*>(p);
+  u.b = *reinterpret_cast<const F32x4*>(p + 4);
+}
+MMH_HD void cvt8(const ActX8& u, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = act2f(u.v[i]);
+}
+MMH_HD void cvt8(const F32x8& u, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[i] = u.a.v[i]; f[4 + i] = u.b.v[i]; }
+}
 MMH_HD void zero8(float (&f)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) f[i] = 0.f;
@@ -147,32 +182,40 @@ int launch_map(const F& f, int64_t n, void*) {
   return 0;
 }
 template <class F>
-int launch_pg(const F& f, int64_t n_pix, int groups, void*) {
-  MMH_CHECK(n_pix < (int64_t(1) << 31), "too many pixels for one launch");
+int launch_pg(const F& f, const RowGeom& rg, int groups, void*) {
   for (int g = 0; g < groups; ++g) {
     typename F::Ctx c;
     f.prep(g, c);
-    for (uint32_t pix = 0; pix < static_cast<uint32_t>(n_pix); ++pix) f(pix, g, c);
+    for (int row = 0; row < rg.n_rows; ++row)
+      for (int col = 0; col < rg.n_cols; ++col) {
+        const int b = row / rg.h_ext, h = row % rg.h_ext - rg.lo, w = col - rg.lo;
+        typename F::In in;
+        f.load(b, h, w, g, c, in);
+        f.finish(in, b, h, w, g, c);
+      }
   }
   return 0;
 }
 // per-channel reduction: item (pixel, group g) adds NV*8 values into out[v*C + g*8 + j]
 template <int NV, class F>
-int launch_reduce_ch(const F& f, int64_t n_pix, int groups, int C, float* out, void*) {
-  MMH_CHECK(n_pix < (int64_t(1) << 31), "too many pixels for one launch");
+int launch_reduce_ch(const F& f, const RowGeom& rg, int groups, int C, float* out, void*) {
   for (int g = 0; g < groups; ++g) {
     typename F::Ctx c;
     f.prep(g, c);
     double acc[NV][8];
     for (int v = 0; v < NV; ++v)
       for (int j = 0; j < 8; ++j) acc[v][j] = 0.0;
-    for (uint32_t pix = 0; pix < static_cast<uint32_t>(n_pix); ++pix) {
-      float a[NV][8];
-      for (int v = 0; v < NV; ++v) zero8(a[v]);
-      f(pix, g, c, a);
-      for (int v = 0; v < NV; ++v)
-        for (int j = 0; j < 8; ++j) acc[v][j] += a[v][j];
-    }
+    for (int row = 0; row < rg.n_rows; ++row)
+      for (int col = 0; col < rg.n_cols; ++col) {
+        const int b = row / rg.h_ext, h = row % rg.h_ext - rg.lo, w = col - rg.lo;
+        float a[NV][8];
+        for (int v = 0; v < NV; ++v) zero8(a[v]);
+        typename F::In in;
+        f.load(b, h, w, g, c, in);
+        f.accum(in, b, h, w, g, c, a);
+        for (int v = 0; v < NV; ++v)
+          for (int j = 0; j < 8; ++j) acc[v][j] += a[v][j];
+      }
     for (int v = 0; v < NV; ++v)
       for (int j = 0; j < 8; ++j) out[v * C + g * 8 + j] += static_cast<float>(acc[v][j]);
   }
@@ -209,44 +252,79 @@ int launch_map(const F& f, int64_t n, void* stream) {
 // threads per block: the largest multiple of `groups` <= 256 (a thread never changes its channel group)
 inline int pg_threads(int groups) { return (256 / groups) * groups; }
 
+
 template <class F>
-__global__ void __launch_bounds__(256) pg_kernel(const F f, const uint32_t n_pix, const int groups) {
-  const uint32_t ppb = blockDim.x / groups;                  // pixels per block and sweep
+__global__ void __launch_bounds__(256, 2) pg_kernel(const F f, const RowGeom rg, const int groups, const int chunks) {
+  constexpr int U = F::kUnroll;
+  const int ppb = blockDim.x / groups;                       // pixels per block and sweep
   const int g = threadIdx.x % groups;
-  uint32_t pix = blockIdx.x * ppb + threadIdx.x / groups;
-  const uint32_t stride = gridDim.x * ppb;
+  const int lr = threadIdx.x / groups;
   typename F::Ctx c;
   f.prep(g, c);
-  for (; pix < n_pix; pix += stride) f(pix, g, c);
+  const int n_items = rg.n_rows * chunks;                    // item = (row, run of U * ppb columns)
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int row = item / chunks, chunk = item - row * chunks;
+    const int b = row / rg.h_ext, h = row - b * rg.h_ext - rg.lo;
+    const int col0 = chunk * (ppb * U) + lr;
+    typename F::In in[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int col = col0 + u * ppb;
+      if (col < rg.n_cols) f.load(b, h, col - rg.lo, g, c, in[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int col = col0 + u * ppb;
+      if (col < rg.n_cols) f.finish(in[u], b, h, col - rg.lo, g, c);
+    }
+  }
 }
 template <class F>
-int launch_pg(const F& f, int64_t n_pix, int groups, void* stream) {
-  if (n_pix <= 0) return 0;
+int launch_pg(const F& f, const RowGeom& rg, int groups, void* stream) {
+  if (rg.n_rows <= 0 || rg.n_cols <= 0) return 0;
   MMH_CHECK(groups >= 1 && groups <= 256, "channel groups=%d unsupported", groups);
-  MMH_CHECK(n_pix < (int64_t(1) << 31), "too many pixels for one launch");
   const int threads = pg_threads(groups);
   const int ppb = threads / groups;
-  const int64_t want = (n_pix + ppb - 1) / ppb;
-  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+  const int chunks = (rg.n_cols + ppb * F::kUnroll - 1) / (ppb * F::kUnroll);
+  const int64_t want = static_cast<int64_t>(rg.n_rows) * chunks;
+  MMH_CHECK(want < (int64_t(1) << 31), "too many pixels for one launch");
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
   const int blocks = static_cast<int>(want < cap ? want : cap);
-  pg_kernel<F><<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(f, static_cast<uint32_t>(n_pix), groups);
+  pg_kernel<F><<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(f, rg, groups, chunks);
   MMH_CUDA(cudaGetLastError());
   return 0;
 }
 
 template <int NV, class F>
-__global__ void __launch_bounds__(256) reduce_ch_kernel(const F f, const uint32_t n_pix, const int groups, const int C,
-                                                        float* __restrict__ out) {
+__global__ void __launch_bounds__(256, 2) reduce_ch_kernel(const F f, const RowGeom rg, const int groups, const int chunks,
+                                                           const int C, float* __restrict__ out) {
+  constexpr int U = F::kUnroll;
   extern __shared__ float red[];   // [ppb][groups][NV*8]
-  const uint32_t ppb = blockDim.x / groups;
+  const int ppb = blockDim.x / groups;
   const int g = threadIdx.x % groups;
-  const uint32_t lr = threadIdx.x / groups;
+  const int lr = threadIdx.x / groups;
   float acc[NV][8];
 #pragma unroll
   for (int v = 0; v < NV; ++v) zero8(acc[v]);
   typename F::Ctx c;
   f.prep(g, c);
-  for (uint32_t pix = blockIdx.x * ppb + lr; pix < n_pix; pix += gridDim.x * ppb) f(pix, g, c, acc);
+  const int n_items = rg.n_rows * chunks;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int row = item / chunks, chunk = item - row * chunks;
+    const int b = row / rg.h_ext, h = row - b * rg.h_ext - rg.lo;
+    const int col0 = chunk * (ppb * U) + lr;
+    typename F::In in[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int col = col0 + u * ppb;
+      if (col < rg.n_cols) f.load(b, h, col - rg.lo, g, c, in[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int col = col0 + u * ppb;
+      if (col < rg.n_cols) f.accum(in[u], b, h, col - rg.lo, g, c, acc);
+    }
+  }
   float* mine = red + (static_cast<size_t>(lr) * groups + g) * (NV * 8);
 #pragma unroll
   for (int v = 0; v < NV; ++v)
@@ -258,23 +336,24 @@ __global__ void __launch_bounds__(256) reduce_ch_kernel(const F f, const uint32_
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
     const int gg = idx / (NV * 8), vj = idx % (NV * 8);
     float s = 0.f;
-    for (uint32_t l = 0; l < ppb; ++l) s += red[(static_cast<size_t>(l) * groups + gg) * (NV * 8) + vj];
+    for (int l = 0; l < ppb; ++l) s += red[(static_cast<size_t>(l) * groups + gg) * (NV * 8) + vj];
     atomicAdd(out + (vj / 8) * C + gg * 8 + (vj % 8), s);
   }
 }
 template <int NV, class F>
-int launch_reduce_ch(const F& f, int64_t n_pix, int groups, int C, float* out, void* stream) {
-  if (n_pix <= 0) return 0;
+int launch_reduce_ch(const F& f, const RowGeom& rg, int groups, int C, float* out, void* stream) {
+  if (rg.n_rows <= 0 || rg.n_cols <= 0) return 0;
   MMH_CHECK(groups >= 1 && groups <= 256, "channel groups=%d unsupported", groups);
-  MMH_CHECK(n_pix < (int64_t(1) << 31), "too many pixels for one launch");
   const int threads = pg_threads(groups);
   const int ppb = threads / groups;
   const size_t smem = static_cast<size_t>(threads) * NV * 8 * sizeof(float);
-  const int64_t want = (n_pix + ppb * 8 - 1) / (ppb * 8);
-  const int64_t cap = static_cast<int64_t>(num_sms()) * 4;
+  const int chunks = (rg.n_cols + ppb * F::kUnroll - 1) / (ppb * F::kUnroll);
+  const int64_t items = static_cast<int64_t>(rg.n_rows) * chunks;
+  MMH_CHECK(items < (int64_t(1) << 31), "too many pixels for one launch");
+  const int64_t want = (items + 3) / 4;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
   const int blocks = static_cast<int>(want < cap ? (want < 1 ? 1 : want) : cap);
-  reduce_ch_kernel<NV, F><<<blocks, threads, smem, static_cast<cudaStream_t>(stream)>>>(
-      f, static_cast<uint32_t>(n_pix), groups, C, out);
+  reduce_ch_kernel<NV, F><<<blocks, threads, smem, static_cast<cudaStream_t>(stream)>>>(f, rg, groups, chunks, C, out);
   MMH_CUDA(cudaGetLastError());
   return 0;
 }

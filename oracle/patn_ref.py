@@ -51,13 +51,16 @@ def dropout_key(seed, layer_id, step):
 
 
 def dropout_mask(shape, key, device="cpu"):
-    """keep-mask (float 0/1) for an NCHW tensor: bit 0 of mix32(linear NCHW index * 0x9E3779B1 + key)."""
-    n = 1
-    for s in shape:
-        n *= s
-    idx = torch.arange(n, dtype=torch.int64, device=device)
-    h = _mix32(idx * 0x9E3779B1 + key)
-    return (h & 1).to(torch.float32).reshape(shape)
+    """keep-mask (float 0/1) for an NCHW tensor [B, C, H, W]: one hash word per (pixel, group of 8 channels),
+    word = ((b*H + h)*W + w) * ceil(C/8) + c//8; element (b, c, h, w) keeps iff bit (c % 8) of
+    mix32(word * 0x9E3779B1 + key) is set (the same function the CUDA kernels evaluate, ew_framework.h::drop_bits)."""
+    B, C, H, W = shape
+    G = (C + 7) // 8
+    pix = torch.arange(B * H * W, dtype=torch.int64, device=device).view(B, 1, H, W)
+    c = torch.arange(C, dtype=torch.int64, device=device).view(1, C, 1, 1)
+    word = pix * G + c // 8
+    h = _mix32(word * 0x9E3779B1 + key)
+    return ((h >> (c % 8)) & 1).to(torch.float32)
 
 
 class DropCtx:
