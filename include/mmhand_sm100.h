@@ -265,6 +265,21 @@ int mmh_pack_weight_folded(const float* src, int64_t s_n, int64_t s_c, int64_t s
 int mmh_unpack_wgrad(const float* src, float* dst, int64_t s_n, int64_t s_c, int64_t s_t, int32_t N, int32_t C,
                      int32_t T, int32_t accumulate, void* stream);
 /* torch.optim.Adam step (models/MMHandModel.py:90-98) on a flat fp32 buffer; g is multiplied by grad_scale */
+/*
+ * Batched parameter jobs: one launch packs every weight of a network into its tensor-core operands (kind 0:
+ * fp32 master, element (n, c, t) at src[n*s_n + c*s_c + t] -> bf16 dst[t][Np][Cp], zero padded) or folds every
+ * packed weight gradient back into the OIHW .grad tensors (kind 1: dst[n*s_n + c*s_c + t] += src[t][N][C]).
+ * `jobs` lives in device memory (the caller uploads it once); a job owns the tiles [tile_begin, next tile_begin)
+ * of 256 (n, c) pairs each. Replaces ~450 small launches per training step.
+ */
+typedef struct MmhParamJob {
+  const void* src;
+  void* dst;
+  int64_t s_n, s_c;
+  int32_t kind, N, C, T, Np, Cp, tile_begin, reserved;
+} MmhParamJob;
+int mmh_param_jobs(const MmhParamJob* jobs, int32_t n_jobs, int32_t total_tiles, void* stream);
+
 int mmh_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
              int32_t step, float grad_scale, void* stream);
 int mmh_memset(void* p, int32_t byte, int64_t bytes, void* stream);

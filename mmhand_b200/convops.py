@@ -101,23 +101,6 @@ def fwd_plans(lib, g: ConvGeom, a_buf, w_packed, out_buf, Cin_p, Cout_p, bias=No
     return plans
 
 
-def fold_width(k, Cin_p):
-    """Contraction width of one kernel row when the k column taps are folded into it (multiple of 64)."""
-    return (k * Cin_p + 63) // 64 * 64
-
-
-def fwd_plans_folded(lib, g: ConvGeom, a_buf, w_folded, out_buf, Cin_p, Cout_p, bias=None, act=0, out_f32=False):
-    """kw-folded forward of a k x k stride-1 convolution with few input channels: one tap per kernel row whose
-    K = fold_width(k, Cin_p) spans k consecutive pixels of the NHWC grid (overlapping-row view, a_ld = Cin_p).
-    TMA then moves 128-byte rows instead of k separate 32-byte ones. ``a_buf`` needs >= k tail rows of slack."""
-    il, ol = g.in_lay, g.out_lay
-    assert g.kind == 's1' and il.ld == Cin_p
-    taps = [(kh, kh * il.Wg) for kh in range(g.k)]
-    d = conv_desc(a_buf, il.rows, il.ld, fold_width(g.k, Cin_p), w_folded, g.k, Cout_p, taps, il.plane_rows, il.Hg,
-                  il.Wg, g.Ho, g.Wo, out_buf, ol.ld, out_f32=out_f32, bias=bias, act=act)
-    return [ConvPlan(lib, d)]
-
-
 def dgrad_plans(lib, g: ConvGeom, dy_buf, wd_packed, dx_buf, Cin_p, Cout_p, dx_ld=None):
     """Plans of the data gradient: A = dY (layout g.out_lay), output = gradient of g.in_lay (every row)."""
     plans = []

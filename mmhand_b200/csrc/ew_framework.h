@@ -249,6 +249,16 @@ int launch_map(const F& f, int64_t n, void* stream) {
   return 0;
 }
 
+// grid = (column split, rows per image incl. halo, images); the column split grows until there are about
+// `per_sm` blocks per SM (flat row lists: rows = images = 1 and the split is the whole grid)
+inline dim3 row_grid(const RowGeom& rg, int max_split, int per_sm) {
+  const int64_t rows = rg.n_rows;
+  int64_t split = (static_cast<int64_t>(num_sms()) * per_sm + rows - 1) / rows;
+  if (split > max_split) split = max_split;
+  if (split < 1) split = 1;
+  return dim3(static_cast<unsigned>(split), static_cast<unsigned>(rg.h_ext), static_cast<unsigned>(rg.n_rows / rg.h_ext));
+}
+
 // threads per block: the largest multiple of `groups` <= 256 (a thread never changes its channel group)
 inline int pg_threads(int groups) { return (256 / groups) * groups; }
 
@@ -261,10 +271,10 @@ __global__ void __launch_bounds__(256, 2) pg_kernel(const F f, const RowGeom rg,
   const int lr = threadIdx.x / groups;
   typename F::Ctx c;
   f.prep(g, c);
-  const int n_items = rg.n_rows * chunks;                    // item = (row, run of U * ppb columns)
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int row = item / chunks, chunk = item - row * chunks;
-    const int b = row / rg.h_ext, h = row - b * rg.h_ext - rg.lo;
+  // grid = (column split, row, image): image and row come from special registers, i.e. they are uniform and
+  // every address term that depends on them is computed once per block in the uniform datapath
+  const int b = blockIdx.z, h = static_cast<int>(blockIdx.y) - rg.lo;
+  for (int chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
     const int col0 = chunk * (ppb * U) + lr;
     typename F::In in[U];
 #pragma unroll
@@ -286,11 +296,8 @@ int launch_pg(const F& f, const RowGeom& rg, int groups, void* stream) {
   const int threads = pg_threads(groups);
   const int ppb = threads / groups;
   const int chunks = (rg.n_cols + ppb * F::kUnroll - 1) / (ppb * F::kUnroll);
-  const int64_t want = static_cast<int64_t>(rg.n_rows) * chunks;
-  MMH_CHECK(want < (int64_t(1) << 31), "too many pixels for one launch");
-  const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
-  const int blocks = static_cast<int>(want < cap ? want : cap);
-  pg_kernel<F><<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(f, rg, groups, chunks);
+  const dim3 grid = row_grid(rg, chunks, 8);
+  pg_kernel<F><<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(f, rg, groups, chunks);
   MMH_CUDA(cudaGetLastError());
   return 0;
 }
@@ -308,10 +315,8 @@ __global__ void __launch_bounds__(256, 2) reduce_ch_kernel(const F f, const RowG
   for (int v = 0; v < NV; ++v) zero8(acc[v]);
   typename F::Ctx c;
   f.prep(g, c);
-  const int n_items = rg.n_rows * chunks;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int row = item / chunks, chunk = item - row * chunks;
-    const int b = row / rg.h_ext, h = row - b * rg.h_ext - rg.lo;
+  const int b = blockIdx.z, h = static_cast<int>(blockIdx.y) - rg.lo;
+  for (int chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
     const int col0 = chunk * (ppb * U) + lr;
     typename F::In in[U];
 #pragma unroll
@@ -348,12 +353,8 @@ int launch_reduce_ch(const F& f, const RowGeom& rg, int groups, int C, float* ou
   const int ppb = threads / groups;
   const size_t smem = static_cast<size_t>(threads) * NV * 8 * sizeof(float);
   const int chunks = (rg.n_cols + ppb * F::kUnroll - 1) / (ppb * F::kUnroll);
-  const int64_t items = static_cast<int64_t>(rg.n_rows) * chunks;
-  MMH_CHECK(items < (int64_t(1) << 31), "too many pixels for one launch");
-  const int64_t want = (items + 3) / 4;
-  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
-  const int blocks = static_cast<int>(want < cap ? (want < 1 ? 1 : want) : cap);
-  reduce_ch_kernel<NV, F><<<blocks, threads, smem, static_cast<cudaStream_t>(stream)>>>(f, rg, groups, chunks, C, out);
+  const dim3 grid = row_grid(rg, (chunks + 3) / 4, 4);
+  reduce_ch_kernel<NV, F><<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(f, rg, groups, chunks, C, out);
   MMH_CUDA(cudaGetLastError());
   return 0;
 }

@@ -56,9 +56,47 @@ struct UnpackF {
   }
 };
 
+struct ParamJobsF {
+  const MmhParamJob* jobs; int n_jobs;
+  // item = (tile, lane): the job is found by bisection on tile_begin (uniform per block)
+  MMH_HD void operator()(int64_t i) const {
+    const int tile = static_cast<int>(i >> 8), lane = static_cast<int>(i & 255);
+    int lo = 0, hi = n_jobs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+    }
+    const MmhParamJob& j = jobs[lo];
+    const int e = (tile - j.tile_begin) * 256 + lane;        // (n, c) pair, c fastest
+    if (j.kind == 0) {
+      if (e >= j.Np * j.Cp) return;
+      const int n = e / j.Cp, c = e - n * j.Cp;
+      const bool live = n < j.N && c < j.C;
+      const float* src = static_cast<const float*>(j.src) + n * j.s_n + c * j.s_c;
+      act_t* dst = static_cast<act_t*>(j.dst) + e;
+      const int64_t plane = static_cast<int64_t>(j.Np) * j.Cp;
+      for (int t = 0; t < j.T; ++t) dst[t * plane] = f2act(live ? src[t] : 0.f);
+    } else {
+      if (e >= j.N * j.C) return;
+      const int n = e / j.C, c = e - n * j.C;
+      const float* src = static_cast<const float*>(j.src) + e;
+      float* dst = static_cast<float*>(j.dst) + n * j.s_n + c * j.s_c;
+      const int64_t plane = static_cast<int64_t>(j.N) * j.C;
+      for (int t = 0; t < j.T; ++t) dst[t] += src[t * plane];
+    }
+  }
+};
+
 }  // namespace mmh
 
 using namespace mmh;
+
+extern "C" int mmh_param_jobs(const MmhParamJob* jobs, int32_t n_jobs, int32_t total_tiles, void* stream) {
+  MMH_CHECK(jobs && n_jobs >= 1 && total_tiles >= 0, "bad argument");
+  ParamJobsF f;
+  f.jobs = jobs; f.n_jobs = n_jobs;
+  return launch_map(f, static_cast<int64_t>(total_tiles) * 256, stream);
+}
 
 extern "C" int mmh_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                         float eps, int32_t step, float grad_scale, void* stream) {

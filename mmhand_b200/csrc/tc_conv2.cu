@@ -37,7 +37,7 @@ namespace mmh {
 
 constexpr int kC2Threads = 192;
 constexpr int kC2MaxGroups = 16;
-constexpr int kC2MaxA = 4;
+constexpr int kC2MaxA = 8;
 constexpr int kC2MaxB = 8;
 constexpr uint32_t kC2TmemCols = 512;
 constexpr uint32_t kC2AccStride = 256;
@@ -45,6 +45,7 @@ constexpr uint32_t kC2AccStride = 256;
 struct Conv2Params {
   int32_t n_groups, cpt, KC, ksteps;
   int32_t N, BN, tiles_n, tiles_m, M;
+  int32_t MB;                      // 128-row blocks per tile sharing every weight tile (narrow N, NCTA = 1)
   int32_t Hg, Wg, Hv, Wv;
   int32_t out_f32, out_ld, out_wg, out_sh, out_sw, out_h0, out_w0, zero_invalid, act, n_store;
   int64_t out_img_rows;
@@ -114,7 +115,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
       for (int tile = first_tile; tile < n_tiles; tile += tile_step) {
         const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
-        const int m0 = (tm * NCTA + static_cast<int>(cta)) * 128;
+        const int m0 = (tm * NCTA + static_cast<int>(cta)) * 128 * p.MB;
         const int n0 = tn * p.BN + static_cast<int>(cta * p.b_rows);
         for (int g = 0; g < p.n_groups; ++g) {
           const int t_begin = p.g_first[g], t_end = p.g_first[g + 1];
@@ -165,7 +166,8 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kC2AccStride;
-        uint32_t accum = 0;
+        uint32_t n_done = 0;
+        const uint32_t mb_bytes = 128 * p.row_bytes;
         for (int g = 0; g < p.n_groups; ++g) {
           const int t_begin = p.g_first[g], t_end = p.g_first[g + 1];
           for (int kc = 0; kc < p.cpt; ++kc) {
@@ -177,15 +179,16 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               mbar_wait(&fullB[sb], pb);
               tc_fence_after();
               const uint32_t wb = b_base + sb * p.b_slot_bytes;
-              for (int j = 0; j < nb; ++j) {
+              for (int j = 0; j < nb; ++j, ++n_done) {
                 const uint32_t ta = wa + static_cast<uint32_t>(p.rel[t0 + j]) * p.row_bytes;
                 const uint32_t tb = wb + j * p.b_tile_stride;
-                for (int k = 0; k < p.ksteps; ++k) {
-                  const uint64_t ad = desc_hi | static_cast<uint64_t>(((ta + k * 32) >> 4) & 0x3FFF);
-                  const uint64_t bd = desc_hi | static_cast<uint64_t>(((tb + k * 32) >> 4) & 0x3FFF);
-                  if (NCTA == 2) umma_bf16_pair(d_tmem, ad, bd, idesc, accum);
-                  else umma_bf16(d_tmem, ad, bd, idesc, accum);
-                  accum = 1;
+                for (int mb = 0; mb < p.MB; ++mb) {
+                  for (int k = 0; k < p.ksteps; ++k) {
+                    const uint64_t ad = desc_hi | static_cast<uint64_t>(((ta + mb * mb_bytes + k * 32) >> 4) & 0x3FFF);
+                    const uint64_t bd = desc_hi | static_cast<uint64_t>(((tb + k * 32) >> 4) & 0x3FFF);
+                    if (NCTA == 2) umma_bf16_pair(d_tmem + mb * p.BN, ad, bd, idesc, (n_done | k) != 0 ? 1u : 0u);
+                    else umma_bf16(d_tmem + mb * p.BN, ad, bd, idesc, (n_done | k) != 0 ? 1u : 0u);
+                  }
                 }
               }
               if (NCTA == 2) umma_commit_pair(&emptyB[sb]); else umma_commit(&emptyB[sb]);
@@ -209,45 +212,47 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = first_tile; tile < n_tiles; tile += tile_step) {
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
-      const int q = (tm * NCTA + static_cast<int>(cta)) * 128 + row;
       const int n0 = tn * p.BN;
-      const int img = q / hw;
-      const int rem = q - img * hw;
-      const int h = rem / p.Wg;
-      const int x = rem - h * p.Wg;
-      const bool in_range = q < p.M;
-      const bool valid = in_range && h < p.Hv && x < p.Wv;
-      const bool do_store = valid || (in_range && p.zero_invalid);
-      const int64_t orow = static_cast<int64_t>(img) * p.out_img_rows +
-                           static_cast<int64_t>(h * p.out_sh + p.out_h0) * p.out_wg + (x * p.out_sw + p.out_w0);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + acc * kC2AccStride + (static_cast<uint32_t>(quad * 32) << 16);
-      for (int j = 0; j < nchunks; ++j) {
-        uint32_t v[16];
-        tmem_ld16(t_addr + j * 16, v);
-        tmem_ld_wait();
-        const int nc = n0 + j * 16;
-        if (do_store && nc < p.n_store) {
-          float f[16];
+      for (int mb = 0; mb < p.MB; ++mb) {
+        const int q = ((tm * NCTA + static_cast<int>(cta)) * p.MB + mb) * 128 + row;
+        const int img = q / hw;
+        const int rem = q - img * hw;
+        const int h = rem / p.Wg;
+        const int x = rem - h * p.Wg;
+        const bool in_range = q < p.M;
+        const bool valid = in_range && h < p.Hv && x < p.Wv;
+        const bool do_store = valid || (in_range && p.zero_invalid);
+        const int64_t orow = static_cast<int64_t>(img) * p.out_img_rows +
+                             static_cast<int64_t>(h * p.out_sh + p.out_h0) * p.out_wg + (x * p.out_sw + p.out_w0);
+        const uint32_t t_addr = tmem_base + acc * kC2AccStride + mb * p.BN + (static_cast<uint32_t>(quad * 32) << 16);
+        for (int j = 0; j < nchunks; ++j) {
+          uint32_t v[16];
+          tmem_ld16(t_addr + j * 16, v);
+          tmem_ld_wait();
+          const int nc = n0 + j * 16;
+          if (do_store && nc < p.n_store) {
+            float f[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float val = valid ? __uint_as_float(v[i]) : 0.f;
-            if (valid) {
-              if (p.bias != nullptr) val += __ldg(p.bias + nc + i);
-              if (p.act == 1) val = fmaxf(val, 0.f);
-              else if (p.act == 2) val = tanhf(val);
+            for (int i = 0; i < 16; ++i) {
+              float val = valid ? __uint_as_float(v[i]) : 0.f;
+              if (valid) {
+                if (p.bias != nullptr) val += __ldg(p.bias + nc + i);
+                if (p.act == 1) val = fmaxf(val, 0.f);
+                else if (p.act == 2) val = tanhf(val);
+              }
+              f[i] = val;
             }
-            f[i] = val;
-          }
-          if (p.out_f32) {
-            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.out_ld + nc);
+            if (p.out_f32) {
+              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.out_ld + nc);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-          } else {
-            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + orow * p.out_ld + nc);
-            dst[0] = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
-            dst[1] = make_uint4(pack2(f[8], f[9]), pack2(f[10], f[11]), pack2(f[12], f[13]), pack2(f[14], f[15]));
+              for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            } else {
+              uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + orow * p.out_ld + nc);
+              dst[0] = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+              dst[1] = make_uint4(pack2(f[8], f[9]), pack2(f[10], f[11]), pack2(f[12], f[13]), pack2(f[14], f[15]));
+            }
           }
         }
       }
@@ -353,7 +358,19 @@ int mmh_conv2_create(const MmhConvDesc* d, MmhConv2** out_plan) {
   k.n_groups = ng;
   for (int g = 0; g < ng; ++g) gtaps_max = std::max(gtaps_max, k.g_first[g + 1] - k.g_first[g]);
 
-  const int need_rows = 128 + span_max;
+  int mb = 1;
+  if (ncta == 1 && k.BN <= 128) {
+    mb = 256 / k.BN;
+    if (mb > 4) mb = 4;
+    while (mb > 1 && (static_cast<uint32_t>(128 * mb + span_max) * k.row_bytes > 49152u ||
+                      static_cast<int64_t>((d->M + 128 * mb - 1) / (128 * mb)) * k.tiles_n < 2 * num_sms()))
+      mb >>= 1;
+  }
+  mb = env_int("MMH_CONV_MB", mb);
+  if (mb < 1 || mb * k.BN > 256 || ncta != 1) mb = 1;
+  k.MB = mb;
+  k.tiles_m = (k.M + 128 * ncta * mb - 1) / (128 * ncta * mb);
+  const int need_rows = 128 * mb + span_max;
   k.a_boxes = (need_rows + 255) / 256;
   k.a_box_rows = ((need_rows + k.a_boxes - 1) / k.a_boxes + 7) / 8 * 8;
   k.a_box_bytes = k.a_box_rows * k.row_bytes;
@@ -367,7 +384,7 @@ int mmh_conv2_create(const MmhConvDesc* d, MmhConv2** out_plan) {
   k.b_batch = batch;
   k.b_slot_bytes = k.b_batch * k.b_tile_stride;
   const uint32_t budget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/;
-  k.nA = env_int("MMH_CONV_NA", k.a_slot_bytes <= 16384 ? 4 : 2);
+  k.nA = env_int("MMH_CONV_NA", k.a_slot_bytes <= 8192 ? 8 : (k.a_slot_bytes <= 20480 ? 4 : 2));
   if (k.nA > kC2MaxA) k.nA = kC2MaxA;
   if (k.nA * k.a_slot_bytes + 2 * k.b_slot_bytes > budget) { set_error("conv tile does not fit in shared memory"); return fail(); }
   k.nB = (budget - k.nA * k.a_slot_bytes) / k.b_slot_bytes;

@@ -90,28 +90,18 @@ class ConvL:
         self.weight, self.transposed, self.bias, self.act, self.out_f32 = weight, transposed, bias, act, out_f32
         self.need_dx = need_dx
         self.T = geom.k * geom.k
-        # few-channel k x k stems: fold the k column taps into the contraction (128-byte TMA rows instead of 32)
-        self.fold = False   # superseded: the window kernel reuses one activation window per kernel row (tc_conv2.cu)
-        if x_buf is not None:
-            self.x = x_buf
-        else:
-            self.x_store = ops.zeros(geom.in_lay.rows + 2 * geom.k, self.Cin_p)    # tail slack for folded views
-            self.x = self.x_store[:geom.in_lay.rows]
+        self.x = x_buf if x_buf is not None else ops.zeros(geom.in_lay.rows, self.Cin_p)
         self.raw = raw_buf if raw_buf is not None else ops.zeros(
             geom.out_lay.rows, self.Cout_p, dtype=torch.float32 if out_f32 else None)
         self.bias_p = None
         if bias is not None:
             self.bias_p = ops.zeros(self.Cout_p, dtype=torch.float32)
-        if self.fold:
-            self.Kw = convops.fold_width(geom.k, self.Cin_p)
-            self.wp = ops.zeros(geom.k, self.Cout_p, self.Kw)
-            self.fwd = convops.fwd_plans_folded(ops.lib, geom, self.x, self.wp, self.raw, self.Cin_p, self.Cout_p,
-                                                bias=self.bias_p, act=act, out_f32=out_f32)
-        else:
-            self.wp = ops.zeros(self.T, self.Cout_p, self.Cin_p)
-            self.fwd = convops.fwd_plans(ops.lib, geom, self.x, self.wp, self.raw, self.Cin_p, self.Cout_p,
-                                         bias=self.bias_p, act=act, out_f32=out_f32)
+        self.wp = ops.zeros(self.T, self.Cout_p, self.Cin_p)
+        self.fwd = convops.fwd_plans(ops.lib, geom, self.x, self.wp, self.raw, self.Cin_p, self.Cout_p,
+                                     bias=self.bias_p, act=act, out_f32=out_f32)
         self.bwd_ready = False
+        self.has_wgrad = False
+        self.dw = None
 
     # weight strides (n = out channel, c = in channel, t = tap) of the fp32 master tensor
     def _strides(self):
@@ -121,17 +111,31 @@ class ConvL:
         return w.stride(0), w.stride(1), 1
 
     def pack(self, with_dgrad):
+        """Immediate (one launch per operand) packing; the engines batch the same work through pack_jobs()."""
         ops = self.eng.ops
         sn, sc, st = self._strides()
-        if self.fold:
-            ops.pack_weight_folded(self.weight, sn, sc, st, self.Cout, self.Cin, self.g.k, self.g.k, self.wp,
-                                   self.Cout_p, self.Cin_p, self.Kw)
-        else:
-            ops.pack_weight(self.weight, sn, sc, st, self.Cout, self.Cin, self.T, self.wp, self.Cout_p, self.Cin_p)
+        ops.pack_weight(self.weight, sn, sc, st, self.Cout, self.Cin, self.T, self.wp, self.Cout_p, self.Cin_p)
         if with_dgrad and self.need_dx and self.bwd_ready:
             ops.pack_weight(self.weight, sc, sn, st, self.Cin, self.Cout, self.T, self.wd, self.Cin_p, self.Cout_p)
+        self.pack_bias()
+
+    def pack_bias(self):
         if self.bias is not None:
-            ops.unpack_wgrad(self.bias, self.bias_p, 1, 0, 0, self.Cout, 1, 1, False)      # fp32 copy
+            self.eng.ops.unpack_wgrad(self.bias, self.bias_p, 1, 0, 0, self.Cout, 1, 1, False)      # fp32 copy
+
+    def pack_jobs(self):
+        """Batched-kernel job descriptions (mmh_param_jobs kind 0) of this conv's tensor-core operands."""
+        sn, sc, _ = self._strides()
+        jobs = [dict(kind=0, src=self.weight, dst=self.wp, s_n=sn, s_c=sc, N=self.Cout, C=self.Cin, T=self.T,
+                     Np=self.Cout_p, Cp=self.Cin_p)]
+        if self.need_dx and self.bwd_ready:
+            jobs.append(dict(kind=0, src=self.weight, dst=self.wd, s_n=sc, s_c=sn, N=self.Cin, C=self.Cout, T=self.T,
+                             Np=self.Cin_p, Cp=self.Cout_p))
+        return jobs
+
+    def unpack_job(self):
+        sn, sc, _ = self._strides()
+        return dict(kind=1, src=self.dw, dst=self.weight.grad, s_n=sn, s_c=sc, N=self.Cout, C=self.Cin, T=self.T)
 
     def prepare_backward(self, dy_key, dx_key, need_wgrad=True):
         if self.bwd_ready:
@@ -142,14 +146,22 @@ class ConvL:
             self.dx = self.eng.scratch(("dx", dx_key, g.in_lay.rows, self.Cin_p), g.in_lay.rows, self.Cin_p)
             self.wd = ops.zeros(self.T, self.Cin_p, self.Cout_p)
             self.dgrad = convops.dgrad_plans(ops.lib, g, self.dy, self.wd, self.dx, self.Cin_p, self.Cout_p)
-        if need_wgrad:
-            self.dw = ops.zeros(self.T, self.Cout, self.Cin, dtype=torch.float32)
-            self.wgrad = convops.wgrad_plans(ops.lib, g, self.x, self.dy, self.dw, self.Cin_p, self.Cout_p,
-                                             self.Cin, self.Cout)
-            if self.bias is not None:
-                self.dbias = ops.zeros(2 * self.Cout_p, dtype=torch.float32)
-        self.has_wgrad = need_wgrad
+        if need_wgrad and self.bias is not None:
+            self.dbias = ops.zeros(2 * self.Cout_p, dtype=torch.float32)
+        self.has_wgrad = need_wgrad          # the packed-gradient buffer is bound by the engine (bind_dw)
         self.bwd_ready = True
+
+    def dw_numel(self):
+        return self.T * self.Cout * self.Cin if self.has_wgrad else 0
+
+    def bind_dw(self, flat, off):
+        """Packed weight gradient [T][Cout][Cin] fp32 = a slice of the engine's flat buffer (one memset, one unpack
+        launch per backward pass)."""
+        n = self.dw_numel()
+        self.dw = flat[off:off + n].view(self.T, self.Cout, self.Cin)
+        self.wgrad = convops.wgrad_plans(self.eng.ops.lib, self.g, self.x, self.dy, self.dw, self.Cin_p, self.Cout_p,
+                                         self.Cin, self.Cout)
+        return off + n
 
     def run_fwd(self):
         for p in self.fwd:
@@ -159,11 +171,8 @@ class ConvL:
         """Consumes self.dy. Weight gradient accumulates into weight.grad; data gradient lands in self.dx."""
         ops = self.eng.ops
         if want_wgrad and self.has_wgrad:
-            ops.memset0(self.dw)
             for p in self.wgrad:
                 ops.run_wgrad(p, (self.name, "wgrad"))
-            sn, sc, stt = self._strides()
-            ops.unpack_wgrad(self.dw, self.weight.grad, sn, sc, stt, self.Cout, self.Cin, self.T, True)
             if self.bias is not None:
                 ops.memset0(self.dbias)
                 ops.bn_stats(self.dy, self.g.out_lay.rows, self.Cout_p, self.Cout_p, self.dbias)
@@ -244,13 +253,39 @@ class EngineBase:
         raise NotImplementedError
 
     def repack(self, force=False):
-        self.store.ensure()
+        """bf16 tensor-core operands of every weight (forward and, once backward is prepared, data-gradient form):
+        one batched launch per optimiser step."""
+        if self.store.ensure():
+            self._pack_table = self._unpack_table = None        # parameter storage moved: rebuild the job tables
         v = self.store.versions()
         if not force and v == self.packed_version:
             return
+        key = tuple(c.bwd_ready for c in self.convs())
+        if getattr(self, "_pack_table", None) is None or self._pack_key != key:
+            jobs = [j for c in self.convs() for j in c.pack_jobs()]
+            self._pack_table, self._pack_key = self.ops.make_param_jobs(jobs), key
+        self.ops.run_param_jobs(self._pack_table)
         for c in self.convs():
-            c.pack(True)
+            c.pack_bias()
         self.packed_version = v
+
+    def bind_wgrad(self):
+        """Flat packed-gradient buffer behind every conv's dw + the batched unpack table."""
+        convs = [c for c in self.convs() if c.has_wgrad]
+        self.dw_all = self.ops.zeros(sum(c.dw_numel() for c in convs), dtype=torch.float32)
+        off = 0
+        for c in convs:
+            off = c.bind_dw(self.dw_all, off)
+        self._unpack_table = None
+
+    def begin_wgrad(self):
+        self.ops.memset0(self.dw_all)
+
+    def end_wgrad(self):
+        if getattr(self, "_unpack_table", None) is None:
+            self.store.ensure()
+            self._unpack_table = self.ops.make_param_jobs([c.unpack_job() for c in self.convs() if c.has_wgrad])
+        self.ops.run_param_jobs(self._unpack_table)
 
     def _stage_fwd(self, conv: ConvL, bn: BNL, training):
         conv.run_fwd()
@@ -352,6 +387,7 @@ class GeneratorEngine(EngineBase):
         self.up2.prepare_backward("up2", "up2")
         self.cout.prepare_backward("out", "out")
         self.dtrunk = self.ops.zeros(self.B * self.h4 * self.w4, self.dim, dtype=torch.float32)
+        self.bind_wgrad()
         self.bwd_ready = True
         self.repack(force=True)
 
@@ -421,6 +457,7 @@ class GeneratorEngine(EngineBase):
         h4, w4, dim = self.h4, self.w4, self.dim
         step, net_id = self.step, self.net_id
         ops.step = step
+        self.begin_wgrad()
         ops.tanh_bwd(dfake, self.fake, self.cout.dy, self.cout.g.out_lay, self.out_nc)
         self.cout.run_bwd()
         self._stage_bwd(self.up2, self.bnu2, [self.cout.dx_source()], True, False, 0)
@@ -457,6 +494,7 @@ class GeneratorEngine(EngineBase):
                             trunk=self.dtrunk if s == 0 else None)
             self._stage_bwd(st["d1"], st["bn1"], [st["d2"].dx_source()], True, False, 0)
             self._stage_bwd(st["c7"], st["bn7"], [st["d1"].dx_source()], True, False, 0, want_dx=False)
+        self.end_wgrad()
 
 
 # ====================================================================================================
@@ -502,6 +540,7 @@ class DiscriminatorEngine(EngineBase):
             b["c1"].prepare_backward("c1", "c1")
             b["c2"].prepare_backward("c2", "c2")
         self.dtrunk = self.ops.zeros(self.B * self.h4 * self.w4, self.dim, dtype=torch.float32)
+        self.bind_wgrad()
         self.bwd_ready = True
         self.repack(force=True)
 
@@ -549,6 +588,8 @@ class DiscriminatorEngine(EngineBase):
         ops, B, h4, w4, dim = self.ops, self.B, self.h4, self.w4, self.dim
         step, net_id = self.step, self.net_id
         ops.step = step
+        if want_wgrad:
+            self.begin_wgrad()
         dcur = dlogits
         for i in range(self.nb - 1, -1, -1):
             b = self.blocks[i]
@@ -566,6 +607,8 @@ class DiscriminatorEngine(EngineBase):
         self._stage_bwd(self.d1, self.bn1, [self.d2.dx_source()], True, False, 0, want_wgrad=want_wgrad)
         self._stage_bwd(self.c7, self.bn7, [self.d1.dx_source()], True, False, 0, want_wgrad=want_wgrad,
                         want_dx=want_input_grad)
+        if want_wgrad:
+            self.end_wgrad()
         return self.c7.dx_source() if want_input_grad else None
 
 

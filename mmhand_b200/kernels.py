@@ -295,6 +295,26 @@ class Ops:
         self._run(self.lib.mmh_unpack_wgrad, (_p(src), _p(dst), s_n, s_c, s_t, N, Cc, T, 1 if accumulate else 0,
                                               self.st()))
 
+    def make_param_jobs(self, jobs):
+        """jobs: list of dicts (kind, src, dst, s_n, s_c, N, C, T, Np, Cp) -> (device table, n, tiles, keep-alive)."""
+        arr = (L.ParamJob * len(jobs))()
+        tile = 0
+        for a, j in zip(arr, jobs):
+            a.src, a.dst = j["src"].data_ptr(), j["dst"].data_ptr()
+            a.s_n, a.s_c, a.kind = j["s_n"], j["s_c"], j["kind"]
+            a.N, a.C, a.T, a.Np, a.Cp = j["N"], j["C"], j["T"], j.get("Np", j["N"]), j.get("Cp", j["C"])
+            a.tile_begin = tile
+            pairs = a.Np * a.Cp if a.kind == 0 else a.N * a.C
+            tile += (pairs + 255) // 256
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
+        table = host.to(self.device)
+        return table, len(jobs), tile, [j["src"] for j in jobs] + [j["dst"] for j in jobs]
+
+    def run_param_jobs(self, packed):
+        table, n, tiles, keep = packed
+        if n:
+            self._run(self.lib.mmh_param_jobs, (table.data_ptr(), n, tiles, self.st()), keep=(table, keep))
+
     def adam(self, p, g, m, v, lr, b1, b2, eps, step, grad_scale=1.0, dyn=None):
         """dyn: optional callable() -> (lr, step) evaluated again on every replay."""
         patch = None

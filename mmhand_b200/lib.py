@@ -43,6 +43,12 @@ class WgradDesc(C.Structure):
     ]
 
 
+class ParamJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("s_n", C.c_int64), ("s_c", C.c_int64),
+                ("kind", C.c_int32), ("N", C.c_int32), ("C", C.c_int32), ("T", C.c_int32), ("Np", C.c_int32),
+                ("Cp", C.c_int32), ("tile_begin", C.c_int32), ("reserved", C.c_int32)]
+
+
 class Lay(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
                 ("B", "H", "W", "Hg", "Wg", "h0", "w0", "phase", "ld", "c0", "C", "reserved")]
@@ -159,6 +165,7 @@ _SIMPLE_SIGS = {
     "mmh_pack_weight": [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _vp],
     "mmh_pack_weight_folded": [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp],
     "mmh_unpack_wgrad": [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp],
+    "mmh_param_jobs": [_vp, _i32, _i32, _vp],
     "mmh_adam": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _f32, _vp],
     "mmh_memset": [_vp, _i32, _i64, _vp],
     "mmh_heatmap_rasterize": [_vp, _i64, _i32, _i32, _f64, _f64, _vp, _vp],
