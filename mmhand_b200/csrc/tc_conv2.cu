@@ -45,6 +45,7 @@ constexpr uint32_t kC2AccStride = 256;
 struct Conv2Params {
   int32_t n_groups, cpt, KC, ksteps;
   int32_t N, BN, tiles_n, tiles_m, M;
+  int32_t dbg;                     // MMH_C2_DEBUG: 1 skip A loads, 2 skip B loads, 4 skip MMAs, 8 skip stores (timing only)
   int32_t MB;                      // 128-row blocks per tile sharing every weight tile (narrow N, NCTA = 1)
   int32_t Hg, Wg, Hv, Wv;
   int32_t out_f32, out_ld, out_wg, out_sh, out_sw, out_h0, out_w0, zero_invalid, act, n_store;
@@ -57,7 +58,7 @@ struct Conv2Params {
   const float* bias;
   int32_t g_first[kC2MaxGroups + 1];
   int32_t g_min[kC2MaxGroups];
-  int32_t rel[MMH_MAX_TAPS];      // row offset of the tap inside its group's window
+  int32_t rel16[MMH_MAX_TAPS];    // byte offset / 16 of the tap's first row inside its group's window
   int32_t w_slot[MMH_MAX_TAPS];
 };
 
@@ -124,7 +125,9 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const int ch = kc * p.KC;
             mbar_wait(&emptyA[sa], pa ^ 1);
             uint8_t* dst = a_ring + static_cast<size_t>(sa) * p.a_slot_bytes;
-            if (NCTA == 2) {
+            if (p.dbg & 1) {
+              if (leader) mbar_arrive(&fullA[sa]);
+            } else if (NCTA == 2) {
               const uint32_t bar = mapa_shared(smem_u32(&fullA[sa]), 0);
               if (leader) mbar_expect_tx(&fullA[sa], 2 * p.a_boxes * p.a_box_bytes);
               for (uint32_t b = 0; b < p.a_boxes; ++b)
@@ -139,7 +142,9 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               const int nb = min(static_cast<int>(p.b_batch), t_end - t0);
               mbar_wait(&emptyB[sb], pb ^ 1);
               uint8_t* bd = b_ring + static_cast<size_t>(sb) * p.b_slot_bytes;
-              if (NCTA == 2) {
+              if (p.dbg & 2) {
+                if (leader) mbar_arrive(&fullB[sb]);
+              } else if (NCTA == 2) {
                 const uint32_t bar = mapa_shared(smem_u32(&fullB[sb]), 0);
                 if (leader) mbar_expect_tx(&fullB[sb], 2 * nb * p.b_tile_bytes);
                 for (int j = 0; j < nb; ++j)
@@ -157,45 +162,60 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     if (leader && elect_one()) {
-      // ===== MMA issuer
+      // ===== MMA issuer. Everything the loop adds up is pre-encoded in descriptor units (16 bytes) so that one MMA
+      // costs two uniform adds: descriptor low word = (address >> 4) | LBO field, high word constant.
       const uint32_t idesc = make_idesc_bf16(128 * NCTA, p.BN, 0, 0);
-      const uint64_t desc_hi = make_smem_desc(0, 16, p.sbo, p.swz);
-      const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_ring);
+      const uint64_t desc_proto = make_smem_desc(0, 16, p.sbo, p.swz);
+      const uint32_t desc_hi32 = static_cast<uint32_t>(desc_proto >> 32);
+      const uint32_t a_base = (smem_u32(a_ring) >> 4) + static_cast<uint32_t>(desc_proto);
+      const uint32_t b_base = (smem_u32(b_ring) >> 4) + static_cast<uint32_t>(desc_proto);
+      const uint32_t a_slot16 = p.a_slot_bytes >> 4, b_slot16 = p.b_slot_bytes >> 4, b_tile16 = p.b_tile_stride >> 4;
+      const uint32_t mb16 = (128u * p.row_bytes) >> 4;
+      const int ksteps = p.ksteps, MB = p.MB, BN = p.BN, b_batch = p.b_batch, n_groups = p.n_groups, cpt = p.cpt;
+      const uint32_t nA = p.nA, nB = p.nB;
+      const bool skip = (p.dbg & 4) != 0;
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, acc_phase = 0;
       for (int tile = first_tile; tile < n_tiles; tile += tile_step) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kC2AccStride;
-        uint32_t n_done = 0;
-        const uint32_t mb_bytes = 128 * p.row_bytes;
-        for (int g = 0; g < p.n_groups; ++g) {
+        uint32_t fresh = 0;                                   // accumulate flag of the next k = 0 MMA
+        for (int g = 0; g < n_groups; ++g) {
           const int t_begin = p.g_first[g], t_end = p.g_first[g + 1];
-          for (int kc = 0; kc < p.cpt; ++kc) {
+          for (int kc = 0; kc < cpt; ++kc) {
             mbar_wait(&fullA[sa], pa);
             tc_fence_after();
-            const uint32_t wa = a_base + sa * p.a_slot_bytes;
-            for (int t0 = t_begin; t0 < t_end; t0 += p.b_batch) {
-              const int nb = min(static_cast<int>(p.b_batch), t_end - t0);
+            const uint32_t wa = a_base + sa * a_slot16;
+            for (int t0 = t_begin; t0 < t_end; t0 += b_batch) {
+              const int nb = min(b_batch, t_end - t0);
               mbar_wait(&fullB[sb], pb);
               tc_fence_after();
-              const uint32_t wb = b_base + sb * p.b_slot_bytes;
-              for (int j = 0; j < nb; ++j, ++n_done) {
-                const uint32_t ta = wa + static_cast<uint32_t>(p.rel[t0 + j]) * p.row_bytes;
-                const uint32_t tb = wb + j * p.b_tile_stride;
-                for (int mb = 0; mb < p.MB; ++mb) {
-                  for (int k = 0; k < p.ksteps; ++k) {
-                    const uint64_t ad = desc_hi | static_cast<uint64_t>(((ta + mb * mb_bytes + k * 32) >> 4) & 0x3FFF);
-                    const uint64_t bd = desc_hi | static_cast<uint64_t>(((tb + k * 32) >> 4) & 0x3FFF);
-                    if (NCTA == 2) umma_bf16_pair(d_tmem + mb * p.BN, ad, bd, idesc, (n_done | k) != 0 ? 1u : 0u);
-                    else umma_bf16(d_tmem + mb * p.BN, ad, bd, idesc, (n_done | k) != 0 ? 1u : 0u);
+              const uint32_t wb = b_base + sb * b_slot16;
+              if (!skip) {
+                for (int j = 0; j < nb; ++j) {
+                  const uint32_t ta = wa + static_cast<uint32_t>(p.rel16[t0 + j]);
+                  const uint32_t tb = wb + j * b_tile16;
+                  for (int mb = 0; mb < MB; ++mb) {
+                    const uint32_t d = d_tmem + mb * BN;
+                    const uint32_t am = ta + mb * mb16;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                      if (k < ksteps) {
+                        const uint64_t ad = (static_cast<uint64_t>(desc_hi32) << 32) | (am + 2 * k);
+                        const uint64_t bd = (static_cast<uint64_t>(desc_hi32) << 32) | (tb + 2 * k);
+                        if (NCTA == 2) umma_bf16_pair(d, ad, bd, idesc, k == 0 ? fresh : 1u);
+                        else umma_bf16(d, ad, bd, idesc, k == 0 ? fresh : 1u);
+                      }
+                    }
                   }
+                  fresh = 1;
                 }
               }
               if (NCTA == 2) umma_commit_pair(&emptyB[sb]); else umma_commit(&emptyB[sb]);
-              if (++sb == p.nB) { sb = 0; pb ^= 1; }
+              if (++sb == nB) { sb = 0; pb ^= 1; }
             }
             if (NCTA == 2) umma_commit_pair(&emptyA[sa]); else umma_commit(&emptyA[sa]);
-            if (++sa == p.nA) { sa = 0; pa ^= 1; }
+            if (++sa == nA) { sa = 0; pa ^= 1; }
           }
         }
         if (NCTA == 2) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
@@ -232,7 +252,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tmem_ld16(t_addr + j * 16, v);
           tmem_ld_wait();
           const int nc = n0 + j * 16;
-          if (do_store && nc < p.n_store) {
+          if (do_store && nc < p.n_store && !(p.dbg & 8)) {
             float f[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -350,9 +370,10 @@ int mmh_conv2_create(const MmhConvDesc* d, MmhConv2** out_plan) {
       k.g_min[ng] = taps[t].first;
       ++ng;
     }
-    k.rel[t] = taps[t].first - k.g_min[ng - 1];
+    const int rel = taps[t].first - k.g_min[ng - 1];
+    k.rel16[t] = static_cast<int32_t>((static_cast<uint32_t>(rel) * k.row_bytes) >> 4);
     k.w_slot[t] = taps[t].second;
-    span_max = std::max(span_max, k.rel[t]);
+    span_max = std::max(span_max, rel);
   }
   k.g_first[ng] = d->T;
   k.n_groups = ng;
@@ -369,6 +390,7 @@ int mmh_conv2_create(const MmhConvDesc* d, MmhConv2** out_plan) {
   mb = env_int("MMH_CONV_MB", mb);
   if (mb < 1 || mb * k.BN > 256 || ncta != 1) mb = 1;
   k.MB = mb;
+  k.dbg = env_int("MMH_C2_DEBUG", 0);
   k.tiles_m = (k.M + 128 * ncta * mb - 1) / (128 * ncta * mb);
   const int need_rows = 128 * mb + span_max;
   k.a_boxes = (need_rows + 255) / 256;

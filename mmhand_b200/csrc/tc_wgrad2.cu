@@ -156,55 +156,77 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ 
       }
     } else if (warp == 1) {
       if (leader && elect_one()) {
+        // descriptor low words are built by adding pre-encoded (>> 4) offsets: two uniform adds per MMA
         uint32_t stage = 0, phase = 0;
-        const uint64_t dy_hi = make_smem_desc(0, p.dy_box_bytes, p.dy_sbo, p.dy_swz);
+        const uint64_t dy_proto = make_smem_desc(0, p.dy_box_bytes, p.dy_sbo, p.dy_swz);
+        const uint32_t dy_hi = static_cast<uint32_t>(dy_proto >> 32), dy_lo = static_cast<uint32_t>(dy_proto);
+        const uint32_t smem16 = smem_u32(smem) >> 4, stage16 = p.stage_bytes >> 4, win16 = p.win_off >> 4;
+        const uint32_t dy_k16 = (2 * p.dy_sbo) >> 4, w_k16 = (2 * p.w_sbo) >> 4, row16 = p.w_row_bytes >> 4;
+        const uint32_t n_stages = p.n_stages;
+        const int BNc = p.BNc;
+        const bool skip = (p.dbg & 2) != 0;
         if (p.mode == 0) {
           const uint32_t idesc = make_idesc_bf16(128 * NCTA, p.BNc, 1, 1);
-          const uint64_t w_hi = make_smem_desc(0, p.w_box_bytes, p.w_sbo, p.w_swz);
+          const uint64_t w_proto = make_smem_desc(0, p.w_box_bytes, p.w_sbo, p.w_swz);
+          const uint32_t w_hi = static_cast<uint32_t>(w_proto >> 32), w_lo = static_cast<uint32_t>(w_proto);
           const int t_begin = p.g_first[g0], ntaps = p.g_first[g0 + 1] - t_begin;
+          uint32_t rel16[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rel16[j] = j < ntaps ? static_cast<uint32_t>(p.rel[t_begin + j]) * row16 : 0u;
           for (int it = 0; it < n_iters; ++it) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t sd = smem_u32(smem + static_cast<size_t>(stage) * p.stage_bytes);
-            const uint32_t sw = sd + p.win_off;
+            const uint32_t sd = smem16 + stage * stage16 + dy_lo;
+            const uint32_t sw = smem16 + stage * stage16 + win16 + w_lo;
+            if (!skip) {
 #pragma unroll
-            for (int k = 0; k < kW2BK / 16; ++k) {
-              const uint64_t ad = dy_hi | static_cast<uint64_t>(((sd + k * 2 * p.dy_sbo) >> 4) & 0x3FFF);
-              for (int j = 0; j < ntaps; ++j) {
-                const uint32_t wa = sw + static_cast<uint32_t>(p.rel[t_begin + j]) * p.w_row_bytes + k * 2 * p.w_sbo;
-                const uint64_t bd = w_hi | static_cast<uint64_t>((wa >> 4) & 0x3FFF);
-                if (p.dbg & 2) continue;
-                if (NCTA == 2) umma_bf16_pair(tmem_base + j * p.BNc, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
-                else umma_bf16(tmem_base + j * p.BNc, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < kW2BK / 16; ++k) {
+                const uint64_t ad = (static_cast<uint64_t>(dy_hi) << 32) | (sd + k * dy_k16);
+                const uint32_t accf = (it | k) != 0 ? 1u : 0u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  if (j < ntaps) {
+                    const uint64_t bd = (static_cast<uint64_t>(w_hi) << 32) | (sw + rel16[j] + k * w_k16);
+                    if (NCTA == 2) umma_bf16_pair(tmem_base + j * BNc, ad, bd, idesc, accf);
+                    else umma_bf16(tmem_base + j * BNc, ad, bd, idesc, accf);
+                  }
+                }
               }
             }
             if (NCTA == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
-            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
         } else {
           // taps on M: A = window (MN-major, leading-dimension stride = one row), B = dy
           const uint32_t idesc = make_idesc_bf16(128, p.BNc, 1, 1);
-          const uint64_t w_hi = make_smem_desc(0, p.w_row_bytes, p.w_sbo, p.w_swz);
+          const uint64_t w_proto = make_smem_desc(0, p.w_row_bytes, p.w_sbo, p.w_swz);
+          const uint32_t w_hi = static_cast<uint32_t>(w_proto >> 32), w_lo = static_cast<uint32_t>(w_proto);
+          const uint32_t wbytes16 = p.w_bytes >> 4, step16 = static_cast<uint32_t>(p.kw_per_mma) * row16;
+          const int n_groups = p.n_groups;
+          // accumulators per group (all groups of the stems have the same tap count)
+          const int apg = (p.g_first[g0 + 1] - p.g_first[g0] + p.kw_per_mma - 1) / p.kw_per_mma;
           for (int it = 0; it < n_iters; ++it) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t sd = smem_u32(smem + static_cast<size_t>(stage) * p.stage_bytes);
-            const uint32_t sw = sd + p.win_off;
+            const uint32_t sd = smem16 + stage * stage16 + dy_lo;
+            const uint32_t sw = smem16 + stage * stage16 + win16 + w_lo;
+            if (!skip) {
 #pragma unroll
-            for (int k = 0; k < kW2BK / 16; ++k) {
-              const uint64_t bd = dy_hi | static_cast<uint64_t>(((sd + k * 2 * p.dy_sbo) >> 4) & 0x3FFF);
-              int acc = 0;
-              for (int g = 0; g < p.n_groups; ++g) {
-                const int ntaps = p.g_first[g0 + g + 1] - p.g_first[g0 + g];
-                for (int j = 0; j < ntaps; j += p.kw_per_mma, ++acc) {
-                  const uint32_t wa = sw + g * p.w_bytes + static_cast<uint32_t>(j) * p.w_row_bytes + k * 2 * p.w_sbo;
-                  const uint64_t ad = w_hi | static_cast<uint64_t>((wa >> 4) & 0x3FFF);
-                  umma_bf16(tmem_base + acc * p.BNc, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < kW2BK / 16; ++k) {
+                const uint64_t bd = (static_cast<uint64_t>(dy_hi) << 32) | (sd + k * dy_k16);
+                const uint32_t accf = (it | k) != 0 ? 1u : 0u;
+                uint32_t d = tmem_base;
+                for (int g = 0; g < n_groups; ++g) {
+                  uint32_t wa = sw + g * wbytes16 + k * w_k16;
+                  for (int a = 0; a < apg; ++a, wa += step16, d += BNc) {
+                    const uint64_t ad = (static_cast<uint64_t>(w_hi) << 32) | wa;
+                    umma_bf16(d, ad, bd, idesc, accf);
+                  }
                 }
               }
             }
             umma_commit(&empty_bar[stage]);
-            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
         }
         if (NCTA == 2) umma_commit_pair(acc_bar); else umma_commit(acc_bar);
@@ -353,6 +375,10 @@ int mmh_wgrad2_create(const MmhWgradDesc* d, MmhWgrad2** out_plan) {
     span_max = std::max(span_max, k.rel[end - 1]);
   }
   k.g_first[ng] = d->T;
+  if (mode == 1) {
+    for (int g = 0; g < ng; ++g)
+      if (k.g_first[g + 1] - k.g_first[g] != gt_max) { set_error("wgrad taps-on-M mode needs equal kernel rows"); return fail(); }
+  }
 
   int ncta = 1;
   if (mode == 0) {

@@ -233,21 +233,21 @@ def case_conv_wgrad(kind='s1', B=2, H=16, W=16, Cin=64, Cout=64, k=3, mode='refl
     return r
 
 
-def case_perf(B=16, H=64, W=64, Cin=256, Cout=256, iters=20):
+def case_perf(B=16, H=64, W=64, Cin=256, Cout=256, iters=20, k=3):
     """Device time of the dominant 3x3 layer (fprop, dgrad, wgrad). MMH_PERF_ITERS overrides iters (ncu runs)."""
     iters = int(os.environ.get("MMH_PERF_ITERS", iters))
     warm = 1 if iters == 1 else 3
     lib = _lib()
     Cin_p, Cout_p = chan_pad(Cin), chan_pad(Cout)
-    g = geom_s1(B, H, W, 3, 'reflect', Cin_p, Cout_p)
+    g = geom_s1(B, H, W, k, 'reflect', Cin_p, Cout_p)
     a_buf = torch.randn(g.in_lay.rows, Cin_p, device=DEV).to(torch.bfloat16)
-    wp = (torch.randn(9, Cout_p, Cin_p, device=DEV) * 0.05).to(torch.bfloat16)
-    wd = (torch.randn(9, Cin_p, Cout_p, device=DEV) * 0.05).to(torch.bfloat16)
+    wp = (torch.randn(k * k, Cout_p, Cin_p, device=DEV) * 0.05).to(torch.bfloat16)
+    wd = (torch.randn(k * k, Cin_p, Cout_p, device=DEV) * 0.05).to(torch.bfloat16)
     out = torch.zeros(g.out_lay.rows, Cout_p, dtype=torch.bfloat16, device=DEV)
     dx = torch.zeros(g.in_lay.rows, Cin_p, dtype=torch.bfloat16, device=DEV)
-    dw = torch.zeros(9, Cout, Cin, dtype=torch.float32, device=DEV)
-    res = {"case": "perf_B%d_%dx%d_%d-%d" % (B, H, W, Cin, Cout), "ok": True}
-    flops = 2.0 * B * H * W * Cin * Cout * 9
+    dw = torch.zeros(k * k, Cout, Cin, dtype=torch.float32, device=DEV)
+    res = {"case": "perf_B%d_%dx%d_%d-%d_k%d" % (B, H, W, Cin, Cout, k), "ok": True}
+    flops = 2.0 * B * H * W * Cin_p * Cout_p * k * k
     for name, plans in (("fprop", convops.fwd_plans(lib, g, a_buf, wp, out, Cin_p, Cout_p)),
                         ("dgrad", convops.dgrad_plans(lib, g, out, wd, dx, Cin_p, Cout_p)),
                         ("wgrad", convops.wgrad_plans(lib, g, a_buf, out, dw, Cin_p, Cout_p, Cin, Cout))):
@@ -304,4 +304,8 @@ CASES = {
     "wgrad_up": lambda: case_conv_wgrad('up', 2, 16, 16, 256, 128),
     "perf": lambda: case_perf(),
     "perf512": lambda: case_perf(16, 64, 64, 512, 512),
+    "perf_stem": lambda: case_perf(16, 256, 256, 3, 64, k=7),
+    "perf_stem42": lambda: case_perf(16, 256, 256, 42, 64, k=7),
+    "perf_out": lambda: case_perf(16, 256, 256, 64, 3, k=7),
+    "perf_d1": lambda: case_perf(16, 128, 128, 128, 128),
 }
