@@ -25,7 +25,7 @@ GFLOP_PER_IMG = 2490.0       # minimal required G+D train
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="per-GPU batch")
@@ -193,7 +193,10 @@ def run_ours(a):
             ms = t.item()
         return ms, ops.launches - l0
 
-    for i in range(max(a.warmup, 3)):
+    # warm-up: at least 3 steps, and enough to fill the image pools (pool_size / B steps) so that the timed steps
+    # run the steady-state pool path (swaps) like any step of a real epoch
+    warm = max(a.warmup, 3, -(-opt.pool_size // B) + 1)
+    for i in range(warm):
         model.set_input(dev[i % 2])
         model.optimize_parameters()
     sampler = ClockSampler(local)
@@ -246,7 +249,7 @@ def run_ours(a):
         return
     line = {
         "metric": "G+D train-step images/sec @256x256", "value": value, "unit": "images/s", "n_gpus": world,
-        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
+        "steps": a.steps, "warmup": warm, "ms_per_step": ms / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "configs[2]: full G+D training, L1+VGG19 perceptual loss, 256x256, BN, dropout on",
                    "per_gpu_batch": B, "global_batch": B * world, "frame": S, "parallelism": "dp%d" % world,

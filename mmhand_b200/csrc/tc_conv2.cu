@@ -67,6 +67,61 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// Epilogue of one 128-row block, one thread per output row: TMEM -> registers -> (bias, activation) -> global.
+// ACT / BIAS are compile-time so that the per-element code is straight-line (a run-time switch per element made
+// the epilogue instruction-bound: ~35 SASS instructions and four branches per output value).
+// 16 columns per step, software-pipelined: the TMEM load of chunk j + 1 is in flight while chunk j is converted
+// and stored; every store is one full 32-byte sector (STG.256).
+template <int ACT, bool BIAS>
+__device__ __forceinline__ void epilogue_row(const Conv2Params& p, uint32_t t_addr, int nchunks, int n0, int64_t orow,
+                                             bool valid, bool do_store) {
+  auto emit = [&](const uint32_t (&v)[16], int j) {
+    const int nc = n0 + j * 16;
+    if (!(do_store && nc < p.n_store) || (p.dbg & 8)) return;
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+    if (BIAS) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + nc);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 b = __ldg(b4 + i);
+        f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (ACT == 1) f[i] = fmaxf(f[i], 0.f);
+      else if (ACT == 2) f[i] = tanhf(f[i]);
+      f[i] = valid ? f[i] : 0.f;
+    }
+    if (p.out_f32) {
+      float* dst = static_cast<float*>(p.out) + orow * p.out_ld + nc;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        st_global_v8(dst + 8 * i, __float_as_uint(f[8 * i]), __float_as_uint(f[8 * i + 1]),
+                     __float_as_uint(f[8 * i + 2]), __float_as_uint(f[8 * i + 3]), __float_as_uint(f[8 * i + 4]),
+                     __float_as_uint(f[8 * i + 5]), __float_as_uint(f[8 * i + 6]), __float_as_uint(f[8 * i + 7]));
+    } else {
+      st_global_v8(static_cast<__nv_bfloat16*>(p.out) + orow * p.out_ld + nc, pack2(f[0], f[1]), pack2(f[2], f[3]),
+                   pack2(f[4], f[5]), pack2(f[6], f[7]), pack2(f[8], f[9]), pack2(f[10], f[11]), pack2(f[12], f[13]),
+                   pack2(f[14], f[15]));
+    }
+  };
+  uint32_t va[16], vb[16];
+  tmem_ld16(t_addr, va);
+  for (int j = 0; j < nchunks; j += 2) {
+    tmem_ld_wait();
+    if (j + 1 < nchunks) tmem_ld16(t_addr + (j + 1) * 16, vb);
+    emit(va, j);
+    if (j + 1 < nchunks) {
+      tmem_ld_wait();
+      if (j + 2 < nchunks) tmem_ld16(t_addr + (j + 2) * 16, va);
+      emit(vb, j + 1);
+    }
+  }
+}
+
 template <int NCTA>
 __global__ void __launch_bounds__(kC2Threads, 1)
 conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -247,34 +302,13 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int64_t orow = static_cast<int64_t>(img) * p.out_img_rows +
                              static_cast<int64_t>(h * p.out_sh + p.out_h0) * p.out_wg + (x * p.out_sw + p.out_w0);
         const uint32_t t_addr = tmem_base + acc * kC2AccStride + mb * p.BN + (static_cast<uint32_t>(quad * 32) << 16);
-        for (int j = 0; j < nchunks; ++j) {
-          uint32_t v[16];
-          tmem_ld16(t_addr + j * 16, v);
-          tmem_ld_wait();
-          const int nc = n0 + j * 16;
-          if (do_store && nc < p.n_store && !(p.dbg & 8)) {
-            float f[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float val = valid ? __uint_as_float(v[i]) : 0.f;
-              if (valid) {
-                if (p.bias != nullptr) val += __ldg(p.bias + nc + i);
-                if (p.act == 1) val = fmaxf(val, 0.f);
-                else if (p.act == 2) val = tanhf(val);
-              }
-              f[i] = val;
-            }
-            if (p.out_f32) {
-              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.out_ld + nc);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-            } else {
-              uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + orow * p.out_ld + nc);
-              dst[0] = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
-              dst[1] = make_uint4(pack2(f[8], f[9]), pack2(f[10], f[11]), pack2(f[12], f[13]), pack2(f[14], f[15]));
-            }
-          }
-        }
+        // bias-free linear layers (every BatchNorm'd convolution, every data gradient) take the straight-line path
+        if (p.bias == nullptr && p.act == 0) epilogue_row<0, false>(p, t_addr, nchunks, n0, orow, valid, do_store);
+        else if (p.bias == nullptr) { if (p.act == 1) epilogue_row<1, false>(p, t_addr, nchunks, n0, orow, valid, do_store);
+                                      else epilogue_row<2, false>(p, t_addr, nchunks, n0, orow, valid, do_store); }
+        else if (p.act == 0) epilogue_row<0, true>(p, t_addr, nchunks, n0, orow, valid, do_store);
+        else if (p.act == 1) epilogue_row<1, true>(p, t_addr, nchunks, n0, orow, valid, do_store);
+        else epilogue_row<2, true>(p, t_addr, nchunks, n0, orow, valid, do_store);
       }
       tc_fence_before();
       __syncwarp();

@@ -202,12 +202,12 @@ class MMHandModel(BaseModel):
         """ImagePool queries (host RNG, reference :279-289) into static buffers."""
         for w in which:
             pool, other = ((self.fake_PP_pool, self.input_H1) if w == 'pp' else (self.fake_PB_pool, self.input_P2))
-            picked = pool.query(torch.cat((self.fake_p2, other), 1).data)
+            cand = torch.cat((self.fake_p2, other), 1).data
             name = '_pool_' + w
-            if getattr(self, name, None) is None or getattr(self, name).shape != picked.shape:
-                setattr(self, name, torch.empty_like(picked))
+            if getattr(self, name, None) is None or getattr(self, name).shape != cand.shape:
+                setattr(self, name, torch.empty_like(cand))
                 self._tapes = None
-            getattr(self, name).copy_(picked)
+            pool.query(cand, out=getattr(self, name))
 
     def backward_D_PB(self):
         return self.backward_D_basic(self.netD_PB, self.input_H2, self.input_P2, self._pool_pb, 6, 2)
