@@ -58,7 +58,7 @@ struct Conv2Params {
   const float* bias;
   int32_t g_first[kC2MaxGroups + 1];
   int32_t g_min[kC2MaxGroups];
-  int32_t rel16[MMH_MAX_TAPS];    // byte offset / 16 of the tap's first row inside its group's window
+  int32_t rel16[MMH_MAX_TAPS + 1];  // byte offset / 16 of the tap's first row inside its group's window (+1: prefetch)
   int32_t w_slot[MMH_MAX_TAPS];
 };
 
@@ -119,6 +119,77 @@ __device__ __forceinline__ void epilogue_row(const Conv2Params& p, uint32_t t_ad
       if (j + 2 < nchunks) tmem_ld16(t_addr + (j + 2) * 16, va);
       emit(vb, j + 1);
     }
+  }
+}
+
+// MMA issue loop of one CTA (pair). KS = MMAs of K = 16 per (tap, 64/32/16-channel chunk), MB = 128-row blocks per
+// tile; both compile-time so that one MMA costs two uniform adds and nothing else. With run-time bounds the
+// compiler emitted a 4 x 4 predicated unroll and ~25 uniform-datapath instructions per MMA: invisible behind
+// 128 x 256 x 16 MMAs (128+ cycles each) but 5x the tensor time of the 128 x 64 x 16 MMAs of the 7x7 stems.
+template <int NCTA, int KS, int MB>
+__device__ __forceinline__ void mma_issue(const Conv2Params& p, uint8_t* a_ring, uint8_t* b_ring, uint64_t* fullA,
+                                          uint64_t* emptyA, uint64_t* fullB, uint64_t* emptyB, uint64_t* tmem_full,
+                                          uint64_t* tmem_empty, uint32_t tmem_base, int first_tile, int tile_step,
+                                          int n_tiles) {
+  // descriptor low word = (address >> 4) | LBO field, high word constant: everything the loop adds up is
+  // pre-encoded in descriptor units (16 bytes)
+  const uint32_t idesc = make_idesc_bf16(128 * NCTA, p.BN, 0, 0);
+  const uint64_t desc_proto = make_smem_desc(0, 16, p.sbo, p.swz);
+  const uint64_t desc_hi = desc_proto & 0xFFFFFFFF00000000ull;
+  const uint32_t a_base = (smem_u32(a_ring) >> 4) + static_cast<uint32_t>(desc_proto);
+  const uint32_t b_base = (smem_u32(b_ring) >> 4) + static_cast<uint32_t>(desc_proto);
+  const uint32_t a_slot16 = p.a_slot_bytes >> 4, b_slot16 = p.b_slot_bytes >> 4, b_tile16 = p.b_tile_stride >> 4;
+  const uint32_t mb16 = (128u * p.row_bytes) >> 4;
+  const uint32_t BN = p.BN;
+  const int b_batch = p.b_batch, n_groups = p.n_groups, cpt = p.cpt;
+  const uint32_t nA = p.nA, nB = p.nB;
+  const bool skip = (p.dbg & 4) != 0;
+  uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, acc_phase = 0;
+  for (int tile = first_tile; tile < n_tiles; tile += tile_step) {
+    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + acc * kC2AccStride;
+    uint32_t fresh = 0;                                   // accumulate flag of the next k = 0 MMA
+    for (int g = 0; g < n_groups; ++g) {
+      const int t_begin = p.g_first[g], t_end = p.g_first[g + 1];
+      for (int kc = 0; kc < cpt; ++kc) {
+        mbar_wait(&fullA[sa], pa);
+        tc_fence_after();
+        const uint32_t wa = a_base + sa * a_slot16;
+        for (int t0 = t_begin; t0 < t_end; t0 += b_batch) {
+          const int nb = min(b_batch, t_end - t0);
+          mbar_wait(&fullB[sb], pb);
+          tc_fence_after();
+          if (!skip) {
+            uint32_t tb = b_base + sb * b_slot16;
+            uint32_t rel = static_cast<uint32_t>(p.rel16[t0]);
+            for (int j = 0; j < nb; ++j) {
+              const uint32_t rel_next = static_cast<uint32_t>(p.rel16[t0 + j + 1]);   // one tap ahead of its use
+              const uint32_t ta = wa + rel;
+#pragma unroll
+              for (int mb = 0; mb < MB; ++mb) {
+#pragma unroll
+                for (int k = 0; k < KS; ++k) {
+                  const uint64_t ad = desc_hi | (ta + mb * mb16 + 2 * k);
+                  const uint64_t bd = desc_hi | (tb + 2 * k);
+                  if (NCTA == 2) umma_bf16_pair(d_tmem + mb * BN, ad, bd, idesc, k == 0 ? fresh : 1u);
+                  else umma_bf16(d_tmem + mb * BN, ad, bd, idesc, k == 0 ? fresh : 1u);
+                }
+              }
+              fresh = 1;
+              rel = rel_next;
+              tb += b_tile16;
+            }
+          }
+          if (NCTA == 2) umma_commit_pair(&emptyB[sb]); else umma_commit(&emptyB[sb]);
+          if (++sb == nB) { sb = 0; pb ^= 1; }
+        }
+        if (NCTA == 2) umma_commit_pair(&emptyA[sa]); else umma_commit(&emptyA[sa]);
+        if (++sa == nA) { sa = 0; pa ^= 1; }
+      }
+    }
+    if (NCTA == 2) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
+    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
   }
 }
 
@@ -217,65 +288,24 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     if (leader && elect_one()) {
-      // ===== MMA issuer. Everything the loop adds up is pre-encoded in descriptor units (16 bytes) so that one MMA
-      // costs two uniform adds: descriptor low word = (address >> 4) | LBO field, high word constant.
-      const uint32_t idesc = make_idesc_bf16(128 * NCTA, p.BN, 0, 0);
-      const uint64_t desc_proto = make_smem_desc(0, 16, p.sbo, p.swz);
-      const uint32_t desc_hi32 = static_cast<uint32_t>(desc_proto >> 32);
-      const uint32_t a_base = (smem_u32(a_ring) >> 4) + static_cast<uint32_t>(desc_proto);
-      const uint32_t b_base = (smem_u32(b_ring) >> 4) + static_cast<uint32_t>(desc_proto);
-      const uint32_t a_slot16 = p.a_slot_bytes >> 4, b_slot16 = p.b_slot_bytes >> 4, b_tile16 = p.b_tile_stride >> 4;
-      const uint32_t mb16 = (128u * p.row_bytes) >> 4;
-      const int ksteps = p.ksteps, MB = p.MB, BN = p.BN, b_batch = p.b_batch, n_groups = p.n_groups, cpt = p.cpt;
-      const uint32_t nA = p.nA, nB = p.nB;
-      const bool skip = (p.dbg & 4) != 0;
-      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, acc_phase = 0;
-      for (int tile = first_tile; tile < n_tiles; tile += tile_step) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kC2AccStride;
-        uint32_t fresh = 0;                                   // accumulate flag of the next k = 0 MMA
-        for (int g = 0; g < n_groups; ++g) {
-          const int t_begin = p.g_first[g], t_end = p.g_first[g + 1];
-          for (int kc = 0; kc < cpt; ++kc) {
-            mbar_wait(&fullA[sa], pa);
-            tc_fence_after();
-            const uint32_t wa = a_base + sa * a_slot16;
-            for (int t0 = t_begin; t0 < t_end; t0 += b_batch) {
-              const int nb = min(b_batch, t_end - t0);
-              mbar_wait(&fullB[sb], pb);
-              tc_fence_after();
-              const uint32_t wb = b_base + sb * b_slot16;
-              if (!skip) {
-                for (int j = 0; j < nb; ++j) {
-                  const uint32_t ta = wa + static_cast<uint32_t>(p.rel16[t0 + j]);
-                  const uint32_t tb = wb + j * b_tile16;
-                  for (int mb = 0; mb < MB; ++mb) {
-                    const uint32_t d = d_tmem + mb * BN;
-                    const uint32_t am = ta + mb * mb16;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                      if (k < ksteps) {
-                        const uint64_t ad = (static_cast<uint64_t>(desc_hi32) << 32) | (am + 2 * k);
-                        const uint64_t bd = (static_cast<uint64_t>(desc_hi32) << 32) | (tb + 2 * k);
-                        if (NCTA == 2) umma_bf16_pair(d, ad, bd, idesc, k == 0 ? fresh : 1u);
-                        else umma_bf16(d, ad, bd, idesc, k == 0 ? fresh : 1u);
-                      }
-                    }
-                  }
-                  fresh = 1;
-                }
-              }
-              if (NCTA == 2) umma_commit_pair(&emptyB[sb]); else umma_commit(&emptyB[sb]);
-              if (++sb == nB) { sb = 0; pb ^= 1; }
-            }
-            if (NCTA == 2) umma_commit_pair(&emptyA[sa]); else umma_commit(&emptyA[sa]);
-            if (++sa == nA) { sa = 0; pa ^= 1; }
-          }
-        }
-        if (NCTA == 2) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      // ===== MMA issuer (one elected lane of the pair's leader CTA)
+#define MMH_ISSUE(KS_, MB_)                                                                                          \
+  mma_issue<NCTA, KS_, MB_>(p, a_ring, b_ring, fullA, emptyA, fullB, emptyB, tmem_full, tmem_empty, tmem_base,       \
+                            first_tile, tile_step, n_tiles)
+      const int mbv = NCTA == 2 ? 1 : p.MB;
+      switch (p.ksteps * 8 + mbv) {
+        case 4 * 8 + 1: MMH_ISSUE(4, 1); break;
+        case 2 * 8 + 1: MMH_ISSUE(2, 1); break;
+        case 1 * 8 + 1: MMH_ISSUE(1, 1); break;
+        case 4 * 8 + 2: if (NCTA == 1) MMH_ISSUE(4, 2); break;
+        case 2 * 8 + 2: if (NCTA == 1) MMH_ISSUE(2, 2); break;
+        case 1 * 8 + 2: if (NCTA == 1) MMH_ISSUE(1, 2); break;
+        case 4 * 8 + 4: if (NCTA == 1) MMH_ISSUE(4, 4); break;
+        case 2 * 8 + 4: if (NCTA == 1) MMH_ISSUE(2, 4); break;
+        case 1 * 8 + 4: if (NCTA == 1) MMH_ISSUE(1, 4); break;
+        default: break;
       }
+#undef MMH_ISSUE
     }
   } else {
     // ===== epilogue warps: TMEM lane quadrant = warp id % 4
@@ -422,7 +452,7 @@ int mmh_conv2_create(const MmhConvDesc* d, MmhConv2** out_plan) {
       mb >>= 1;
   }
   mb = env_int("MMH_CONV_MB", mb);
-  if (mb < 1 || mb * k.BN > 256 || ncta != 1) mb = 1;
+  if ((mb != 1 && mb != 2 && mb != 4) || mb * k.BN > 256 || ncta != 1) mb = 1;
   k.MB = mb;
   k.dbg = env_int("MMH_C2_DEBUG", 0);
   k.tiles_m = (k.M + 128 * ncta * mb - 1) / (128 * ncta * mb);
