@@ -208,7 +208,7 @@ def run_ours(a):
     value = B * world * a.steps / (ms / 1000.0)
     e2e = B * world * a.steps / (ms_e2e / 1000.0)
 
-    # roofline of the dominant kernel (conv_sgemm_kernel: every forward / data-gradient convolution): one extra
+    # roofline of the dominant kernel (conv2_kernel: every forward / data-gradient convolution): one extra
     # instrumented step with a CUDA-event pair around each of its launches on the launching stream
     recs = []
 
@@ -239,7 +239,7 @@ def run_ours(a):
         pass
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
     achieved = f_conv / t_conv / 1e12 if t_conv > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "conv_sgemm_kernel (tcgen05 implicit-GEMM fprop/dgrad)",
+    roofline = {"bound": "tensor", "kernel": "conv2_kernel (tcgen05 implicit-GEMM fprop/dgrad, csrc/tc_conv2.cu)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PF sustained",
                 "launches_per_step": len(recs), "kernel_ms_per_step": t_conv * 1000.0,
