@@ -195,9 +195,12 @@ typedef struct MmhGradGather {
 } MmhGradGather;
 int mmh_grad_gather(const MmhGradGather* p, void* stream);
 
-/* BatchNorm backward (+ ReLU / dropout masks recomputed from the saved raw output). */
+/* BatchNorm backward (+ ReLU / dropout masks recomputed from the saved raw output).
+ * The upstream gradient is either a materialised plain buffer (dz != NULL, nsrc == 0) or gathered on the fly
+ * (dz == NULL): dz = trunk (fp32 plain, optional) + sum over nsrc <= 2 consumer data gradients with their halos
+ * folded back -- the gather of mmh_grad_gather without the round trip through memory. */
 typedef struct MmhBnBwd {
-  const void* dz; /* plain [B*H*W][C] */
+  const void* dz; /* plain [B*H*W][C] or NULL */
   int32_t dz_f32, relu, dropout;
   uint32_t drop_key;
   const void* x;
@@ -208,6 +211,9 @@ typedef struct MmhBnBwd {
   const float* k; /* apply: [2][C] (mean dz, mean dz*xhat) */
   void* dy;       /* apply: bf16 on layout yl (interior only) */
   MmhLay yl;
+  int32_t nsrc, reserved;
+  MmhGradSrc src[2];
+  const float* trunk;
 } MmhBnBwd;
 int mmh_bn_bwd_reduce(const MmhBnBwd* p, void* stream);
 int mmh_bn_bwd_apply(const MmhBnBwd* p, void* stream);

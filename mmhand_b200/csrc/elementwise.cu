@@ -9,7 +9,13 @@
 
 namespace mmh {
 
-MMH_HD float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+MMH_HD float sigmoidf_(float x) {
+#if defined(__CUDA_ARCH__)
+  return __fdividef(1.0f, 1.0f + __expf(-x));      // ex2.approx + rcp.approx: ~2 ulp, outputs are stored as bf16
+#else
+  return 1.0f / (1.0f + expf(-x));
+#endif
+}
 
 struct NoCtx {};
 
@@ -54,7 +60,7 @@ struct AssembleF {
 
 // ------------------------------------------------------------------------------------------------ BN stats
 struct BnStatsF {
-  static constexpr int kUnroll = 4;
+  static constexpr int kUnroll = 8;       // one 16-byte load per item: eight in flight per thread
   typedef NoCtx Ctx;
   struct In { ActX8 x; };
   const act_t* x; int ld;
@@ -271,20 +277,72 @@ struct GradGatherF {
 
 // ------------------------------------------------------------------------------------------------ BN backward
 // dy = a*(dz_eff - k0 - xhat*k1) with xhat = (x - mean)*rstd is evaluated as  a*dz_eff + bx*x + cc
-struct BnBwdIn { union { F32x8 f; ActX8 h; } dz; ActX8 x; };
+//
+// NS = 0: dz is a materialised plain buffer (fp32 or bf16). NS = 1, 2: dz is gathered on the fly from NS consumer
+// data gradients (+ an optional fp32 plain term): the primary element of every source is loaded in the load phase
+// (one 16-byte load each, all in flight together); the mirrored halo elements that fold onto border pixels are
+// added in the finish phase by the few threads that own a border pixel. Nothing is written or re-read in between.
+struct BnDzSlot { union { F32x8 f; ActX8 h; }; };
+struct BnNoSlot {};
+template <bool ON> struct BnSlotSel { typedef BnDzSlot type; };
+template <> struct BnSlotSel<false> { typedef BnNoSlot type; };
+// TR: an fp32 plain term is part of the gathered gradient (NS > 0 only); compile-time so that the common
+// single-source case keeps 8 registers of loads per item in flight instead of 16
+template <int NS, bool TR>
+struct BnBwdIn { typename BnSlotSel<(NS == 0) || TR>::type dz; ActX8 x; ActX8 s[NS ? NS : 1]; };
+
+MMH_HD bool on_fold_border(int i, int n, int lo, int hi) { return (i >= 1 && i <= lo) || (i <= n - 2 && i >= n - 1 - hi); }
+// halo elements of source s that mirror onto (h, w), excluding (h, w) itself
+MMH_HD void fold_extra8(const GradSrcD& s, int b, int h, int w, int cg, float (&acc)[8]) {
+  int hs[3], ws[3];
+  const int nh = preimages(h, s.l.H, s.lo, s.hi, s.reflect, hs);
+  const int nw = preimages(w, s.l.W, s.lo, s.hi, s.reflect, ws);
+  for (int a = 0; a < nh; ++a)
+    for (int c = 0; c < nw; ++c) {
+      if (a == 0 && c == 0) continue;
+      float v[8];
+      ld8_bf16(s.p + lay_off(s.l, b, hs[a], ws[c]) + cg, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+}
+
+template <int NS, bool TR>
 struct BnBwdBase {
+  typedef BnBwdIn<NS, TR> In;
   const void* dz; int dz_f32, relu, dropout; uint32_t key;
   const act_t* x; LayD xl; const float* coef; const float* save;
-  MMH_HD void load(int b, int h, int w, int g, BnBwdIn& in) const {
+  GradSrcD src[NS ? NS : 1]; const float* trunk;
+  MMH_HD void load(int b, int h, int w, int g, In& in) const {
     const int64_t plain = static_cast<int64_t>((b * xl.H + h) * xl.W + w) * xl.C + g * 8;
-    if (dz_f32) ld_raw(static_cast<const float*>(dz) + plain, in.dz.f);
-    else ld_raw(static_cast<const act_t*>(dz) + plain, in.dz.h);
+    if constexpr (NS == 0) {
+      if (dz_f32) ld_raw(static_cast<const float*>(dz) + plain, in.dz.f);
+      else ld_raw(static_cast<const act_t*>(dz) + plain, in.dz.h);
+    } else {
+      if constexpr (TR) ld_raw(trunk + plain, in.dz.f);
+#pragma unroll
+      for (int s = 0; s < NS; ++s) ld_raw(src[s].p + lay_off(src[s].l, b, h, w) + g * 8, in.s[s]);
+    }
     ld_raw(x + lay_off(xl, b, h, w) + g * 8, in.x);
   }
   // effective upstream gradient (after the recomputed ReLU / dropout masks) and raw activation of one vector
-  MMH_HD void eff(const BnBwdIn& in, int b, int h, int w, int g, const float (&a)[8], const float (&bb)[8],
+  MMH_HD void eff(const In& in, int b, int h, int w, int g, const float (&a)[8], const float (&bb)[8],
                   float (&dze)[8], float (&xv)[8]) const {
-    if (dz_f32) cvt8(in.dz.f, dze); else cvt8(in.dz.h, dze);
+    if constexpr (NS == 0) {
+      if (dz_f32) cvt8(in.dz.f, dze); else cvt8(in.dz.h, dze);
+    } else {
+      if constexpr (TR) cvt8(in.dz.f, dze); else zero8(dze);
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        float v[8];
+        cvt8(in.s[s], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dze[j] += v[j];
+        if (src[s].reflect && (on_fold_border(h, src[s].l.H, src[s].lo, src[s].hi) ||
+                               on_fold_border(w, src[s].l.W, src[s].lo, src[s].hi)))
+          fold_extra8(src[s], b, h, w, g * 8, dze);
+      }
+    }
     cvt8(in.x, xv);
     if (relu) {
 #pragma unroll
@@ -298,11 +356,12 @@ struct BnBwdBase {
     }
   }
 };
+template <int NS, bool TR>
 struct BnBwdReduceF {
-  static constexpr int kUnroll = 4;
+  static constexpr int kUnroll = (NS * 4 + (TR ? 8 : 0)) > 8 ? 2 : 4;
   struct Ctx { float a[8], b[8], mean[8], rstd[8]; };
-  typedef BnBwdIn In;
-  BnBwdBase cm;
+  typedef BnBwdIn<NS, TR> In;
+  BnBwdBase<NS, TR> cm;
   MMH_HD void prep(int g, Ctx& c) const {
     const int C = cm.xl.C;
 #pragma unroll
@@ -322,11 +381,12 @@ struct BnBwdReduceF {
     }
   }
 };
+template <int NS, bool TR>
 struct BnBwdApplyF {
-  static constexpr int kUnroll = 4;
+  static constexpr int kUnroll = (NS * 4 + (TR ? 8 : 0)) > 8 ? 2 : 4;
   struct Ctx { float a[8], b[8], bx[8], cc[8]; };
-  typedef BnBwdIn In;
-  BnBwdBase cm; const float* k; act_t* dy; LayD yl;
+  typedef BnBwdIn<NS, TR> In;
+  BnBwdBase<NS, TR> cm; const float* k; act_t* dy; LayD yl;
   MMH_HD void prep(int g, Ctx& c) const {
     const int C = cm.xl.C;
 #pragma unroll
@@ -358,7 +418,7 @@ struct BnBwdFinalizeF {
 };
 
 // ------------------------------------------------------------------------------------------------ gate backward
-struct GateBwdIn { F32x8 dv; ActX8 c1, x2, x3; float e2[8], e3[8]; };
+struct GateBwdIn { F32x8 dv; ActX8 c1, x2, x3, e2, e3; };
 struct GateBwdBase {
   const float* dout; const act_t* c1; const act_t* x2o; const act_t* x3o; LayD sl;
   const float* coef; const float* save;
@@ -427,22 +487,28 @@ struct GateBwdApplyF {
       c.cc[j] = -a * k[ch] + a * k[C + ch] * rstd * mean;
     }
   }
+  // extra gradients of x2o / x3o (the next block's stream convs read them through the swapped concatenation):
+  // primary element in the load phase, mirrored halo elements by the border threads in the finish phase
   MMH_HD void load(int b, int h, int w, int g, const Ctx&, In& in) const {
     cm.load(b, h, w, g, in);
-    zero8(in.e2);
-    zero8(in.e3);
-    if (ex2.p != nullptr) fold_add8(ex2, b, h, w, g * 8, in.e2);
-    if (ex3.p != nullptr) fold_add8(ex3, b, h, w, g * 8, in.e3);
+    if (ex2.p != nullptr) ld_raw(ex2.p + lay_off(ex2.l, b, h, w) + g * 8, in.e2);
+    if (ex3.p != nullptr) ld_raw(ex3.p + lay_off(ex3.l, b, h, w) + g * 8, in.e3);
+  }
+  MMH_HD void add_extra(const GradSrcD& s, const ActX8& prim, int b, int h, int w, int g, float (&d)[8]) const {
+    float v[8];
+    cvt8(prim, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] += v[j];
+    if (s.reflect && (on_fold_border(h, s.l.H, s.lo, s.hi) || on_fold_border(w, s.l.W, s.lo, s.hi)))
+      fold_extra8(s, b, h, w, g * 8, d);
   }
   MMH_HD void finish(const In& in, int b, int h, int w, int g, const Ctx& c) const {
     float d1[8], v1[8], d2[8], d3[8], o[8];
     cm.eff(in, c.a, c.b, d1, v1, d2, d3);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      o[j] = c.a[j] * d1[j] + c.bx[j] * v1[j] + c.cc[j];
-      d2[j] += in.e2[j];
-      d3[j] += in.e3[j];
-    }
+    for (int j = 0; j < 8; ++j) o[j] = c.a[j] * d1[j] + c.bx[j] * v1[j] + c.cc[j];
+    if (ex2.p != nullptr) add_extra(ex2, in.e2, b, h, w, g, d2);
+    if (ex3.p != nullptr) add_extra(ex3, in.e3, b, h, w, g, d3);
     const int64_t off = lay_off(yl, b, h, w) + g * 8;
     st8_bf16(dy1 + off, o);
     st8_bf16(dy2 + off, d2);
@@ -532,25 +598,56 @@ extern "C" int mmh_grad_gather(const MmhGradGather* p, void* stream) {
   return launch_pg(f, make_rowgeom(p->B, p->H, p->W, 0, 0), p->C / 8, stream);
 }
 
-static BnBwdBase bn_common(const MmhBnBwd* p) {
-  BnBwdBase c;
+template <int NS, bool TR>
+static BnBwdBase<NS, TR> bn_common(const MmhBnBwd* p) {
+  BnBwdBase<NS, TR> c;
   c.dz = p->dz; c.dz_f32 = p->dz_f32; c.relu = p->relu; c.dropout = p->dropout; c.key = p->drop_key;
   c.x = static_cast<const act_t*>(p->x); c.xl = to_layd(p->xl); c.coef = p->coef; c.save = p->save;
+  for (int s = 0; s < NS; ++s) c.src[s] = to_gsd(p->src[s]);
+  c.trunk = p->trunk;
   return c;
 }
-extern "C" int mmh_bn_bwd_reduce(const MmhBnBwd* p, void* stream) {
-  MMH_CHECK(p && p->dz && p->x && p->coef && p->save && p->sums, "null argument");
+static int bn_bwd_check(const MmhBnBwd* p) {
+  MMH_CHECK(p && p->x && p->coef && p->save, "null argument");
   MMH_REQ_VEC(p->xl.C);
-  BnBwdReduceF f;
-  f.cm = bn_common(p);
+  MMH_CHECK(p->nsrc >= 0 && p->nsrc <= 2, "nsrc=%d unsupported (0..2)", p->nsrc);
+  MMH_CHECK(p->nsrc > 0 ? p->dz == nullptr : (p->dz != nullptr && p->trunk == nullptr),
+            "give either dz or gradient sources (+ trunk)");
+  for (int s = 0; s < p->nsrc; ++s) {
+    MMH_CHECK(p->src[s].p != nullptr, "null gradient source");
+    MMH_CHECK(p->src[s].l.H == p->xl.H && p->src[s].l.W == p->xl.W && p->src[s].l.B == p->xl.B,
+              "gradient source %d has another shape", s);
+  }
+  return 0;
+}
+template <int NS, bool TR>
+static int bn_bwd_reduce_t(const MmhBnBwd* p, void* stream) {
+  BnBwdReduceF<NS, TR> f;
+  f.cm = bn_common<NS, TR>(p);
   return launch_reduce_ch<2>(f, make_rowgeom(p->xl.B, p->xl.H, p->xl.W, 0, 0), p->xl.C / 8, p->xl.C, p->sums, stream);
 }
-extern "C" int mmh_bn_bwd_apply(const MmhBnBwd* p, void* stream) {
-  MMH_CHECK(p && p->dz && p->x && p->coef && p->save && p->k && p->dy, "null argument");
-  MMH_REQ_VEC(p->xl.C);
-  BnBwdApplyF f;
-  f.cm = bn_common(p); f.k = p->k; f.dy = static_cast<act_t*>(p->dy); f.yl = to_layd(p->yl);
+template <int NS, bool TR>
+static int bn_bwd_apply_t(const MmhBnBwd* p, void* stream) {
+  BnBwdApplyF<NS, TR> f;
+  f.cm = bn_common<NS, TR>(p); f.k = p->k; f.dy = static_cast<act_t*>(p->dy); f.yl = to_layd(p->yl);
   return launch_pg(f, make_rowgeom(p->xl.B, p->xl.H, p->xl.W, 0, 0), p->xl.C / 8, stream);
+}
+#define MMH_BN_BWD_DISPATCH(fn)                                                            \
+  do {                                                                                     \
+    const bool tr = p->trunk != nullptr;                                                   \
+    if (p->nsrc == 0) return fn<0, false>(p, stream);                                      \
+    if (p->nsrc == 1) return tr ? fn<1, true>(p, stream) : fn<1, false>(p, stream);        \
+    return tr ? fn<2, true>(p, stream) : fn<2, false>(p, stream);                          \
+  } while (0)
+extern "C" int mmh_bn_bwd_reduce(const MmhBnBwd* p, void* stream) {
+  if (bn_bwd_check(p)) return 1;
+  MMH_CHECK(p->sums, "null argument");
+  MMH_BN_BWD_DISPATCH(bn_bwd_reduce_t);
+}
+extern "C" int mmh_bn_bwd_apply(const MmhBnBwd* p, void* stream) {
+  if (bn_bwd_check(p)) return 1;
+  MMH_CHECK(p->k && p->dy, "null argument");
+  MMH_BN_BWD_DISPATCH(bn_bwd_apply_t);
 }
 extern "C" int mmh_bn_bwd_finalize(const float* sums_global, const float* sums_local, float count, float* k,
                                    float* dgamma, float* dbeta, int32_t C, void* stream) {

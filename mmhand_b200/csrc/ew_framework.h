@@ -302,6 +302,9 @@ int launch_pg(const F& f, const RowGeom& rg, int groups, void* stream) {
   return 0;
 }
 
+// Persistent: the grid is one resident wave (2 blocks per SM) and a block walks over (row, column chunk) units, so
+// that a launch ends with 2 * SMs * NV * C atomics on the NV * C result words (one block per row used to mean
+// B * H blocks hammering the same few cache lines: measured 41 % of HBM speed on the 512-channel layers).
 template <int NV, class F>
 __global__ void __launch_bounds__(256, 2) reduce_ch_kernel(const F f, const RowGeom rg, const int groups, const int chunks,
                                                            const int C, float* __restrict__ out) {
@@ -315,8 +318,11 @@ __global__ void __launch_bounds__(256, 2) reduce_ch_kernel(const F f, const RowG
   for (int v = 0; v < NV; ++v) zero8(acc[v]);
   typename F::Ctx c;
   f.prep(g, c);
-  const int b = blockIdx.z, h = static_cast<int>(blockIdx.y) - rg.lo;
-  for (int chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
+  const int units = rg.n_rows * chunks;
+  for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    // block-uniform: row, image and chunk of this unit
+    const int row = unit / chunks, chunk = unit - row * chunks;
+    const int b = row / rg.h_ext, h = row - b * rg.h_ext - rg.lo;
     const int col0 = chunk * (ppb * U) + lr;
     typename F::In in[U];
 #pragma unroll
@@ -353,8 +359,11 @@ int launch_reduce_ch(const F& f, const RowGeom& rg, int groups, int C, float* ou
   const int ppb = threads / groups;
   const size_t smem = static_cast<size_t>(threads) * NV * 8 * sizeof(float);
   const int chunks = (rg.n_cols + ppb * F::kUnroll - 1) / (ppb * F::kUnroll);
-  const dim3 grid = row_grid(rg, (chunks + 3) / 4, 4);
-  reduce_ch_kernel<NV, F><<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(f, rg, groups, chunks, C, out);
+  const int64_t units = static_cast<int64_t>(rg.n_rows) * chunks;
+  MMH_CHECK(units < (int64_t(1) << 31), "too many work units");
+  const int64_t wave = static_cast<int64_t>(num_sms()) * 2;
+  const int blocks = static_cast<int>(units < wave ? units : wave);
+  reduce_ch_kernel<NV, F><<<blocks, threads, smem, static_cast<cudaStream_t>(stream)>>>(f, rg, groups, chunks, C, out);
   MMH_CUDA(cudaGetLastError());
   return 0;
 }

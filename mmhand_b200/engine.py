@@ -9,6 +9,8 @@ no host synchronisation). Layer structure and arithmetic follow the reference mo
   DiscriminatorEngine  models/Discriminator.py:58-154
   VggEngine            losses/L1_plus_perceptualLoss.py:22-27,54-61 (VGG19.features[0:4])
 """
+import os
+
 import torch
 
 from . import convops
@@ -17,6 +19,10 @@ from .layouts import Lay, chan_pad, geom_s1, geom_s2, geom_up
 
 BN_EPS = 1e-5
 BN_MOM = 0.1
+
+# MMH_FUSE_GATHER=0 materialises dz with mmh_grad_gather before the BN backward (A/B measurements only)
+FUSE_GATHER = os.environ.get("MMH_FUSE_GATHER", "1") != "0"
+
 
 def plain_lay(B, H, W, Cc):
     return Lay(B, H, W, H, W, 0, 0, False, Cc, 0, Cc)
@@ -252,6 +258,12 @@ class EngineBase:
     def convs(self):
         raise NotImplementedError
 
+    def prepare_training(self):
+        """One-off allocation of the backward buffers / plans and the first packing of the weights. Callers that
+        record launch tapes do this before recording, so that a replay holds only the per-step work."""
+        self._prepare_backward()
+        self.repack()
+
     def repack(self, force=False):
         """bf16 tensor-core operands of every weight (forward and, once backward is prepared, data-gradient form):
         one batched launch per optimiser step."""
@@ -298,11 +310,14 @@ class EngineBase:
         ops = self.ops
         ol = conv.g.out_lay
         B, H, W, Cc = ol.B, ol.H, ol.W, ol.C
-        if dz_out_f32 is not None:
-            dz, f32 = dz_out_f32, True
+        if dz_out_f32 is None and len(srcs) <= 2 and FUSE_GATHER:
+            dz, f32 = (list(srcs), trunk), False          # gathered inside the two BN backward kernels
         else:
-            dz, f32 = self.scratch(("dz", B * H * W, Cc), B * H * W, Cc), False
-        ops.grad_gather(srcs, B, H, W, Cc, dz, plain_lay(B, H, W, Cc), f32, trunk=trunk)
+            if dz_out_f32 is not None:
+                dz, f32 = dz_out_f32, True
+            else:
+                dz, f32 = self.scratch(("dz", B * H * W, Cc), B * H * W, Cc), False
+            ops.grad_gather(srcs, B, H, W, Cc, dz, plain_lay(B, H, W, Cc), f32, trunk=trunk)
         bn.backward(dz, f32, relu, dropout, key, conv.raw, ol, conv.dy, ol, B * H * W, want_wgrad)
         conv.run_bwd(want_wgrad, want_dx)
 
@@ -652,6 +667,18 @@ class VggEngine:
             self._scratch[key] = t
         return t
 
+    def prepare_training(self):
+        """Backward buffers, plans and data-gradient operands of the generated-image slot (once)."""
+        if self.bwd_ready:
+            return
+        c1, c2 = self.c1[0], self.c2[0]
+        c2.need_dx = True
+        c2.prepare_backward("v2", "v2", need_wgrad=False)
+        c1.prepare_backward("v1", "v1", need_wgrad=False)
+        c2.pack(True)
+        c1.pack(True)
+        self.bwd_ready = True
+
     def features(self, x, slot):
         c1, c2 = self.c1[slot], self.c2[slot]
         self.ops.assemble(x, None, c1.x, c1.g.in_lay, 1, 1, False, scale=self.scale, shift=self.shift)
@@ -669,13 +696,7 @@ class VggEngine:
         if dfake is None:
             ops.perc_loss(ff, ft, mse, lambda_perc / n, 0.0, loss_acc, None)
             return
-        if not self.bwd_ready:
-            c2.need_dx = True
-            c2.prepare_backward("v2", "v2", need_wgrad=False)
-            c1.prepare_backward("v1", "v1", need_wgrad=False)
-            c2.pack(True)
-            c1.pack(True)
-            self.bwd_ready = True
+        self.prepare_training()
         ops.perc_loss(ff, ft, mse, lambda_perc / n, lambda_perc / n, loss_acc, c2.dy)
         c2.run_bwd(False)
         # through the ReLU of conv1 (its output lives in conv2's input buffer)

@@ -216,7 +216,17 @@ class Ops:
         self._run(self.lib.mmh_grad_gather, (C.byref(p), self.st()), keep=p)
 
     def _bn_bwd(self, dz, dz_f32, relu, dropout, key, x, xl, coef, save, sums=None, k=None, dy=None, yl=None):
+        """dz: plain buffer, or a tuple (sources, trunk) = gather the upstream gradient inside the kernel."""
         p = L.BnBwd()
+        if isinstance(dz, tuple):
+            srcs, trunk = dz
+            assert len(srcs) <= 2 and (srcs or trunk is not None)
+            if not srcs:            # the fp32 trunk alone is just a plain fp32 dz
+                dz, dz_f32 = trunk, True
+            else:
+                p.nsrc, p.trunk, dz = len(srcs), _p(trunk), None
+                for i, s in enumerate(srcs):
+                    p.src[i] = s.c()
         p.dz, p.dz_f32, p.relu, p.dropout = _p(dz), 1 if dz_f32 else 0, int(relu), int(dropout)
         patch = self._key(key, p)
         p.x, p.xl, p.coef, p.save = _p(x), clay(xl), _p(coef), _p(save)

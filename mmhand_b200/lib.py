@@ -92,6 +92,7 @@ class BnBwd(C.Structure):
         ("dz", C.c_void_p), ("dz_f32", C.c_int32), ("relu", C.c_int32), ("dropout", C.c_int32),
         ("drop_key", C.c_uint32), ("x", C.c_void_p), ("xl", Lay), ("coef", C.c_void_p), ("save", C.c_void_p),
         ("sums", C.c_void_p), ("k", C.c_void_p), ("dy", C.c_void_p), ("yl", Lay),
+        ("nsrc", C.c_int32), ("reserved", C.c_int32), ("src", GradSrc * 2), ("trunk", C.c_void_p),
     ]
 
 

@@ -255,6 +255,12 @@ class MMHandModel(BaseModel):
             self._pool_inputs()
             tapes[1].replay(self._step)
         elif use_tape:
+            # one-off work (backward buffers, plans, first weight packing) stays outside the recorded sequence
+            self._g_engine().prepare_training()
+            for net in (self.netD_PB, self.netD_PP):
+                self._d_engine(net).prepare_training()
+            if hasattr(self.criterionL1, 'vgg_engine'):
+                self.criterionL1.vgg_engine(B, H, W).prepare_training()
             with ops.record() as tg:
                 self._segment_G()
             self._pool_inputs()
