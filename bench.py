@@ -25,14 +25,23 @@ GFLOP_PER_IMG = 2490.0       # minimal required G+D train
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="default: 20 (train, infer), 245 (raster: ~1M poses)")
+    ap.add_argument("--workload", default="train", choices=["train", "infer", "raster"],
+                    help="train = configs[2] (the headline metric); infer = configs[1] (generator-only inference, "
+                         "batch 32); raster = configs[3] (keypoint -> heatmap rasteriser, 4096 poses per step)")
+    ap.add_argument("--poses-per-step", type=int, default=4096)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="per-GPU batch")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: 16 train, 32 infer)")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.steps is None:
+        a.steps = 245 if a.workload == "raster" else 20
+    if a.batch is None:
+        a.batch = 32 if (a.workload == "infer" and a.impl == "ours") else 16
+    return a
 
 
 def synth_batch(B, S, seed, pin=False):
@@ -268,9 +277,245 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+# ======================================================================================= secondary workloads
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs CUDA devices"
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", init_method="env://", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def _timed_loop(n, body, world):
+    """K calls of body(i) between barrier + synchronize, CUDA events on the launching stream, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        body(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    return ms
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def run_infer(a):
+    """configs[1]: Generator-only inference (the aug.py path), batch 32, 256x256, eval-mode BN, no_grad.
+    Shards by image across ranks, no collective."""
+    import torch
+
+    world, rank, local = _dist_setup()
+    from mmhand_b200 import runtime
+    from models.Generator import Generator
+    from models.network_utils import get_norm_layer, init_weights
+    B, S = a.batch, a.size
+    torch.manual_seed(49)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        g = Generator([3, 42, 6], 3, 64, get_norm_layer('batch'), True, 9).to(torch.device("cuda", local))
+        init_weights(g, 'normal')
+    g.eval()
+    ops = runtime.get_ops(torch.device("cuda", local))
+    hosts, devs = [], []
+    for i in range(2):
+        b = synth_batch(B, S, 2000 + 17 * rank + i, pin=True)
+        h = [b["H1"], torch.cat((b["P1"], b["P2"]), 1).pin_memory(), torch.cat((b["D1"], b["D2"]), 1).pin_memory()]
+        hosts.append(h)
+        devs.append([t.cuda(non_blocking=True) for t in h])
+    out_host = torch.empty(B, 3, S, S, dtype=torch.float32).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in hosts[0])
+
+    def dev_step(i):
+        with torch.no_grad():
+            g(devs[i % 2])
+
+    def e2e_step(i):
+        with torch.no_grad():
+            y = g([t.cuda(non_blocking=True) for t in hosts[i % 2]])
+        out_host.copy_(y, non_blocking=True)
+        torch.cuda.current_stream().synchronize()       # aug.py writes each batch of images to disk
+
+    warm = max(a.warmup, 3)
+    for i in range(warm):
+        dev_step(i)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ops.launches
+    ms = _timed_loop(a.steps, dev_step, world)
+    launches = ops.launches - l0
+    ms_e2e = _timed_loop(a.steps, e2e_step, world)
+    sampler.stop_flag = True
+    sampler.join(timeout=3)
+    value = B * world * a.steps / (ms / 1000.0)
+    e2e = B * world * a.steps / (ms_e2e / 1000.0)
+
+    recs = []
+
+    def hook(kind, tag, plan, launch):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        launch()
+        e1.record()
+        d = plan.desc
+        recs.append((e0, e1, 2.0 * d.M * d.N * d.C * d.T * (d.Hv * d.Wv) / float(d.Hg * d.Wg)))
+
+    ops.conv_hook = hook
+    dev_step(0)
+    torch.cuda.synchronize()
+    ops.conv_hook = None
+    t_conv = sum(e0.elapsed_time(e1) for e0, e1, _ in recs) / 1000.0
+    f_conv = sum(f for _, _, f in recs)
+    peaks = _peaks()
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    achieved = f_conv / t_conv / 1e12 if t_conv > 0 else 0.0
+    if rank != 0:
+        return
+    gflop_img = 611.68
+    line = {
+        "metric": "generator inference images/sec @256x256", "value": value, "unit": "images/s", "n_gpus": world,
+        "steps": a.steps, "warmup": warm, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "configs[1]: Generator-only inference (aug.py path), eval-mode BN, no_grad",
+                   "per_gpu_batch": B, "frame": S, "parallelism": "dp%d (independent images, no collective)" % world,
+                   "l2": "activations of one batch (> 2 GB) exceed the 126 MB L2"},
+        "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e / a.steps},
+        "gpu_launches": launches, "clocks": sampler.summary(),
+        "roofline": {"bound": "tensor", "kernel": "conv2_kernel (tcgen05 implicit-GEMM fprop, csrc/tc_conv2.cu)",
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PF sustained",
+                     "launches_per_step": len(recs), "kernel_ms_per_step": t_conv * 1000.0,
+                     "step_tensor_util": gflop_img * 1e9 * value / world / (peak * 1e12)},
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        from oracle import patn_ref as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        sd = {k: v.detach().cpu().clone() for k, v in g.state_dict().items()}
+        x = [t[:1].clone() for t in hosts[0]]
+        with torch.no_grad():
+            O.generator_forward(sd, x, train=False)
+            n, t0 = 0, time.time()
+            while time.time() - t0 < a.cpu_seconds:
+                O.generator_forward(sd, x, train=False)
+                n += 1
+        rate = n / (time.time() - t0)
+        line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "%d eval forwards of batch 1, oracle port of Generator.forward, torch fp32 CPU" % n}
+    print(json.dumps(line))
+
+
+def run_raster(a):
+    """configs[3]: keypoint -> 21-joint Gaussian heatmaps (mmh_heatmap_rasterize), K steps of P poses each
+    (default 245 x 4096 = 1,003,520 poses). Poses shard across ranks, no collective. Output buffers alternate
+    between two P-pose blocks (2 x 22.5 GB at P = 4096), far larger than L2."""
+    import numpy as np
+    import torch
+
+    world, rank, local = _dist_setup()
+    from mmhand_b200 import runtime
+    from mmhand_b200.rasterize import get_heatmaps
+    P, S = a.poses_per_step, a.size
+    dev = torch.device("cuda", local)
+    ops = runtime.get_ops(dev)
+    rng = np.random.RandomState(49 + rank)
+    uv_host = torch.from_numpy(rng.uniform(16.0, 240.0 * S / 256.0, size=(2, P, 21, 2))).pin_memory()
+    uv_dev = uv_host.to(dev)
+    outs = [torch.empty(P, 21, S, S, dtype=torch.float32, device=dev) for _ in range(2)]
+    chk = torch.zeros(1, dtype=torch.float64, device=dev)
+    chk_host = torch.zeros(1, dtype=torch.float64).pin_memory()
+
+    def dev_step(i):
+        get_heatmaps(uv_dev[i % 2], (S, S), out=outs[i % 2])
+
+    def e2e_step(i):
+        uv = uv_host[i % 2].to(dev, non_blocking=True)
+        o = get_heatmaps(uv, (S, S), out=outs[i % 2])
+        chk_host.copy_(o[:, :, S // 2, :].sum(dtype=torch.float64).reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    warm = max(a.warmup, 3)
+    for i in range(warm):
+        dev_step(i)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ops.launches
+    ms = _timed_loop(a.steps, dev_step, world)
+    launches = ops.launches - l0
+    ms_e2e = _timed_loop(a.steps, e2e_step, world)
+    sampler.stop_flag = True
+    sampler.join(timeout=3)
+    value = P * world * a.steps / (ms / 1000.0)
+    e2e = P * world * a.steps / (ms_e2e / 1000.0)
+    # one kernel per step: its average launch duration is the step time
+    bytes_per_pose = 21 * S * S * 4 + 21 * 2 * 8
+    peaks = _peaks()
+    peak = peaks.get("hbm_gbs", 6500.0)
+    achieved = bytes_per_pose * P * a.steps / (ms / 1000.0) / 1e9
+    if rank != 0:
+        return
+    line = {
+        "metric": "keypoint->heatmap rasterisation poses/sec @256x256x21", "value": value, "unit": "poses/s",
+        "n_gpus": world, "steps": a.steps, "warmup": warm, "ms_per_step": ms / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[3]: 21-joint Gaussian heatmaps, fp64 arithmetic, fp32 maps",
+                   "poses_per_step": P, "poses_total": P * a.steps * world, "frame": S,
+                   "parallelism": "dp%d (independent poses, no collective)" % world,
+                   "l2": "two alternating %.1f GB output blocks, far larger than L2" % (bytes_per_pose * P / 1e9)},
+        "e2e": {"value": e2e, "unit": "poses/s", "h2d_bytes_per_step": P * 21 * 2 * 8, "d2h_bytes_per_step": 8,
+                "ms_per_step": ms_e2e / a.steps,
+                "note": "maps stay in HBM for the training step that consumes them; the host reads one checksum"},
+        "gpu_launches": launches, "clocks": sampler.summary(),
+        "roofline": {"bound": "hbm", "kernel": "map_kernel<RasterF> (csrc/raster.cu)", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback",
+                     "bytes_per_pose": bytes_per_pose},
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        from oracle.raster_ref import get_heatmaps as ref_heatmaps
+        uvn = uv_host[0].numpy()
+        n, t0 = 0, time.time()
+        while time.time() - t0 < min(a.cpu_seconds, 15.0):
+            ref_heatmaps(uvn[n % P], (S, S))
+            n += 1
+        rate = n / (time.time() - t0)
+        line["cpu_baseline"] = {"value": rate, "unit": "poses/s", "cores": 1, "kind": "port",
+                                "sample": "%d poses, numpy restatement of Genericdataset.get_heatmaps (one DataLoader worker)" % n}
+    print(json.dumps(line))
+
+
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "infer":
+        run_infer(args)
+    elif args.workload == "raster":
+        run_raster(args)
     else:
         run_ours(args)

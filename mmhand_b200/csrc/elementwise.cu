@@ -5,6 +5,7 @@
 // Dual-mode source: CUDA by default, host loops with -DMMH_HOST_EMU (CPU tests of the index arithmetic).
 #include <math.h>
 
+#include "bn_finalize.h"
 #include "ew_framework.h"
 
 namespace mmh {
@@ -73,33 +74,6 @@ struct BnStatsF {
     cvt8(in.x, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[0][j] += v[j]; acc[1][j] += v[j] * v[j]; }
-  }
-};
-
-struct BnFinalizeF {
-  const float* sums; const float* gamma; const float* beta; float* rm; float* rv; float* coef; float* save;
-  float count, momentum, eps; int train, C;
-  MMH_HD void operator()(int64_t c) const {
-    float mean, var;
-    if (train) {
-      mean = sums[c] / count;
-      var = sums[C + c] / count - mean * mean;
-      if (var < 0.f) var = 0.f;
-      if (rm != nullptr) {
-        const float unb = count > 1.f ? var * count / (count - 1.f) : var;
-        rm[c] = (1.f - momentum) * rm[c] + momentum * mean;
-        rv[c] = (1.f - momentum) * rv[c] + momentum * unb;
-      }
-    } else {
-      mean = rm[c];
-      var = rv[c];
-    }
-    const float rstd = 1.0f / sqrtf(var + eps);
-    const float ga = gamma != nullptr ? gamma[c] : 1.f, be = beta != nullptr ? beta[c] : 0.f;
-    coef[c] = ga * rstd;
-    coef[C + c] = be - mean * ga * rstd;
-    save[c] = mean;
-    save[C + c] = rstd;
   }
 };
 
@@ -407,16 +381,6 @@ struct BnBwdApplyF {
     st8_bf16(dy + lay_off(yl, b, h, w) + g * 8, o);
   }
 };
-struct BnBwdFinalizeF {
-  const float* sg; const float* sl; float* k; float* dgamma; float* dbeta; float count; int C;
-  MMH_HD void operator()(int64_t c) const {
-    k[c] = sg[c] / count;
-    k[C + c] = sg[C + c] / count;
-    if (dgamma != nullptr) dgamma[c] += sl[C + c];
-    if (dbeta != nullptr) dbeta[c] += sl[c];
-  }
-};
-
 // ------------------------------------------------------------------------------------------------ gate backward
 struct GateBwdIn { F32x8 dv; ActX8 c1, x2, x3, e2, e3; };
 struct GateBwdBase {

@@ -202,13 +202,21 @@ def test_heatmap_rasteriser():
     from mmhand_b200.rasterize import get_heatmaps
     from oracle.raster_ref import get_heatmaps_batch
     rng = np.random.RandomState(49)
-    uv = rng.uniform(16, 240, size=(64, 21, 2))
-    # adversarial poses: integer pixels, borders, outside the frame
+    uv = rng.uniform(16, 240, size=(256, 21, 2))
+    # adversarial poses: integer pixels, borders, outside the frame, threshold grazing, far outside, NaN
     uv[0, :, :] = np.array([[10.0 * j, 7.0 * j] for j in range(21)])
     uv[1, :, :] = np.array([[0.0, 0.0], [255.0, 255.0], [-30.0, 40.0], [300.0, 128.0]] + [[128.5, 0.25]] * 17)
+    r = np.sqrt(332.2958775)
+    uv[2, :, :] = np.array([[128.0 + r * np.cos(t), 128.0 + r * np.sin(t)] for t in np.linspace(0, 6.2, 21)])
+    uv[3, :4, :] = np.array([[1e12, -1e12], [-18.5, 100.0], [273.0, 273.9], [-40.0, 300.0]])
+    uv[64:128] = rng.uniform(-30, 286, size=(64, 21, 2))
     got = get_heatmaps(torch.from_numpy(uv), (256, 256)).cpu().numpy()
-    want = get_heatmaps_batch(uv, (256, 256))
-    assert got.shape == (64, 21, 256, 256)
-    assert np.abs(got - want).max() <= 1e-6
+    assert got.shape == (256, 21, 256, 256)
+    for c0 in range(0, 256, 64):
+        want = get_heatmaps_batch(uv[c0:c0 + 64], (256, 256))
+        assert np.abs(got[c0:c0 + 64] - want).max() <= 1e-6
+        assert np.array_equal(got[c0:c0 + 64] > 0, want > 0)   # identical threshold decisions
     assert (got[0, 5] > 0).sum() == 1041       # known answer: interior integer-centred joint
-    assert np.array_equal(got > 0, want > 0)   # identical threshold decisions
+    nan = get_heatmaps(torch.tensor([[[float("nan"), 3.0]]], dtype=torch.float64), (256, 256))
+    assert torch.isnan(nan).all()
+    assert get_heatmaps(torch.zeros(0, 21, 2, dtype=torch.float64), (256, 256)).shape == (0, 21, 256, 256)

@@ -28,8 +28,15 @@ def test_kernel_body_matches_oracle_bit_exactly():
         uv[0, 0] = (0.0, 0.0)
         uv[0, 1] = (255.0, 255.0)
         uv[0, 2] = (128.0, 128.0 + np.sqrt(332.2958775))       # threshold grazing
+        uv[0, 3] = (1e12, -1e12)                               # far outside: must not overflow the bounding box
+        uv[0, 4] = (-18.5, 100.0)                              # disc touches the frame from outside
+        uv[0, 5] = (273.0, 273.9)
+        uv[0, 6] = (-40.0, 300.0)
+        uv[0, 7] = (float("nan"), 10.0)                        # NaN propagates like numpy's exp
         got = gpu_heatmaps(torch.from_numpy(uv), (256, 256)).numpy()
         want = get_heatmaps_batch(uv, (256, 256))
-        assert np.array_equal(got, want)
+        assert np.array_equal(got, want, equal_nan=True)
+        assert np.isnan(got[0, 7]).all() and not np.isnan(got[0, :7]).any()
+        assert gpu_heatmaps(torch.zeros(0, 21, 2, dtype=torch.float64), (256, 256)).shape == (0, 21, 256, 256)
     finally:
         runtime._TEST_OPS = None
