@@ -163,7 +163,7 @@ def run_ours(a):
         dist.init_process_group("nccl", init_method="env://", device_id=torch.device("cuda", local))
     from mmhand_b200 import runtime
     from models.MMHandModel import MMHandModel
-    from oracle.ref_shims import make_opt
+    from mmhand_b200.options import make_opt
 
     torch.manual_seed(49)
     random.seed(49 + rank)

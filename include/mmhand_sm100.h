@@ -296,6 +296,33 @@ int mmh_memset(void* p, int32_t byte, int64_t bytes, void* stream);
 int mmh_heatmap_rasterize(const double* uv, int64_t n_maps, int32_t H, int32_t W, double sigma, double thresh,
                           float* out, void* stream);
 
+/* ---- synchronised BatchNorm over NVLink peer memory ------------------------------------------------
+ * Replaces apex.parallel.convert_syncbn_model + its per-layer NCCL all-reduces (models/MMHandModel.py:109-116):
+ * the BN finalise kernels exchange their 2*C partial sums through mailboxes mapped into every peer GPU of the box
+ * (one process per GPU; CUDA IPC) and reduce them in rank order, so all ranks hold bit-identical statistics.
+ * The mailbox is the one device allocation the library owns (an IPC object must be the base of its allocation).
+ * Protocol: create on every rank -> exchange the MMH_PEER_HANDLE_BYTES handles out of band (torch.distributed) ->
+ * connect. Every rank must issue the same exchanges in the same order with the same `seq` (1, 2, 3, ...).
+ * mmh_peer_status: 0 ok, 1 = a wait timed out (a peer died; results are NaN), -1 = no peer support. */
+#define MMH_PEER_HANDLE_BYTES 64
+typedef struct MmhPeer MmhPeer;
+int mmh_peer_create(int32_t rank, int32_t world, MmhPeer** out);
+int mmh_peer_handle(MmhPeer* g, void* handle64);
+int mmh_peer_connect(MmhPeer* g, const void* handles /* world x MMH_PEER_HANDLE_BYTES, rank order */);
+int mmh_peer_status(MmhPeer* g);
+int mmh_peer_destroy(MmhPeer* g);
+/* in-place sum over ranks of n <= 2048 floats */
+int mmh_peer_sum(MmhPeer* g, uint32_t seq, float* data, int32_t n, void* stream);
+/* mmh_bn_finalize (train mode) on the global statistics: sums (local partial sums) is overwritten by the global
+ * sums; count_global = elements per channel over all ranks. */
+int mmh_bn_finalize_sync(MmhPeer* g, uint32_t seq, float* sums, float count_global, const float* gamma,
+                         const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                         int32_t C, float* coef, float* save, void* stream);
+/* mmh_bn_bwd_finalize with the exchange: sums_global := sum over ranks of sums_local; k from the global sums,
+ * dgamma / dbeta from the local ones (they join the gradient all-reduce). */
+int mmh_bn_bwd_finalize_sync(MmhPeer* g, uint32_t seq, const float* sums_local, float* sums_global,
+                             float count_global, float* k, float* dgamma, float* dbeta, int32_t C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -206,9 +206,14 @@ class BNL:
         if training:
             ops.memset0(self.sums)
             ops.bn_stats(raw, rows, ld, self.C, self.sums)
-            count = self.eng.sync_stats(self.sums, count)
-            ops.bn_finalize(self.sums, count, m.weight, m.bias, m.running_mean, m.running_var, BN_MOM, BN_EPS, True,
-                            self.C, self.coef, self.save)
+            w = self.eng.peer_world()
+            if w is not None:       # exchange fused into the finalise kernel (NVLink peer memory)
+                ops.bn_finalize_sync(w, self.sums, count * w.size, m.weight, m.bias, m.running_mean, m.running_var,
+                                     BN_MOM, BN_EPS, self.C, self.coef, self.save)
+            else:
+                count = self.eng.sync_stats(self.sums, count)
+                ops.bn_finalize(self.sums, count, m.weight, m.bias, m.running_mean, m.running_var, BN_MOM, BN_EPS,
+                                True, self.C, self.coef, self.save)
             ops.host(m.note_batch)
         else:
             ops.bn_finalize(None, 1.0, m.weight, m.bias, m.running_mean, m.running_var, BN_MOM, BN_EPS, False, self.C,
@@ -218,9 +223,8 @@ class BNL:
         ops, m = self.eng.ops, self.mod
         ops.memset0(self.bsums)
         ops.bn_bwd_reduce(dz, dz_f32, relu, dropout, key, x, xl, self.coef, self.save, self.bsums)
-        sg, count = self.eng.sync_bwd_stats(self.bsums, self.bsums_g, count)
-        ops.bn_bwd_finalize(sg, self.bsums, count, self.k, m.weight.grad if want_wgrad else None,
-                            m.bias.grad if want_wgrad else None, self.C)
+        self.eng.bwd_finalize(self.bsums, self.bsums_g, count, self.k, m.weight.grad if want_wgrad else None,
+                              m.bias.grad if want_wgrad else None, self.C)
         ops.bn_bwd_apply(dz, dz_f32, relu, dropout, key, x, xl, self.coef, self.save, self.k, dy, yl)
 
 
@@ -254,6 +258,20 @@ class EngineBase:
             self.ops.host(exchange)
             return glob, count * self.world.size
         return local, count
+
+    def peer_world(self):
+        """The data-parallel group if its BN exchanges run through peer memory, else None."""
+        w = self.world
+        return w if (w is not None and w.size > 1 and getattr(w, "peer", None) is not None) else None
+
+    def bwd_finalize(self, local, glob, count, k, dgamma, dbeta, Cc):
+        """k = global (sum dz, sum dz*xhat) / global count; dgamma / dbeta accumulate the local sums."""
+        w = self.peer_world()
+        if w is not None:
+            self.ops.bn_bwd_finalize_sync(w, local, glob, count * w.size, k, dgamma, dbeta, Cc)
+        else:
+            sg, count = self.sync_bwd_stats(local, glob, count)
+            self.ops.bn_bwd_finalize(sg, local, count, k, dgamma, dbeta, Cc)
 
     def convs(self):
         raise NotImplementedError
@@ -492,8 +510,7 @@ class GeneratorEngine(EngineBase):
             ol = c2s[0].g.out_lay
             ops.memset0(bn2.bsums)
             ops.gate_bwd_reduce(self.dtrunk, c2s[0].raw, c2s[1].raw, c2s[2].raw, ol, bn2.coef, bn2.save, bn2.bsums)
-            sg, cnt = self.sync_bwd_stats(bn2.bsums, bn2.bsums_g, B * h4 * w4)
-            ops.bn_bwd_finalize(sg, bn2.bsums, cnt, bn2.k, bn2.mod.weight.grad, bn2.mod.bias.grad, dim)
+            self.bwd_finalize(bn2.bsums, bn2.bsums_g, B * h4 * w4, bn2.k, bn2.mod.weight.grad, bn2.mod.bias.grad, dim)
             ops.gate_bwd_apply(self.dtrunk, c2s[0].raw, c2s[1].raw, c2s[2].raw, ol, bn2.coef, bn2.save, bn2.k, ex2, ex3,
                                c2s[0].dy, c2s[1].dy, c2s[2].dy, ol)
             for s in range(3):

@@ -182,6 +182,28 @@ class Ops:
         self._run(self.lib.mmh_bn_finalize, (_p(sums), float(count), _p(gamma), _p(beta), _p(rm), _p(rv), momentum, eps,
                                              1 if train else 0, Cc, _p(coef), _p(save), self.st()))
 
+    def _seq_args(self, world, args):
+        """Arguments of a launch fused with a peer exchange: slot 1 holds the exchange's sequence number, drawn from
+        the group's counter now and again on every tape replay (all ranks issue the same exchanges in order)."""
+        args = [world.peer, world.next_seq()] + list(args)
+        return args, (lambda step, a, w=world: a.__setitem__(1, w.next_seq()))
+
+    def bn_finalize_sync(self, world, sums, count_global, gamma, beta, rm, rv, momentum, eps, Cc, coef, save):
+        """Train-mode BN finalisation on the statistics of all ranks (exchange over NVLink peer memory inside the
+        kernel; ``sums`` becomes the global sums)."""
+        args, patch = self._seq_args(world, (_p(sums), float(count_global), _p(gamma), _p(beta), _p(rm), _p(rv),
+                                             momentum, eps, Cc, _p(coef), _p(save), self.st()))
+        self._run(self.lib.mmh_bn_finalize_sync, args, patch)
+
+    def bn_bwd_finalize_sync(self, world, sums_local, sums_global, count_global, k, dgamma, dbeta, Cc):
+        args, patch = self._seq_args(world, (_p(sums_local), _p(sums_global), float(count_global), _p(k), _p(dgamma),
+                                             _p(dbeta), Cc, self.st()))
+        self._run(self.lib.mmh_bn_bwd_finalize_sync, args, patch)
+
+    def peer_sum(self, world, data):
+        args, patch = self._seq_args(world, (_p(data), data.numel(), self.st()))
+        self._run(self.lib.mmh_peer_sum, args, patch, keep=data)
+
     def norm_act(self, src, sl: Lay, coef, relu, dropout, key, dst, dl: Lay, pad_lo, pad_hi, reflect, resid=None,
                  dst_f32=None):
         p = L.NormAct()

@@ -170,7 +170,16 @@ _SIMPLE_SIGS = {
     "mmh_adam": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _f32, _vp],
     "mmh_memset": [_vp, _i32, _i64, _vp],
     "mmh_heatmap_rasterize": [_vp, _i64, _i32, _i32, _f64, _f64, _vp, _vp],
+    "mmh_peer_create": [_i32, _i32, C.POINTER(_vp)],
+    "mmh_peer_handle": [_vp, _vp],
+    "mmh_peer_connect": [_vp, _vp],
+    "mmh_peer_status": [_vp],
+    "mmh_peer_destroy": [_vp],
+    "mmh_peer_sum": [_vp, C.c_uint32, _vp, _i32, _vp],
+    "mmh_bn_finalize_sync": [_vp, C.c_uint32, _vp, _f32, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _vp, _vp, _vp],
+    "mmh_bn_bwd_finalize_sync": [_vp, C.c_uint32, _vp, _vp, _f32, _vp, _vp, _vp, _i32, _vp],
 }
+PEER_HANDLE_BYTES = 64
 EXPORTS = ["mmh_version", "mmh_last_error", "mmh_is_device_build", "mmh_conv_plan_create", "mmh_conv_plan_destroy",
            "mmh_conv_run", "mmh_wgrad_plan_create", "mmh_wgrad_plan_destroy", "mmh_wgrad_run"] + list(_SIMPLE_SIGS)
 

@@ -29,14 +29,62 @@ def get_ops(device=None) -> Ops:
 
 
 class World:
-    """Data-parallel group (one process per GPU, torch.distributed)."""
+    """Data-parallel group (one process per GPU, torch.distributed).
+
+    On CUDA the BatchNorm statistics are exchanged inside the BN finalise kernels through mailboxes in NVLink peer
+    memory (``peer``: an MmhPeer handle, include/mmhand_sm100.h; csrc/peer.cu); ``MMH_SYNCBN=nccl`` keeps one NCCL
+    all-reduce per exchange instead (also the path of the gloo CPU tests). Gradients are all-reduced with NCCL."""
 
     def __init__(self):
         import torch.distributed as dist
         self.dist = dist
         self.size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.size > 1 else 0
+        self.peer = None
+        self.seq = 0
+        self._lib = None
 
     def all_reduce(self, t):
         if self.size > 1:
             self.dist.all_reduce(t)
+
+    def next_seq(self):
+        self.seq = self.seq % 0xFFFFFFFF + 1          # 1, 2, ..., never 0 (the mailboxes' initial content)
+        return self.seq
+
+    def enable_peer(self, ops):
+        """Create and connect the peer mailboxes (collective: every rank calls it at the same point). All ranks end
+        up on the same path: if any of them cannot map its peers, everybody falls back to NCCL exchanges."""
+        import ctypes
+        import os
+        import warnings
+        if self.size <= 1 or self.peer is not None or ops.device.type != "cuda":
+            return self.peer is not None
+        if os.environ.get("MMH_SYNCBN", "peer") == "nccl" or not ops.lib.mmh_is_device_build():
+            return False
+        from . import lib as L
+        lib, ok, handle, why = ops.lib, 1, ctypes.c_void_p(), ""
+        mine = ctypes.create_string_buffer(L.PEER_HANDLE_BYTES)
+        if self.size > 8 or lib.mmh_peer_create(self.rank, self.size, ctypes.byref(handle)) != 0 or \
+                lib.mmh_peer_handle(handle, mine) != 0:
+            ok, why = 0, lib.mmh_last_error().decode("utf-8", "replace")
+        everyone = [None] * self.size
+        self.dist.all_gather_object(everyone, (ok, mine.raw))
+        if ok and all(o for o, _ in everyone):
+            if lib.mmh_peer_connect(handle, b"".join(h for _, h in everyone)) != 0:
+                ok, why = 0, lib.mmh_last_error().decode("utf-8", "replace")
+        flag = torch.tensor([ok if all(o for o, _ in everyone) else 0], device=ops.device, dtype=torch.int32)
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            self.peer, self._lib = handle, lib
+            return True
+        if handle:
+            lib.mmh_peer_destroy(handle)
+        if self.rank == 0:
+            warnings.warn("mmhand_b200: peer-memory SyncBN exchange unavailable (%s); using NCCL all-reduces" % why)
+        return False
+
+    def check(self):
+        """Raise if a peer exchange timed out (a rank died): called once per optimisation step, no device sync."""
+        if self.peer is not None and self._lib.mmh_peer_status(self.peer) != 0:
+            raise RuntimeError("mmhand_b200: a SyncBN peer exchange timed out (another rank is gone)")

@@ -50,6 +50,9 @@ class MMHandModel(BaseModel):
         if not self.isTrain or opt.continue_train:
             self.load_network()
         self.world = runtime.World() if getattr(opt, 'distributed', False) else None
+        if self.world is not None and self.world.size > 1 and self.device.type == 'cuda':
+            # SyncBN statistics travel through NVLink peer mailboxes inside the BN kernels (collective set-up)
+            self.world.enable_peer(runtime.get_ops(self.device))
         if self.isTrain:
             self.old_lr = opt.lr
             self.fake_PP_pool = ImagePool(opt.pool_size)
@@ -275,6 +278,8 @@ class MMHandModel(BaseModel):
                     self._segment_D((w,))
         self.overflow = False
         self._step += 1
+        if self.world is not None:
+            self.world.check()
         a, lam = self._acc.clone(), self.opt.lambda_GAN
         self.loss_G_GAN_PB, self.loss_G_GAN_PP = a[0], a[1]
         self.loss_originL1, self.loss_perceptual = a[2], a[3]

@@ -83,15 +83,4 @@ def load_reference_model_class():
     return mm.MMHandModel
 
 
-def make_opt(**over):
-    """Hand-built option namespace (the reference's BaseOptions.parse crashes without --distributed, Q8)."""
-    o = dict(batchSize=1, fineSize=256, H_input_nc=3, P_input_nc=21, D_input_nc=3, output_nc=3, ngf=64, ndf=64,
-             n_layers_D=3, norm='batch', no_dropout=False, no_dropout_D=False, init_type='normal',
-             G_n_downsampling=2, D_n_downsampling=2, padding_type='reflect', no_lsgan=True, lambda_A=10.0,
-             lambda_B=10.0, lambda_GAN=5.0, L1_type='l1_plus_perL1', perceptual_layers=3, percep_is_l1=1,
-             pool_size=50, DG_ratio=1, lr=2e-4, beta1=0.5, lr_policy='lambda', lr_decay_iters=50, niter=100,
-             niter_decay=0, epoch_count=1, continue_train=False, which_epoch='latest', isTrain=True,
-             local_rank='cpu', gpu='cpu', distributed=False, opt_level='O0', seed=49, gpu_ids=[],
-             checkpoints_dir='./checkpoints', name='oracle')
-    o.update(over)
-    return types.SimpleNamespace(**o)
+from mmhand_b200.options import make_opt  # noqa: E402,F401  (kept under its historical name for the tests)

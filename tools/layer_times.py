@@ -14,7 +14,7 @@ import torch  # noqa: E402
 from bench import synth_batch  # noqa: E402
 from mmhand_b200 import runtime  # noqa: E402
 from models.MMHandModel import MMHandModel  # noqa: E402
-from oracle.ref_shims import make_opt  # noqa: E402
+from mmhand_b200.options import make_opt  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=16)

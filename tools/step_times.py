@@ -13,7 +13,7 @@ import torch  # noqa: E402
 
 from bench import ClockSampler, synth_batch  # noqa: E402
 from models.MMHandModel import MMHandModel  # noqa: E402
-from oracle.ref_shims import make_opt  # noqa: E402
+from mmhand_b200.options import make_opt  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 torch.cuda.set_device(0)
