@@ -491,7 +491,7 @@ def run_raster(a):
                 "ms_per_step": ms_e2e / a.steps,
                 "note": "maps stay in HBM for the training step that consumes them; the host reads one checksum"},
         "gpu_launches": launches, "clocks": sampler.summary(),
-        "roofline": {"bound": "hbm", "kernel": "map_kernel<RasterF> (csrc/raster.cu)", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": "raster_kernel (csrc/raster.cu)", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback",
                      "bytes_per_pose": bytes_per_pose},

@@ -323,6 +323,22 @@ int mmh_bn_finalize_sync(MmhPeer* g, uint32_t seq, float* sums, float count_glob
 int mmh_bn_bwd_finalize_sync(MmhPeer* g, uint32_t seq, const float* sums_local, float* sums_global,
                              float count_global, float* k, float* dgamma, float* dbeta, int32_t C, void* stream);
 
+/* ---- one-launch BatchNorm statistics: reduction + (exchange) + finalisation ------------------------
+ * The block of the reduction that finishes last (ticket `counter`, one zero-initialised uint32 per stream) runs the
+ * finalisation of mmh_bn_finalize / mmh_bn_bwd_finalize -- preceded, when `peer` is not NULL, by the peer-memory
+ * exchange above -- and resets the accumulators: `sums` must be zero on entry and is zero again on exit, so a BN
+ * layer costs one launch per direction instead of memset + statistics + finalise. peer == NULL: single GPU
+ * (seq ignored). count_global = elements per channel over all ranks. */
+int mmh_bn_stats_finalize(MmhPeer* peer, uint32_t seq, const void* x, int64_t rows, int32_t ld, int32_t C, float* sums,
+                          uint32_t* counter, float count_global, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, float momentum, float eps, float* coef, float* save,
+                          void* stream);
+/* p->sums: zeroed scratch (local sums), p->k: out; dgamma / dbeta accumulate the local sums (NULL to skip) */
+int mmh_bn_bwd_reduce_finalize(MmhPeer* peer, uint32_t seq, const MmhBnBwd* p, uint32_t* counter, float count_global,
+                               float* dgamma, float* dbeta, void* stream);
+int mmh_gate_bwd_reduce_finalize(MmhPeer* peer, uint32_t seq, const MmhGateBwd* p, uint32_t* counter,
+                                 float count_global, float* dgamma, float* dbeta, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

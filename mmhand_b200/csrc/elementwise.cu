@@ -7,6 +7,7 @@
 
 #include "bn_finalize.h"
 #include "ew_framework.h"
+#include "peer.cuh"
 
 namespace mmh {
 
@@ -511,6 +512,24 @@ extern "C" int mmh_bn_stats(const void* x, int64_t rows, int32_t ld, int32_t C, 
   return launch_reduce_ch<2>(f, make_flatgeom(rows), C / 8, C, sums, stream);
 }
 
+extern "C" int mmh_bn_stats_finalize(MmhPeer* peer, uint32_t seq, const void* x, int64_t rows, int32_t ld, int32_t C,
+                                     float* sums, uint32_t* counter, float count_global, const float* gamma,
+                                     const float* beta, float* running_mean, float* running_var, float momentum,
+                                     float eps, float* coef, float* save, void* stream) {
+  MMH_CHECK(x && sums && counter && coef && save, "null argument");
+  MMH_REQ_VEC(C);
+  MMH_CHECK(rows < (int64_t(1) << 31), "too many rows");
+  BnStatsF f;
+  f.x = static_cast<const act_t*>(x); f.ld = ld;
+  BnFwdFin fin;
+  if (peer_dev(peer, seq, 2 * C, &fin.px)) return 1;
+  fin.sums = sums;
+  fin.f.sums = sums; fin.f.gamma = gamma; fin.f.beta = beta; fin.f.rm = running_mean; fin.f.rv = running_var;
+  fin.f.coef = coef; fin.f.save = save; fin.f.count = count_global; fin.f.momentum = momentum; fin.f.eps = eps;
+  fin.f.train = 1; fin.f.C = C;
+  return launch_reduce_ch_fin<2>(f, make_flatgeom(rows), C / 8, C, sums, fin, counter, stream);
+}
+
 extern "C" int mmh_bn_finalize(const float* sums, float count, const float* gamma, const float* beta,
                                float* running_mean, float* running_var, float momentum, float eps, int32_t train,
                                int32_t C, float* coef, float* save, void* stream) {
@@ -590,6 +609,20 @@ static int bn_bwd_reduce_t(const MmhBnBwd* p, void* stream) {
   f.cm = bn_common<NS, TR>(p);
   return launch_reduce_ch<2>(f, make_rowgeom(p->xl.B, p->xl.H, p->xl.W, 0, 0), p->xl.C / 8, p->xl.C, p->sums, stream);
 }
+static BnBwdFin bwd_fin(const float* sums, float count_global, float* k, float* dgamma, float* dbeta, int C) {
+  BnBwdFin fin;
+  fin.sums = sums;
+  fin.f.sg = nullptr; fin.f.sl = nullptr; fin.f.k = k; fin.f.dgamma = dgamma; fin.f.dbeta = dbeta;
+  fin.f.count = count_global; fin.f.C = C;
+  return fin;
+}
+template <int NS, bool TR>
+static int bn_bwd_reduce_fin_t(const MmhBnBwd* p, const BnBwdFin& fin, uint32_t* counter, void* stream) {
+  BnBwdReduceF<NS, TR> f;
+  f.cm = bn_common<NS, TR>(p);
+  return launch_reduce_ch_fin<2>(f, make_rowgeom(p->xl.B, p->xl.H, p->xl.W, 0, 0), p->xl.C / 8, p->xl.C, p->sums, fin,
+                                 counter, stream);
+}
 template <int NS, bool TR>
 static int bn_bwd_apply_t(const MmhBnBwd* p, void* stream) {
   BnBwdApplyF<NS, TR> f;
@@ -607,6 +640,19 @@ extern "C" int mmh_bn_bwd_reduce(const MmhBnBwd* p, void* stream) {
   if (bn_bwd_check(p)) return 1;
   MMH_CHECK(p->sums, "null argument");
   MMH_BN_BWD_DISPATCH(bn_bwd_reduce_t);
+}
+extern "C" int mmh_bn_bwd_reduce_finalize(MmhPeer* peer, uint32_t seq, const MmhBnBwd* p, uint32_t* counter,
+                                          float count_global, float* dgamma, float* dbeta, void* stream) {
+  if (bn_bwd_check(p)) return 1;
+  MMH_CHECK(p->sums && p->k && counter, "null argument");
+  BnBwdFin fin = bwd_fin(p->sums, count_global, const_cast<float*>(p->k), dgamma, dbeta, p->xl.C);
+  if (peer_dev(peer, seq, 2 * p->xl.C, &fin.px)) return 1;
+  const bool tr = p->trunk != nullptr;
+  if (p->nsrc == 0) return bn_bwd_reduce_fin_t<0, false>(p, fin, counter, stream);
+  if (p->nsrc == 1) return tr ? bn_bwd_reduce_fin_t<1, true>(p, fin, counter, stream)
+                              : bn_bwd_reduce_fin_t<1, false>(p, fin, counter, stream);
+  return tr ? bn_bwd_reduce_fin_t<2, true>(p, fin, counter, stream)
+            : bn_bwd_reduce_fin_t<2, false>(p, fin, counter, stream);
 }
 extern "C" int mmh_bn_bwd_apply(const MmhBnBwd* p, void* stream) {
   if (bn_bwd_check(p)) return 1;
@@ -633,6 +679,18 @@ extern "C" int mmh_gate_bwd_reduce(const MmhGateBwd* p, void* stream) {
   GateBwdReduceF f;
   f.cm = gate_common(p);
   return launch_reduce_ch<2>(f, make_rowgeom(p->sl.B, p->sl.H, p->sl.W, 0, 0), p->sl.C / 8, p->sl.C, p->sums, stream);
+}
+extern "C" int mmh_gate_bwd_reduce_finalize(MmhPeer* peer, uint32_t seq, const MmhGateBwd* p, uint32_t* counter,
+                                            float count_global, float* dgamma, float* dbeta, void* stream) {
+  MMH_CHECK(p && p->dout && p->c1 && p->x2o && p->x3o && p->coef && p->save && p->sums && p->k && counter,
+            "null argument");
+  MMH_REQ_VEC(p->sl.C);
+  GateBwdReduceF f;
+  f.cm = gate_common(p);
+  BnBwdFin fin = bwd_fin(p->sums, count_global, const_cast<float*>(p->k), dgamma, dbeta, p->sl.C);
+  if (peer_dev(peer, seq, 2 * p->sl.C, &fin.px)) return 1;
+  return launch_reduce_ch_fin<2>(f, make_rowgeom(p->sl.B, p->sl.H, p->sl.W, 0, 0), p->sl.C / 8, p->sl.C, p->sums, fin,
+                                 counter, stream);
 }
 extern "C" int mmh_gate_bwd_apply(const MmhGateBwd* p, void* stream) {
   MMH_CHECK(p && p->dout && p->c1 && p->x2o && p->x3o && p->coef && p->save && p->k && p->dy1 && p->dy2 && p->dy3,

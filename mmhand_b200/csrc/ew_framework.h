@@ -221,6 +221,17 @@ int launch_reduce_ch(const F& f, const RowGeom& rg, int groups, int C, float* ou
   }
   return 0;
 }
+// reduction + finalisation in one launch: fin(c) consumes the accumulators of channel c, which return to zero
+template <int NV, class F, class Fin>
+int launch_reduce_ch_fin(const F& f, const RowGeom& rg, int groups, int C, float* out, const Fin& fin, uint32_t*,
+                         void* stream) {
+  launch_reduce_ch<NV>(f, rg, groups, C, out, stream);
+  for (int c = 0; c < C; ++c) {
+    fin(c);
+    for (int v = 0; v < NV; ++v) out[v * C + c] = 0.f;
+  }
+  return 0;
+}
 // scalar reduction: item i returns a float, sum added to *out
 template <class F>
 int launch_reduce_scalar(const F& f, int64_t n, float* out, void*) {
@@ -306,10 +317,9 @@ int launch_pg(const F& f, const RowGeom& rg, int groups, void* stream) {
 // that a launch ends with 2 * SMs * NV * C atomics on the NV * C result words (one block per row used to mean
 // B * H blocks hammering the same few cache lines: measured 41 % of HBM speed on the 512-channel layers).
 template <int NV, class F>
-__global__ void __launch_bounds__(256, 2) reduce_ch_kernel(const F f, const RowGeom rg, const int groups, const int chunks,
-                                                           const int C, float* __restrict__ out) {
+__device__ __forceinline__ void reduce_ch_body(const F& f, const RowGeom& rg, const int groups, const int chunks,
+                                               const int C, float* __restrict__ out, float* red) {
   constexpr int U = F::kUnroll;
-  extern __shared__ float red[];   // [ppb][groups][NV*8]
   const int ppb = blockDim.x / groups;
   const int g = threadIdx.x % groups;
   const int lr = threadIdx.x / groups;
@@ -352,6 +362,36 @@ __global__ void __launch_bounds__(256, 2) reduce_ch_kernel(const F f, const RowG
   }
 }
 template <int NV, class F>
+__global__ void __launch_bounds__(256, 2) reduce_ch_kernel(const F f, const RowGeom rg, const int groups, const int chunks,
+                                                           const int C, float* __restrict__ out) {
+  extern __shared__ float red[];   // [ppb][groups][NV*8]
+  reduce_ch_body<NV>(f, rg, groups, chunks, C, out, red);
+}
+// Same reduction; the block that finishes last (ticket counter) finalises: fin(c) reads the accumulators of channel
+// c (complete: every other block fenced before taking its ticket), does the per-channel arithmetic -- and the
+// cross-GPU exchange when there is one -- and the accumulators and the counter go back to zero for the next launch.
+// One launch instead of memset + reduction + finalise.
+template <int NV, class F, class Fin>
+__global__ void __launch_bounds__(256, 2) reduce_ch_fin_kernel(const F f, const RowGeom rg, const int groups,
+                                                               const int chunks, const int C, float* out,
+                                                               const Fin fin, uint32_t* counter) {
+  extern __shared__ float red[];
+  reduce_ch_body<NV>(f, rg, groups, chunks, C, out, red);
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    fin(c);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) out[v * C + c] = 0.f;
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+template <int NV, class F>
 int launch_reduce_ch(const F& f, const RowGeom& rg, int groups, int C, float* out, void* stream) {
   if (rg.n_rows <= 0 || rg.n_cols <= 0) return 0;
   MMH_CHECK(groups >= 1 && groups <= 256, "channel groups=%d unsupported", groups);
@@ -364,6 +404,26 @@ int launch_reduce_ch(const F& f, const RowGeom& rg, int groups, int C, float* ou
   const int64_t wave = static_cast<int64_t>(num_sms()) * 2;
   const int blocks = static_cast<int>(units < wave ? units : wave);
   reduce_ch_kernel<NV, F><<<blocks, threads, smem, static_cast<cudaStream_t>(stream)>>>(f, rg, groups, chunks, C, out);
+  MMH_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int NV, class F, class Fin>
+int launch_reduce_ch_fin(const F& f, const RowGeom& rg, int groups, int C, float* out, const Fin& fin,
+                         uint32_t* counter, void* stream) {
+  if (rg.n_rows <= 0 || rg.n_cols <= 0) return 0;
+  MMH_CHECK(groups >= 1 && groups <= 256, "channel groups=%d unsupported", groups);
+  MMH_CHECK(counter != nullptr, "null ticket counter");
+  const int threads = pg_threads(groups);
+  const int ppb = threads / groups;
+  const size_t smem = static_cast<size_t>(threads) * NV * 8 * sizeof(float);
+  const int chunks = (rg.n_cols + ppb * F::kUnroll - 1) / (ppb * F::kUnroll);
+  const int64_t units = static_cast<int64_t>(rg.n_rows) * chunks;
+  MMH_CHECK(units < (int64_t(1) << 31), "too many work units");
+  const int64_t wave = static_cast<int64_t>(num_sms()) * 2;
+  const int blocks = static_cast<int>(units < wave ? units : wave);
+  reduce_ch_fin_kernel<NV, F, Fin><<<blocks, threads, smem, static_cast<cudaStream_t>(stream)>>>(f, rg, groups, chunks, C,
+                                                                                             out, fin, counter);
   MMH_CUDA(cudaGetLastError());
   return 0;
 }

@@ -19,10 +19,19 @@
 
 #include "../../include/mmhand_sm100.h"
 #include "bn_finalize.h"
+#include "peer.cuh"
 #include "host_common.h"
 
 #ifdef MMH_HOST_EMU
 // The host emulation (CPU tests) has no peer memory: the entry points exist and fail loudly.
+namespace mmh {
+int peer_dev(const MmhPeer* g, uint32_t, int, PeerDev* d) {
+  MMH_CHECK(g == nullptr, "peer mailboxes need CUDA devices");
+  for (int r = 0; r < kPeerMaxWorld; ++r) d->box[r] = nullptr;
+  d->status = nullptr; d->rank = 0; d->world = 1; d->seq = 0;
+  return 0;
+}
+}  // namespace mmh
 extern "C" int mmh_peer_create(int32_t, int32_t, MmhPeer**) { MMH_CHECK(false, "peer mailboxes need CUDA devices"); }
 extern "C" int mmh_peer_handle(MmhPeer*, void*) { MMH_CHECK(false, "peer mailboxes need CUDA devices"); }
 extern "C" int mmh_peer_connect(MmhPeer*, const void*) { MMH_CHECK(false, "peer mailboxes need CUDA devices"); }
@@ -44,56 +53,6 @@ extern "C" int mmh_bn_bwd_finalize_sync(MmhPeer*, uint32_t, const float*, float*
 #include <cuda_runtime.h>
 
 namespace mmh {
-
-constexpr int kPeerMaxWorld = 8;
-constexpr int kPeerSlots = 4;
-constexpr int kPeerWords = 2048;                      // >= 2 * C of the widest BN layer (C <= 1024)
-constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
-
-struct PeerDev {
-  unsigned long long* box[kPeerMaxWorld];
-  int* status;
-  int rank, world;
-  uint32_t seq;
-};
-
-__device__ __forceinline__ size_t peer_off(const PeerDev& p, int src, int w) {
-  return (static_cast<size_t>(p.seq & (kPeerSlots - 1)) * p.world + src) * kPeerWords + w;
-}
-__device__ __forceinline__ void peer_post(const PeerDev& p, float v, int w) {
-  const unsigned long long word = (static_cast<unsigned long long>(p.seq) << 32) | __float_as_uint(v);
-  const size_t off = peer_off(p, p.rank, w);
-  for (int r = 0; r < p.world; ++r)
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.box[r] + off), "l"(word) : "memory");
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ float peer_collect(const PeerDev& p, int w) {
-  float s = 0.f;
-  unsigned long long t0 = 0;
-  for (int r = 0; r < p.world; ++r) {
-    const unsigned long long* src = p.box[p.rank] + peer_off(p, r, w);
-    unsigned long long word;
-    uint32_t spins = 0;
-    while (true) {
-      asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(word) : "l"(src) : "memory");
-      if (static_cast<uint32_t>(word >> 32) == p.seq) break;
-      if ((++spins & 0x3FFu) == 0) {
-        const unsigned long long now = globaltimer_ns();
-        if (t0 == 0) t0 = now;
-        if (now - t0 > kPeerTimeoutNs) {
-          *p.status = 1;                              // host-mapped: visible to mmh_peer_status without a sync
-          return __int_as_float(0x7FC00000);
-        }
-      }
-    }
-    s += __uint_as_float(static_cast<uint32_t>(word));
-  }
-  return s;
-}
 
 __global__ void __launch_bounds__(256) peer_sum_kernel(const PeerDev p, float* __restrict__ data, const int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -194,17 +153,24 @@ extern "C" int mmh_peer_destroy(MmhPeer* g) {
   return 0;
 }
 
-static int peer_dev(const MmhPeer* g, uint32_t seq, int words, PeerDev* d) {
-  MMH_CHECK(g != nullptr && g->connected, "peer group not connected");
+namespace mmh {
+int peer_dev(const MmhPeer* g, uint32_t seq, int words, PeerDev* d) {
+  if (g == nullptr) {                 // single GPU: no exchange
+    for (int r = 0; r < kPeerMaxWorld; ++r) d->box[r] = nullptr;
+    d->status = nullptr; d->rank = 0; d->world = 1; d->seq = 0;
+    return 0;
+  }
+  MMH_CHECK(g->connected, "peer group not connected");
   MMH_CHECK(seq != 0, "sequence numbers start at 1");
   MMH_CHECK(words >= 1 && words <= kPeerWords, "%d words exceed the mailbox (%d)", words, kPeerWords);
-  for (int r = 0; r < g->world; ++r) d->box[r] = g->peers[r];
+  for (int r = 0; r < kPeerMaxWorld; ++r) d->box[r] = r < g->world ? g->peers[r] : nullptr;
   d->status = g->status_dev; d->rank = g->rank; d->world = g->world; d->seq = seq;
   return 0;
 }
+}  // namespace mmh
 
 extern "C" int mmh_peer_sum(MmhPeer* g, uint32_t seq, float* data, int32_t n, void* stream) {
-  MMH_CHECK(data != nullptr, "null argument");
+  MMH_CHECK(data != nullptr && g != nullptr, "null argument");
   PeerDev d;
   if (peer_dev(g, seq, n, &d)) return 1;
   peer_sum_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(d, data, n);
@@ -215,7 +181,7 @@ extern "C" int mmh_peer_sum(MmhPeer* g, uint32_t seq, float* data, int32_t n, vo
 extern "C" int mmh_bn_finalize_sync(MmhPeer* g, uint32_t seq, float* sums, float count_global, const float* gamma,
                                     const float* beta, float* running_mean, float* running_var, float momentum,
                                     float eps, int32_t C, float* coef, float* save, void* stream) {
-  MMH_CHECK(sums && coef && save, "null argument");
+  MMH_CHECK(sums && coef && save && g, "null argument");
   PeerDev d;
   if (peer_dev(g, seq, 2 * C, &d)) return 1;
   BnFinalizeF f;
@@ -229,7 +195,7 @@ extern "C" int mmh_bn_finalize_sync(MmhPeer* g, uint32_t seq, float* sums, float
 extern "C" int mmh_bn_bwd_finalize_sync(MmhPeer* g, uint32_t seq, const float* sums_local, float* sums_global,
                                         float count_global, float* k, float* dgamma, float* dbeta, int32_t C,
                                         void* stream) {
-  MMH_CHECK(sums_local && sums_global && k, "null argument");
+  MMH_CHECK(sums_local && sums_global && k && g, "null argument");
   PeerDev d;
   if (peer_dev(g, seq, 2 * C, &d)) return 1;
   BnBwdFinalizeF f;

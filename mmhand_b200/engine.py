@@ -204,14 +204,17 @@ class BNL:
     def forward(self, raw, rows, ld, count, training):
         ops, m = self.eng.ops, self.mod
         if training:
-            ops.memset0(self.sums)
-            ops.bn_stats(raw, rows, ld, self.C, self.sums)
-            w = self.eng.peer_world()
-            if w is not None:       # exchange fused into the finalise kernel (NVLink peer memory)
-                ops.bn_finalize_sync(w, self.sums, count * w.size, m.weight, m.bias, m.running_mean, m.running_var,
-                                     BN_MOM, BN_EPS, self.C, self.coef, self.save)
-            else:
-                count = self.eng.sync_stats(self.sums, count)
+            eng = self.eng
+            if eng.fused_stats():
+                # one launch: sums -> (peer exchange) -> coefficients; self.sums returns to zero
+                w = eng.peer_world()
+                ops.bn_stats_finalize(w, raw, rows, ld, self.C, self.sums, eng.ticket, count * (w.size if w else 1),
+                                      m.weight, m.bias, m.running_mean, m.running_var, BN_MOM, BN_EPS, self.coef,
+                                      self.save)
+            else:               # NCCL / gloo groups: statistics, all-reduce, finalise
+                ops.memset0(self.sums)
+                ops.bn_stats(raw, rows, ld, self.C, self.sums)
+                count = eng.sync_stats(self.sums, count)
                 ops.bn_finalize(self.sums, count, m.weight, m.bias, m.running_mean, m.running_var, BN_MOM, BN_EPS,
                                 True, self.C, self.coef, self.save)
             ops.host(m.note_batch)
@@ -221,10 +224,16 @@ class BNL:
 
     def backward(self, dz, dz_f32, relu, dropout, key, x, xl, dy, yl, count, want_wgrad=True):
         ops, m = self.eng.ops, self.mod
-        ops.memset0(self.bsums)
-        ops.bn_bwd_reduce(dz, dz_f32, relu, dropout, key, x, xl, self.coef, self.save, self.bsums)
-        self.eng.bwd_finalize(self.bsums, self.bsums_g, count, self.k, m.weight.grad if want_wgrad else None,
-                              m.bias.grad if want_wgrad else None, self.C)
+        eng = self.eng
+        dg, db = (m.weight.grad, m.bias.grad) if want_wgrad else (None, None)
+        if eng.fused_stats():
+            w = eng.peer_world()
+            ops.bn_bwd_reduce_finalize(w, dz, dz_f32, relu, dropout, key, x, xl, self.coef, self.save, self.bsums,
+                                       self.k, eng.ticket, count * (w.size if w else 1), dg, db)
+        else:
+            ops.memset0(self.bsums)
+            ops.bn_bwd_reduce(dz, dz_f32, relu, dropout, key, x, xl, self.coef, self.save, self.bsums)
+            eng.bwd_finalize(self.bsums, self.bsums_g, count, self.k, dg, db, self.C)
         ops.bn_bwd_apply(dz, dz_f32, relu, dropout, key, x, xl, self.coef, self.save, self.k, dy, yl)
 
 
@@ -234,6 +243,7 @@ class EngineBase:
         self._scratch = {}
         self.world = world         # None or an object with all_reduce(tensor) and size
         self.store = ParamStore(ops, module)
+        self.ticket = ops.zeros(1, dtype=torch.int32)    # "last block" ticket of the one-launch statistics kernels
         self.packed_version = None
         self.seed = 0
 
@@ -258,6 +268,12 @@ class EngineBase:
             self.ops.host(exchange)
             return glob, count * self.world.size
         return local, count
+
+    def fused_stats(self):
+        """One-launch BN statistics (reduction + exchange + finalisation in the last block): always, except when the
+        group exchanges through torch.distributed collectives (MMH_SYNCBN=nccl, gloo in the CPU tests)."""
+        w = self.world
+        return w is None or w.size <= 1 or getattr(w, "peer", None) is not None
 
     def peer_world(self):
         """The data-parallel group if its BN exchanges run through peer memory, else None."""
@@ -508,9 +524,16 @@ class GeneratorEngine(EngineBase):
                 ex2, ex3 = s3.view(0, dim), s2.view(0, dim)
             c2s, bn2 = b["c2"], b["bn2"]
             ol = c2s[0].g.out_lay
-            ops.memset0(bn2.bsums)
-            ops.gate_bwd_reduce(self.dtrunk, c2s[0].raw, c2s[1].raw, c2s[2].raw, ol, bn2.coef, bn2.save, bn2.bsums)
-            self.bwd_finalize(bn2.bsums, bn2.bsums_g, B * h4 * w4, bn2.k, bn2.mod.weight.grad, bn2.mod.bias.grad, dim)
+            if self.fused_stats():
+                w = self.peer_world()
+                ops.gate_bwd_reduce_finalize(w, self.dtrunk, c2s[0].raw, c2s[1].raw, c2s[2].raw, ol, bn2.coef, bn2.save,
+                                             bn2.bsums, bn2.k, self.ticket, B * h4 * w4 * (w.size if w else 1),
+                                             bn2.mod.weight.grad, bn2.mod.bias.grad)
+            else:
+                ops.memset0(bn2.bsums)
+                ops.gate_bwd_reduce(self.dtrunk, c2s[0].raw, c2s[1].raw, c2s[2].raw, ol, bn2.coef, bn2.save, bn2.bsums)
+                self.bwd_finalize(bn2.bsums, bn2.bsums_g, B * h4 * w4, bn2.k, bn2.mod.weight.grad, bn2.mod.bias.grad,
+                                  dim)
             ops.gate_bwd_apply(self.dtrunk, c2s[0].raw, c2s[1].raw, c2s[2].raw, ol, bn2.coef, bn2.save, bn2.k, ex2, ex3,
                                c2s[0].dy, c2s[1].dy, c2s[2].dy, ol)
             for s in range(3):

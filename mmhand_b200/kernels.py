@@ -188,6 +188,39 @@ class Ops:
         args = [world.peer, world.next_seq()] + list(args)
         return args, (lambda step, a, w=world: a.__setitem__(1, w.next_seq()))
 
+    def _peer_args(self, world, args, patch=None):
+        """(peer, seq) prefix of the one-launch statistics kernels: no group -> (NULL, 0) and only the caller's
+        patch; with a group, the sequence number is refreshed on replay as well."""
+        if world is None:
+            return [None, 0] + list(args), patch
+        args, seq_patch = self._seq_args(world, args)
+        if patch is None:
+            return args, seq_patch
+        return args, (lambda step, a, p0=patch, p1=seq_patch: (p0(step, a), p1(step, a)))
+
+    def bn_stats_finalize(self, world, x, rows, ld, Cc, sums, counter, count_global, gamma, beta, rm, rv, momentum,
+                          eps, coef, save):
+        """Train-mode BatchNorm statistics in ONE launch: per-channel sums, (peer exchange,) mean / rstd / affine
+        coefficients / running statistics in the last block, accumulators back to zero."""
+        args, patch = self._peer_args(world, (_p(x), rows, ld, Cc, _p(sums), _p(counter), float(count_global),
+                                              _p(gamma), _p(beta), _p(rm), _p(rv), momentum, eps, _p(coef), _p(save),
+                                              self.st()))
+        self._run(self.lib.mmh_bn_stats_finalize, args, patch)
+
+    def bn_bwd_reduce_finalize(self, world, dz, dz_f32, relu, dropout, key, x, xl, coef, save, sums, k, counter,
+                               count_global, dgamma, dbeta):
+        p, patch = self._bn_bwd(dz, dz_f32, relu, dropout, key, x, xl, coef, save, sums=sums, k=k)
+        args, patch = self._peer_args(world, (C.byref(p), _p(counter), float(count_global), _p(dgamma), _p(dbeta),
+                                              self.st()), patch)
+        self._run(self.lib.mmh_bn_bwd_reduce_finalize, args, patch, keep=p)
+
+    def gate_bwd_reduce_finalize(self, world, dout, c1, x2o, x3o, sl, coef, save, sums, k, counter, count_global,
+                                 dgamma, dbeta):
+        p = self._gate_bwd(dout, c1, x2o, x3o, sl, coef, save, sums=sums, k=k)
+        args, patch = self._peer_args(world, (C.byref(p), _p(counter), float(count_global), _p(dgamma), _p(dbeta),
+                                              self.st()))
+        self._run(self.lib.mmh_gate_bwd_reduce_finalize, args, patch, keep=p)
+
     def bn_finalize_sync(self, world, sums, count_global, gamma, beta, rm, rv, momentum, eps, Cc, coef, save):
         """Train-mode BN finalisation on the statistics of all ranks (exchange over NVLink peer memory inside the
         kernel; ``sums`` becomes the global sums)."""

@@ -178,6 +178,10 @@ _SIMPLE_SIGS = {
     "mmh_peer_sum": [_vp, C.c_uint32, _vp, _i32, _vp],
     "mmh_bn_finalize_sync": [_vp, C.c_uint32, _vp, _f32, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _vp, _vp, _vp],
     "mmh_bn_bwd_finalize_sync": [_vp, C.c_uint32, _vp, _vp, _f32, _vp, _vp, _vp, _i32, _vp],
+    "mmh_bn_stats_finalize": [_vp, C.c_uint32, _vp, _i64, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _f32, _f32, _vp,
+                              _vp, _vp],
+    "mmh_bn_bwd_reduce_finalize": [_vp, C.c_uint32, C.POINTER(BnBwd), _vp, _f32, _vp, _vp, _vp],
+    "mmh_gate_bwd_reduce_finalize": [_vp, C.c_uint32, C.POINTER(GateBwd), _vp, _f32, _vp, _vp, _vp],
 }
 PEER_HANDLE_BYTES = 64
 EXPORTS = ["mmh_version", "mmh_last_error", "mmh_is_device_build", "mmh_conv_plan_create", "mmh_conv_plan_destroy",
