@@ -339,6 +339,14 @@ int mmh_bn_bwd_reduce_finalize(MmhPeer* peer, uint32_t seq, const MmhBnBwd* p, u
 int mmh_gate_bwd_reduce_finalize(MmhPeer* peer, uint32_t seq, const MmhGateBwd* p, uint32_t* counter,
                                  float count_global, float* dgamma, float* dbeta, void* stream);
 
+/* ---- stream ordering (cudaEvent wrappers, so that recorded launch sequences can fork / join streams) ----
+ * The weight-gradient kernels of a layer run on a side stream next to the bandwidth-bound BatchNorm-backward
+ * kernels of the following layers (apex's delay_allreduce backward has no such overlap, MMHandModel.py:110-116). */
+int mmh_event_create(void** ev);
+int mmh_event_destroy(void* ev);
+int mmh_event_record(void* ev, void* stream);
+int mmh_stream_wait_event(void* stream, void* ev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,3 +83,31 @@ extern "C" int mmh_is_device_build(void) { return 0; }
 #else
 extern "C" int mmh_is_device_build(void) { return 1; }
 #endif
+
+/* ---- stream-ordering primitives for the launch tapes (side-stream weight gradients) ---- */
+#ifdef MMH_HOST_EMU
+extern "C" int mmh_event_create(void** ev) { MMH_CHECK(ev != nullptr, "null argument"); *ev = reinterpret_cast<void*>(0x1); return 0; }
+extern "C" int mmh_event_destroy(void*) { return 0; }
+extern "C" int mmh_event_record(void*, void*) { return 0; }
+extern "C" int mmh_stream_wait_event(void*, void*) { return 0; }
+#else
+extern "C" int mmh_event_create(void** ev) {
+  MMH_CHECK(ev != nullptr, "null argument");
+  cudaEvent_t e;
+  MMH_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  *ev = e;
+  return 0;
+}
+extern "C" int mmh_event_destroy(void* ev) {
+  if (ev != nullptr) MMH_CUDA(cudaEventDestroy(static_cast<cudaEvent_t>(ev)));
+  return 0;
+}
+extern "C" int mmh_event_record(void* ev, void* stream) {
+  MMH_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev), static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+extern "C" int mmh_stream_wait_event(void* stream, void* ev) {
+  MMH_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), static_cast<cudaEvent_t>(ev), 0));
+  return 0;
+}
+#endif

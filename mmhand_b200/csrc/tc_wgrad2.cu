@@ -439,7 +439,14 @@ int mmh_wgrad2_create(const MmhWgradDesc* d, MmhWgrad2** out_plan) {
   k.win_off = (k.dy_boxes * k.dy_box_bytes + 1023u) & ~1023u;
   k.stage_bytes = k.win_off + k.n_groups * k.w_bytes;
   k.stage_bytes = (k.stage_bytes + 1023u) & ~1023u;
-  const uint32_t budget = 227 * 1024 - 1024 - 256;
+  // The weight gradient runs on a side stream next to the bandwidth-bound BN-backward kernels (engine.py::run_bwd):
+  // leave room in shared memory for two of their blocks (2 x (16 KB + 1 KB)) so that they can be co-resident.
+  static const uint32_t cap_kb = [] {
+    const char* e = getenv("MMH_WGRAD_SMEM_KB");
+    const int v = e != nullptr ? atoi(e) : 190;
+    return static_cast<uint32_t>(v < 64 ? 64 : (v > 227 ? 227 : v));
+  }();
+  const uint32_t budget = cap_kb * 1024 - 1024 - 256;
   k.n_stages = budget / k.stage_bytes;
   if (k.n_stages > kW2MaxStages) k.n_stages = kW2MaxStages;
   if (k.n_stages < 2) { set_error("wgrad tile does not fit in shared memory"); return fail(); }

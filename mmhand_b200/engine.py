@@ -107,6 +107,7 @@ class ConvL:
                                      bias=self.bias_p, act=act, out_f32=out_f32)
         self.bwd_ready = False
         self.has_wgrad = False
+        self.own_dy = False
         self.dw = None
 
     # weight strides (n = out channel, c = in channel, t = tap) of the fp32 master tensor
@@ -147,6 +148,10 @@ class ConvL:
         if self.bwd_ready:
             return
         ops, g = self.eng.ops, self.g
+        # with side-stream weight gradients dy is read asynchronously: every conv owns its dy (no sharing)
+        self.own_dy = need_wgrad and ops.side_stream is not None
+        if self.own_dy:
+            dy_key = (dy_key, self.name)
         self.dy = self.eng.scratch(("dy", dy_key, g.out_lay.rows, self.Cout_p), g.out_lay.rows, self.Cout_p)
         if self.need_dx:
             self.dx = self.eng.scratch(("dx", dx_key, g.in_lay.rows, self.Cin_p), g.in_lay.rows, self.Cin_p)
@@ -176,16 +181,29 @@ class ConvL:
     def run_bwd(self, want_wgrad=True, want_dx=True):
         """Consumes self.dy. Weight gradient accumulates into weight.grad; data gradient lands in self.dx."""
         ops = self.eng.ops
-        if want_wgrad and self.has_wgrad:
-            for p in self.wgrad:
-                ops.run_wgrad(p, (self.name, "wgrad"))
+        do_w = want_wgrad and self.has_wgrad
+        # The weight gradient is off the critical path (nothing before the optimiser reads it): it goes to the side
+        # stream, where it overlaps the bandwidth-bound BN-backward kernels of the next layers; the data gradient,
+        # which those kernels wait for, is enqueued first.
+        overlap = do_w and ops.side_stream is not None and self.own_dy
+        if overlap:
+            ops.fork()
+        if want_dx and self.need_dx:
+            for p in self.dgrad:
+                ops.run_conv(p, (self.name, "dgrad"))
+        if do_w:
+            if overlap:
+                with ops.side():
+                    for p in self.wgrad:
+                        ops.run_wgrad(p, (self.name, "wgrad"))
+                self.eng.side_pending = True
+            else:
+                for p in self.wgrad:
+                    ops.run_wgrad(p, (self.name, "wgrad"))
             if self.bias is not None:
                 ops.memset0(self.dbias)
                 ops.bn_stats(self.dy, self.g.out_lay.rows, self.Cout_p, self.Cout_p, self.dbias)
                 ops.unpack_wgrad(self.dbias, self.bias.grad, 1, 0, 0, self.Cout, 1, 1, True)
-        if want_dx and self.need_dx:
-            for p in self.dgrad:
-                ops.run_conv(p, (self.name, "dgrad"))
 
     def dx_source(self):
         g = self.g
@@ -328,6 +346,9 @@ class EngineBase:
         self.ops.memset0(self.dw_all)
 
     def end_wgrad(self):
+        if getattr(self, "side_pending", False):
+            self.ops.join()            # weight gradients launched on the side stream are complete past this point
+            self.side_pending = False
         if getattr(self, "_unpack_table", None) is None:
             self.store.ensure()
             self._unpack_table = self.ops.make_param_jobs([c.unpack_job() for c in self.convs() if c.has_wgrad])

@@ -83,7 +83,7 @@ class Tape:
 
     @property
     def n_launches(self):
-        return sum(1 for c in self.cmds if c[0] is not None)
+        return sum(1 for c in self.cmds if c[0] is not None and not getattr(c[0], "_mmh_no_kernel", False))
 
 
 class Ops:
@@ -95,6 +95,8 @@ class Ops:
         self.act_dtype = torch.bfloat16 if lib.act_bytes == 2 else torch.float32
         self.tape = None
         self.step = 0            # training step used to resolve KeyRefs in immediate mode
+        self.side_stream = None  # torch.cuda.Stream of the weight-gradient kernels (None: everything on one stream)
+        self._ev = None
         self.conv_hook = None    # optional callable(kind, plan, launch) wrapping conv launches (bench instrumentation)
 
     @staticmethod
@@ -103,7 +105,45 @@ class Ops:
         if not torch.cuda.is_available():
             raise L.MmhError("mmhand_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
-        return Ops(lib, dev, lambda: torch.cuda.current_stream(dev).cuda_stream)
+        ops = Ops(lib, dev, lambda: torch.cuda.current_stream(dev).cuda_stream)
+        import os
+        if os.environ.get("MMH_WGRAD_STREAM", "1") != "0":
+            ops.enable_side_stream(torch.cuda.Stream(dev))
+        return ops
+
+    # ------------------------------------------------------------------ side stream (weight gradients)
+    def enable_side_stream(self, stream):
+        self.side_stream = stream
+        ev = [C.c_void_p(), C.c_void_p()]
+        for e in ev:
+            if self.lib.mmh_event_create(C.byref(e)) != 0:
+                raise L.MmhError(self.lib.mmh_last_error().decode("utf-8", "replace"))
+        self._ev = ev
+
+    def fork(self):
+        """Everything enqueued on the main stream so far happens-before what is launched inside ``side()`` next.
+        (An event may be re-recorded at once: a wait refers to the record that preceded it.)"""
+        side = C.c_void_p(self.side_stream.cuda_stream)
+        self._run(self.lib.mmh_event_record, (self._ev[0], self.st()))
+        self._run(self.lib.mmh_stream_wait_event, (side, self._ev[0]))
+        self.launches -= 2
+
+    def join(self):
+        """The main stream waits for everything launched on the side stream so far."""
+        side = C.c_void_p(self.side_stream.cuda_stream)
+        self._run(self.lib.mmh_event_record, (self._ev[1], side))
+        self._run(self.lib.mmh_stream_wait_event, (self.st(), self._ev[1]))
+        self.launches -= 2
+
+    @contextmanager
+    def side(self):
+        old = self._stream
+        h = self.side_stream.cuda_stream
+        self._stream = lambda: h
+        try:
+            yield
+        finally:
+            self._stream = old
 
     # ------------------------------------------------------------------ launch plumbing
     def st(self):

@@ -142,6 +142,8 @@ def _declare(lib):
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = C.c_int
+    for name in ("mmh_event_record", "mmh_stream_wait_event"):
+        getattr(lib, name)._mmh_no_kernel = True       # stream ordering, not kernels: not counted as launches
 
 
 _vp, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
@@ -182,6 +184,10 @@ _SIMPLE_SIGS = {
                               _vp, _vp],
     "mmh_bn_bwd_reduce_finalize": [_vp, C.c_uint32, C.POINTER(BnBwd), _vp, _f32, _vp, _vp, _vp],
     "mmh_gate_bwd_reduce_finalize": [_vp, C.c_uint32, C.POINTER(GateBwd), _vp, _f32, _vp, _vp, _vp],
+    "mmh_event_create": [C.POINTER(_vp)],
+    "mmh_event_destroy": [_vp],
+    "mmh_event_record": [_vp, _vp],
+    "mmh_stream_wait_event": [_vp, _vp],
 }
 PEER_HANDLE_BYTES = 64
 EXPORTS = ["mmh_version", "mmh_last_error", "mmh_is_device_build", "mmh_conv_plan_create", "mmh_conv_plan_destroy",
