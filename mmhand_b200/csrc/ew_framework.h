@@ -15,6 +15,7 @@
 // Grids are sized in multiples of the SM count.
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 
 #ifndef MMH_HOST_EMU
 #include <cuda_bf16.h>
@@ -270,8 +271,22 @@ inline dim3 row_grid(const RowGeom& rg, int max_split, int per_sm) {
   return dim3(static_cast<unsigned>(split), static_cast<unsigned>(rg.h_ext), static_cast<unsigned>(rg.n_rows / rg.h_ext));
 }
 
-// threads per block: the largest multiple of `groups` <= 256 (a thread never changes its channel group)
-inline int pg_threads(int groups) { return (256 / groups) * groups; }
+// threads per block: the largest multiple of `groups` <= the block size (a thread never changes its channel group).
+// Block size 128 (default; MMH_EW_THREADS=256 for the old setting): four blocks per SM alone, and three of them
+// (instead of one of 256 threads) fit in the registers left by a resident weight-gradient CTA of the side stream
+// (measured: 55.3 -> 54.5 ms per training step with the side stream, no change without it).
+inline int ew_block_threads() {
+  static const int t = [] {
+    const char* e = getenv("MMH_EW_THREADS");
+    const int v = e != nullptr ? atoi(e) : 128;
+    return v == 256 ? 256 : 128;
+  }();
+  return t;
+}
+inline int pg_threads(int groups) {
+  const int t = groups > ew_block_threads() ? 256 : ew_block_threads();
+  return (t / groups) * groups;
+}
 
 
 template <class F>
@@ -401,7 +416,7 @@ int launch_reduce_ch(const F& f, const RowGeom& rg, int groups, int C, float* ou
   const int chunks = (rg.n_cols + ppb * F::kUnroll - 1) / (ppb * F::kUnroll);
   const int64_t units = static_cast<int64_t>(rg.n_rows) * chunks;
   MMH_CHECK(units < (int64_t(1) << 31), "too many work units");
-  const int64_t wave = static_cast<int64_t>(num_sms()) * 2;
+  const int64_t wave = static_cast<int64_t>(num_sms()) * (512 / ew_block_threads());
   const int blocks = static_cast<int>(units < wave ? units : wave);
   reduce_ch_kernel<NV, F><<<blocks, threads, smem, static_cast<cudaStream_t>(stream)>>>(f, rg, groups, chunks, C, out);
   MMH_CUDA(cudaGetLastError());
@@ -420,7 +435,7 @@ int launch_reduce_ch_fin(const F& f, const RowGeom& rg, int groups, int C, float
   const int chunks = (rg.n_cols + ppb * F::kUnroll - 1) / (ppb * F::kUnroll);
   const int64_t units = static_cast<int64_t>(rg.n_rows) * chunks;
   MMH_CHECK(units < (int64_t(1) << 31), "too many work units");
-  const int64_t wave = static_cast<int64_t>(num_sms()) * 2;
+  const int64_t wave = static_cast<int64_t>(num_sms()) * (512 / ew_block_threads());
   const int blocks = static_cast<int>(units < wave ? units : wave);
   reduce_ch_fin_kernel<NV, F, Fin><<<blocks, threads, smem, static_cast<cudaStream_t>(stream)>>>(f, rg, groups, chunks, C,
                                                                                              out, fin, counter);

@@ -458,7 +458,14 @@ int mmh_wgrad2_create(const MmhWgradDesc* d, MmhWgrad2** out_plan) {
   const int units = k.units_g * k.tiles_n * k.tiles_c;
   int split = d->split_k;
   if (split <= 0) {
-    const int slots = num_sms() / ncta;
+    // CTAs per launch = `waves` x the SM count: with several short waves a lower-priority side-stream launch hands
+    // the SMs over to a main-stream convolution at the next CTA boundary instead of holding them to the end
+    static const int waves = [] {
+      const char* e = getenv("MMH_WGRAD_WAVES");
+      const int v = e != nullptr ? atoi(e) : 1;
+      return v < 1 ? 1 : (v > 8 ? 8 : v);
+    }();
+    const int slots = waves * (num_sms() / ncta);
     split = slots / units;
     const int max_split = k.ksteps_total / 8 > 0 ? k.ksteps_total / 8 : 1;
     if (split > max_split) split = max_split;

@@ -95,6 +95,8 @@ class Ops:
         self.act_dtype = torch.bfloat16 if lib.act_bytes == 2 else torch.float32
         self.tape = None
         self.step = 0            # training step used to resolve KeyRefs in immediate mode
+        self.main_stream = None  # optional high-priority stream of the critical path (see Ops.cuda)
+        self.in_side = None      # the torch stream launches currently go to, when it is a side stream
         self.side_stream = None  # torch.cuda.Stream of the weight-gradient kernels (None: everything on one stream)
         self._ev = None
         self.conv_hook = None    # optional callable(kind, plan, launch) wrapping conv launches (bench instrumentation)
@@ -108,44 +110,54 @@ class Ops:
         ops = Ops(lib, dev, lambda: torch.cuda.current_stream(dev).cuda_stream)
         import os
         if os.environ.get("MMH_WGRAD_STREAM", "1") != "0":
-            ops.enable_side_stream(torch.cuda.Stream(dev))
+            ops.enable_side_stream(torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+            if os.environ.get("MMH_MAIN_PRIORITY", "0") != "0":
+                # critical-path launches on a high-priority stream: its CTAs are placed before pending side-stream ones
+                ops.main_stream = torch.cuda.Stream(dev, priority=-1)
         return ops
 
     # ------------------------------------------------------------------ side stream (weight gradients)
-    def enable_side_stream(self, stream):
+    def enable_side_stream(self, stream, update_stream=None):
+        """stream: weight-gradient kernels (index 0); update_stream: optimiser update of one network under the
+        compute of another (index 1, defaults to the same stream)."""
         self.side_stream = stream
-        ev = [C.c_void_p(), C.c_void_p()]
-        for e in ev:
+        self._sides = [stream, update_stream if update_stream is not None else stream]
+        self._ev = []
+        for _ in range(4):
+            e = C.c_void_p()
             if self.lib.mmh_event_create(C.byref(e)) != 0:
                 raise L.MmhError(self.lib.mmh_last_error().decode("utf-8", "replace"))
-        self._ev = ev
+            self._ev.append(e)
 
-    def fork(self):
-        """Everything enqueued on the main stream so far happens-before what is launched inside ``side()`` next.
+    def fork(self, which=0):
+        """Everything enqueued on the main stream so far happens-before what is launched inside ``side(which)`` next.
         (An event may be re-recorded at once: a wait refers to the record that preceded it.)"""
-        side = C.c_void_p(self.side_stream.cuda_stream)
-        self._run(self.lib.mmh_event_record, (self._ev[0], self.st()))
-        self._run(self.lib.mmh_stream_wait_event, (side, self._ev[0]))
+        side = C.c_void_p(self._sides[which].cuda_stream)
+        ev = self._ev[2 * which]
+        self._run(self.lib.mmh_event_record, (ev, self.st()))
+        self._run(self.lib.mmh_stream_wait_event, (side, ev))
         self.launches -= 2
 
-    def join(self):
-        """The main stream waits for everything launched on the side stream so far."""
-        side = C.c_void_p(self.side_stream.cuda_stream)
-        self._run(self.lib.mmh_event_record, (self._ev[1], side))
-        self._run(self.lib.mmh_stream_wait_event, (self.st(), self._ev[1]))
+    def join(self, which=0):
+        """The main stream waits for everything launched on side stream ``which`` so far."""
+        side = C.c_void_p(self._sides[which].cuda_stream)
+        ev = self._ev[2 * which + 1]
+        self._run(self.lib.mmh_event_record, (ev, side))
+        self._run(self.lib.mmh_stream_wait_event, (self.st(), ev))
         self.launches -= 2
 
     @contextmanager
-    def side(self):
+    def side(self, which=0):
         old = self._stream
-        h = self.side_stream.cuda_stream
+        h = self._sides[which].cuda_stream
         self._stream = lambda: h
+        self.in_side = self._sides[which]
         try:
             yield
         finally:
             self._stream = old
+            self.in_side = None
 
-    # ------------------------------------------------------------------ launch plumbing
     def st(self):
         return C.c_void_p(self._stream())
 

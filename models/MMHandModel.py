@@ -157,7 +157,15 @@ class MMHandModel(BaseModel):
         ops = eng.ops
         scale = 1.0
         if self.world is not None and self.world.size > 1:
-            ops.host(lambda: self.world.all_reduce(eng.store.grad))
+            stream = ops.in_side                     # NCCL follows torch's current stream
+
+            def all_reduce():
+                if stream is None:
+                    self.world.all_reduce(eng.store.grad)
+                else:
+                    with torch.cuda.stream(stream):
+                        self.world.all_reduce(eng.store.grad)
+            ops.host(all_reduce)
             scale = 1.0 / self.world.size
         eng.store.adam(lambda: self._lr(optimizer), self.opt.beta1, 0.999, 1e-8, grad_scale=scale)
         eng.repack(force=True)
@@ -225,7 +233,16 @@ class MMHandModel(BaseModel):
         g_eng = self._g_engine()
         g_eng.store.zero_grad()
         self.backward_G()
-        self._adam(g_eng, self.optimizer_G)
+        if ops.side_stream is not None:
+            # Nothing in the discriminator segments reads the generator's weights: its gradient all-reduce, Adam
+            # update and operand repacking (bandwidth-bound) run on the side stream under the discriminators'
+            # convolutions; _segment_D joins before the step ends.
+            ops.fork(1)
+            with ops.side(1):
+                self._adam(g_eng, self.optimizer_G)
+            self._g_update_pending = True
+        else:
+            self._adam(g_eng, self.optimizer_G)
 
     def _segment_D(self, which=('pp', 'pb')):
         ops = self._ops
@@ -238,8 +255,22 @@ class MMHandModel(BaseModel):
             ops.memset0(self._acc[lo:lo + 2])
             bwd()
             self._adam(eng, optim)
+        if getattr(self, '_g_update_pending', False):
+            ops.join(1)
+            self._g_update_pending = False
 
     def optimize_parameters(self):
+        ops = runtime.get_ops(self.device)
+        hp = getattr(ops, 'main_stream', None)
+        if hp is None:
+            return self._optimize_parameters()
+        cur = torch.cuda.current_stream(self.device)
+        hp.wait_stream(cur)
+        with torch.cuda.stream(hp):
+            self._optimize_parameters()
+        cur.wait_stream(hp)
+
+    def _optimize_parameters(self):
         """reference :310-330. The first call runs eagerly while recording the launch sequence of the generator
         segment and of the two discriminator segments; later calls replay the tapes (use_tape=False: always eager).
         The image-pool queries between the segments stay on the host, as in the reference."""

@@ -35,9 +35,10 @@ orig = ops._run
 
 def timed_run(fn, args, patch=None, keep=None):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    st = ops.in_side if ops.in_side is not None else torch.cuda.current_stream()
+    e0.record(st)
     orig(fn, args, patch, keep)
-    e1.record()
+    e1.record(st)
     recs.append((fn.__name__, e0, e1))
 
 
