@@ -72,6 +72,12 @@ typedef struct MmhConvDesc {
   const float* bias; /* may be NULL */
   int32_t act;       /* 0 none, 1 relu, 2 tanh */
   int32_t n_store;   /* channels actually stored (<= N); 0 means N */
+  /* Fused BatchNorm statistics (replaces the mmh_bn_stats pass over `out`): bn_sums[0][c] += sum, bn_sums[1][c] +=
+   * sum of squares of the stored (bf16-rounded) valid outputs of channel c < bn_C. NULL = off. Needs bias == NULL,
+   * act == 0, bf16 output. Finish with mmh_bn_finalize_reset. */
+  float* bn_sums;
+  int32_t bn_C;
+  int32_t reserved0;
 } MmhConvDesc;
 
 typedef struct MmhConvPlan MmhConvPlan;
@@ -334,6 +340,11 @@ int mmh_bn_stats_finalize(MmhPeer* peer, uint32_t seq, const void* x, int64_t ro
                           float* running_mean, float* running_var, float momentum, float eps, float* coef, float* save,
                           void* stream);
 /* p->sums: zeroed scratch (local sums), p->k: out; dgamma / dbeta accumulate the local sums (NULL to skip) */
+/* Finalisation alone, for statistics accumulated by a convolution epilogue (MmhConvDesc.bn_sums): (exchange,)
+ * mmh_bn_finalize in train mode, sums reset to zero. */
+int mmh_bn_finalize_reset(MmhPeer* peer, uint32_t seq, float* sums, float count_global, const float* gamma,
+                          const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                          int32_t C, float* coef, float* save, void* stream);
 int mmh_bn_bwd_reduce_finalize(MmhPeer* peer, uint32_t seq, const MmhBnBwd* p, uint32_t* counter, float count_global,
                                float* dgamma, float* dbeta, void* stream);
 int mmh_gate_bwd_reduce_finalize(MmhPeer* peer, uint32_t seq, const MmhGateBwd* p, uint32_t* counter,

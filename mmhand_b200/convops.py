@@ -51,7 +51,7 @@ class WgradPlan:
 
 
 def conv_desc(a, a_rows, a_ld, Cc, w, w_taps, N, taps, M, Hg, Wg, Hv, Wv, out, out_ld, out_row_off=0,
-              out_f32=False, zero_invalid=True, bias=None, act=0, out_map=None, n_store=0):
+              out_f32=False, zero_invalid=True, bias=None, act=0, out_map=None, n_store=0, bn_sums=None, bn_C=0):
     """taps: list of (weight slot, row shift). out_map: None (identity on the GEMM grid) or a tuple
     (out_img_rows, out_wg, sh, sw, h0, w0)."""
     d = L.ConvDesc()
@@ -80,11 +80,13 @@ def conv_desc(a, a_rows, a_ld, Cc, w, w_taps, N, taps, M, Hg, Wg, Hv, Wv, out, o
     d.bias = bias.data_ptr() if bias is not None else None
     d.act = act
     d.n_store = n_store
+    d.bn_sums = bn_sums.data_ptr() if bn_sums is not None else None
+    d.bn_C = bn_C if bn_sums is not None else 0
     return d
 
 
 def fwd_plans(lib, g: ConvGeom, a_buf, w_packed, out_buf, Cin_p, Cout_p, bias=None, act=0, out_f32=False,
-              out_map=None, zero_invalid=True):
+              out_map=None, zero_invalid=True, bn_sums=None, bn_C=0):
     """Plans of the forward convolution described by ``g`` (one, or four for a transposed conv)."""
     plans = []
     il, ol = g.in_lay, g.out_lay
@@ -96,7 +98,8 @@ def fwd_plans(lib, g: ConvGeom, a_buf, w_packed, out_buf, Cin_p, Cout_p, bias=No
             Hv, Wv = g.Ho, g.Wo
         d = conv_desc(a_buf, il.rows, il.ld, Cin_p, w_packed, g.k * g.k, Cout_p, ln.taps, M, il.Hg, il.Wg, Hv, Wv,
                       out_buf, ol.ld, out_row_off=ln.out_plane * ol.plane_rows if g.kind == 'up' else 0,
-                      out_f32=out_f32, zero_invalid=zero_invalid, bias=bias, act=act, out_map=out_map)
+                      out_f32=out_f32, zero_invalid=zero_invalid, bias=bias, act=act, out_map=out_map,
+                      bn_sums=bn_sums, bn_C=bn_C)
         plans.append(ConvPlan(lib, d))
     return plans
 

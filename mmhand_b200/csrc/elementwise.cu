@@ -530,6 +530,37 @@ extern "C" int mmh_bn_stats_finalize(MmhPeer* peer, uint32_t seq, const void* x,
   return launch_reduce_ch_fin<2>(f, make_flatgeom(rows), C / 8, C, sums, fin, counter, stream);
 }
 
+#ifndef MMH_HOST_EMU
+template <class Fin>
+__global__ void __launch_bounds__(256) fin_reset_kernel(const Fin fin, float* sums, const int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  fin(c);
+  sums[c] = 0.f;
+  sums[C + c] = 0.f;
+}
+#endif
+
+extern "C" int mmh_bn_finalize_reset(MmhPeer* peer, uint32_t seq, float* sums, float count_global, const float* gamma,
+                                     const float* beta, float* running_mean, float* running_var, float momentum,
+                                     float eps, int32_t C, float* coef, float* save, void* stream) {
+  MMH_CHECK(sums && coef && save && C > 0, "bad argument");
+  BnFwdFin fin;
+  if (peer_dev(peer, seq, 2 * C, &fin.px)) return 1;
+  fin.sums = sums;
+  fin.f.sums = sums; fin.f.gamma = gamma; fin.f.beta = beta; fin.f.rm = running_mean; fin.f.rv = running_var;
+  fin.f.coef = coef; fin.f.save = save; fin.f.count = count_global; fin.f.momentum = momentum; fin.f.eps = eps;
+  fin.f.train = 1; fin.f.C = C;
+#ifdef MMH_HOST_EMU
+  (void)stream;
+  for (int c = 0; c < C; ++c) { fin(c); sums[c] = 0.f; sums[C + c] = 0.f; }
+#else
+  fin_reset_kernel<<<(C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(fin, sums, C);
+  MMH_CUDA(cudaGetLastError());
+#endif
+  return 0;
+}
+
 extern "C" int mmh_bn_finalize(const float* sums, float count, const float* gamma, const float* beta,
                                float* running_mean, float* running_var, float momentum, float eps, int32_t train,
                                int32_t C, float* coef, float* save, void* stream) {

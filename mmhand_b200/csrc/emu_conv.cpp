@@ -40,6 +40,7 @@ extern "C" int mmh_conv_run(const MmhConvPlan* plan, void*) {
   const int n_store = d.n_store > 0 ? ((d.n_store + 15) / 16 * 16) : d.N;
   std::vector<float> acc(d.N);
   std::vector<float> arow(d.C);
+  std::vector<double> bn_acc(d.bn_sums != nullptr ? 2 * d.bn_C : 0, 0.0);
   for (int64_t q = 0; q < d.M; ++q) {
     const int64_t img = q / hw, rem = q % hw;
     const int h = static_cast<int>(rem / d.Wg), x = static_cast<int>(rem % d.Wg);
@@ -77,8 +78,17 @@ extern "C" int mmh_conv_run(const MmhConvPlan* plan, void*) {
     } else {
       act_t* o = static_cast<act_t*>(d.out) + orow * d.out_ld;
       for (int n = 0; n < n_store && n < d.N; ++n) o[n] = mmh::f2act(acc[n]);
+      if (d.bn_sums != nullptr && valid) {          // fused BN statistics of the values as stored
+        for (int n = 0; n < d.bn_C && n < n_store; ++n) {
+          const double v = mmh::act2f(mmh::f2act(acc[n]));
+          bn_acc[n] += v;
+          bn_acc[d.bn_C + n] += v * v;
+        }
+      }
     }
   }
+  if (d.bn_sums != nullptr)
+    for (int n = 0; n < 2 * d.bn_C; ++n) d.bn_sums[n] += static_cast<float>(bn_acc[n]);
   return 0;
 }
 

@@ -253,6 +253,7 @@ extern "C" int mmh_conv_plan_create(const MmhConvDesc* d, MmhConvPlan** out_plan
       return 0;
     }
   }
+  if (d->bn_sums != nullptr) { delete plan; MMH_CHECK(false, "fused BN statistics need the generation-2 kernel"); }
   ConvKParams& k = plan->kp;
   memset(&k, 0, sizeof(k));
   k.T = d->T;

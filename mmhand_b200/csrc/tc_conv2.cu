@@ -56,6 +56,9 @@ struct Conv2Params {
   uint32_t b_ring_off, bar_off;
   void* out;
   const float* bias;
+  float* bn_sums;                  // fused BatchNorm statistics: [2][bn_C] += (sum, sum of squares) of the stored values
+  int32_t bn_C;
+  uint32_t stat_off;               // shared-memory accumulators [2][N] (only when bn_sums != nullptr)
   int32_t g_first[kC2MaxGroups + 1];
   int32_t g_min[kC2MaxGroups];
   int32_t rel16[MMH_MAX_TAPS + 1];  // byte offset / 16 of the tap's first row inside its group's window (+1: prefetch)
@@ -72,12 +75,17 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 // the epilogue instruction-bound: ~35 SASS instructions and four branches per output value).
 // 16 columns per step, software-pipelined: the TMEM load of chunk j + 1 is in flight while chunk j is converted
 // and stored; every store is one full 32-byte sector (STG.256).
-template <int ACT, bool BIAS>
+// STATS (bias-free, linear, bf16 output = every BatchNorm'd convolution in training): the per-channel sum and sum of
+// squares of the values as stored (bf16-rounded) are reduced over the warp's 32 rows with one butterfly
+// reduce-scatter over 32 values (16 sums + 16 squares: 31 shuffles, lane l ends up with value l) and added to the
+// CTA's shared-memory accumulators; the statistics pass over the raw output (one full HBM read) disappears.
+template <int ACT, bool BIAS, bool STATS = false>
 __device__ __forceinline__ void epilogue_row(const Conv2Params& p, uint32_t t_addr, int nchunks, int n0, int64_t orow,
-                                             bool valid, bool do_store) {
+                                             bool valid, bool do_store, float* s_stats = nullptr) {
   auto emit = [&](const uint32_t (&v)[16], int j) {
     const int nc = n0 + j * 16;
-    if (!(do_store && nc < p.n_store) || (p.dbg & 8)) return;
+    if (nc >= p.n_store || (p.dbg & 8)) return;          // warp-uniform
+    if (!STATS && !do_store) return;
     float f[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
@@ -94,6 +102,34 @@ __device__ __forceinline__ void epilogue_row(const Conv2Params& p, uint32_t t_ad
       if (ACT == 1) f[i] = fmaxf(f[i], 0.f);
       else if (ACT == 2) f[i] = tanhf(f[i]);
       f[i] = valid ? f[i] : 0.f;
+    }
+    if (STATS) {
+      uint32_t pk[8];
+      float r[32];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        pk[i] = pack2(f[2 * i], f[2 * i + 1]);
+        r[2 * i] = __uint_as_float(pk[i] << 16);
+        r[2 * i + 1] = __uint_as_float(pk[i] & 0xFFFF0000u);
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[16 + i] = r[i] * r[i];
+      const int lane = threadIdx.x & 31;
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+          const float send = up ? r[i] : r[i + off];
+          const float keep = up ? r[i + off] : r[i];
+          r[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      atomicAdd(s_stats + (lane >> 4) * p.N + nc + (lane & 15), r[0]);
+      if (do_store)
+        st_global_v8(static_cast<__nv_bfloat16*>(p.out) + orow * p.out_ld + nc, pk[0], pk[1], pk[2], pk[3], pk[4],
+                     pk[5], pk[6], pk[7]);
+      return;
     }
     if (p.out_f32) {
       float* dst = static_cast<float*>(p.out) + orow * p.out_ld + nc;
@@ -223,6 +259,9 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4 * NCTA); }
     fence_mbar_init();
   }
+  float* s_stats = reinterpret_cast<float*>(smem + p.stat_off);
+  if (p.bn_sums != nullptr)
+    for (int i = threadIdx.x; i < 2 * p.N; i += kC2Threads) s_stats[i] = 0.f;
   if (warp == 1) {
     if (NCTA == 2) { tmem_alloc2(tmem_slot, kC2TmemCols); tmem_relinquish2(); }
     else { tmem_alloc(tmem_slot, kC2TmemCols); tmem_relinquish(); }
@@ -333,7 +372,8 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                              static_cast<int64_t>(h * p.out_sh + p.out_h0) * p.out_wg + (x * p.out_sw + p.out_w0);
         const uint32_t t_addr = tmem_base + acc * kC2AccStride + mb * p.BN + (static_cast<uint32_t>(quad * 32) << 16);
         // bias-free linear layers (every BatchNorm'd convolution, every data gradient) take the straight-line path
-        if (p.bias == nullptr && p.act == 0) epilogue_row<0, false>(p, t_addr, nchunks, n0, orow, valid, do_store);
+        if (p.bn_sums != nullptr) epilogue_row<0, false, true>(p, t_addr, nchunks, n0, orow, valid, do_store, s_stats);
+        else if (p.bias == nullptr && p.act == 0) epilogue_row<0, false>(p, t_addr, nchunks, n0, orow, valid, do_store);
         else if (p.bias == nullptr) { if (p.act == 1) epilogue_row<1, false>(p, t_addr, nchunks, n0, orow, valid, do_store);
                                       else epilogue_row<2, false>(p, t_addr, nchunks, n0, orow, valid, do_store); }
         else if (p.act == 0) epilogue_row<0, true>(p, t_addr, nchunks, n0, orow, valid, do_store);
@@ -347,6 +387,15 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         else mbar_arrive(&tmem_empty[acc]);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.bn_sums != nullptr) {
+      // the four epilogue warps are done with their tiles: CTA partial sums -> global accumulators
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = threadIdx.x - 64; i < 2 * p.N; i += 128) {
+        const int st = i >= p.N ? 1 : 0, c = i - st * p.N;
+        const float v = s_stats[i];
+        if (c < p.bn_C && v != 0.f) atomicAdd(p.bn_sums + st * p.bn_C + c, v);
+      }
     }
   }
 
@@ -410,6 +459,15 @@ int mmh_conv2_create(const MmhConvDesc* d, MmhConv2** out_plan) {
   k.out_img_rows = d->out_img_rows;
   k.out = d->out;
   k.bias = d->bias;
+  k.bn_sums = d->bn_sums;
+  k.bn_C = d->bn_C;
+  if (d->bn_sums != nullptr) {
+    if (d->bias != nullptr || d->act != 0 || d->out_f32 || d->bn_C <= 0 || d->bn_C > d->N) {
+      set_error("fused BN statistics need a bias-free linear bf16 convolution (bn_C=%d, N=%d)", d->bn_C, d->N);
+      return fail();
+    }
+  }
+  const uint32_t stat_bytes = d->bn_sums != nullptr ? ((2u * d->N * 4u + 1023u) & ~1023u) : 0u;
 
   // ---- tap groups: sort by shift, start a new group at a gap of >= 128 rows or when the window would
   // outgrow its slot
@@ -469,7 +527,7 @@ int mmh_conv2_create(const MmhConvDesc* d, MmhConv2** out_plan) {
   batch = env_int("MMH_CONV_BBATCH", batch);
   k.b_batch = batch;
   k.b_slot_bytes = k.b_batch * k.b_tile_stride;
-  const uint32_t budget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/;
+  const uint32_t budget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/ - stat_bytes;
   k.nA = env_int("MMH_CONV_NA", k.a_slot_bytes <= 8192 ? 8 : (k.a_slot_bytes <= 20480 ? 4 : 2));
   if (k.nA > kC2MaxA) k.nA = kC2MaxA;
   if (k.nA * k.a_slot_bytes + 2 * k.b_slot_bytes > budget) { set_error("conv tile does not fit in shared memory"); return fail(); }
@@ -477,7 +535,8 @@ int mmh_conv2_create(const MmhConvDesc* d, MmhConv2** out_plan) {
   if (k.nB > kC2MaxB) k.nB = kC2MaxB;
   k.b_ring_off = k.nA * k.a_slot_bytes;
   k.bar_off = k.b_ring_off + k.nB * k.b_slot_bytes;
-  plan->smem = k.bar_off + 512 + 1024;
+  k.stat_off = k.bar_off + 512;
+  plan->smem = k.bar_off + 512 + stat_bytes + 1024;
 
   const CUtensorMapSwizzle swz = k.KC == 64   ? CU_TENSOR_MAP_SWIZZLE_128B
                                  : k.KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B

@@ -22,6 +22,10 @@ BN_MOM = 0.1
 
 # MMH_FUSE_GATHER=0 materialises dz with mmh_grad_gather before the BN backward (A/B measurements only)
 FUSE_GATHER = os.environ.get("MMH_FUSE_GATHER", "1") != "0"
+# BN statistics in the conv epilogue: 0 off, 1 every BatchNorm'd conv, 2 (default) only where the main loop hides the
+# longer epilogue (contraction length taps * channels >= 2304: the 256/512-channel 3x3 layers; measured on the 7x7
+# stems and the stride-2 layers the epilogue is the bottleneck and the fused statistics cost more than their kernel)
+CONV_STATS = int(os.environ.get("MMH_CONV_STATS", "2"))
 
 
 def plain_lay(B, H, W, Cc):
@@ -105,6 +109,7 @@ class ConvL:
         self.wp = ops.zeros(self.T, self.Cout_p, self.Cin_p)
         self.fwd = convops.fwd_plans(ops.lib, geom, self.x, self.wp, self.raw, self.Cin_p, self.Cout_p,
                                      bias=self.bias_p, act=act, out_f32=out_f32)
+        self.fwd_stats = None
         self.bwd_ready = False
         self.has_wgrad = False
         self.own_dy = False
@@ -174,9 +179,16 @@ class ConvL:
                                          self.Cin, self.Cout)
         return off + n
 
-    def run_fwd(self):
-        for p in self.fwd:
+    def run_fwd(self, stats=False):
+        for p in (self.fwd_stats if stats else self.fwd):
             self.eng.ops.run_conv(p, (self.name, "fwd"))
+
+    def attach_bn(self, bn):
+        """Second set of forward plans whose epilogue accumulates the BatchNorm statistics of ``bn`` (training)."""
+        if self.fwd_stats is None:
+            self.fwd_stats = convops.fwd_plans(self.eng.ops.lib, self.g, self.x, self.wp, self.raw, self.Cin_p,
+                                               self.Cout_p, bn_sums=bn.sums, bn_C=bn.C)
+        return True
 
     def run_bwd(self, want_wgrad=True, want_dx=True):
         """Consumes self.dy. Weight gradient accumulates into weight.grad; data gradient lands in self.dx."""
@@ -219,11 +231,16 @@ class BNL:
         f = lambda n: ops.zeros(n, dtype=torch.float32)
         self.sums, self.coef, self.save, self.bsums, self.bsums_g, self.k = f(2 * Cc), f(2 * Cc), f(2 * Cc), f(2 * Cc), f(2 * Cc), f(2 * Cc)
 
-    def forward(self, raw, rows, ld, count, training):
+    def forward(self, raw, rows, ld, count, training, in_epilogue=False):
+        """in_epilogue: the convolution that produced ``raw`` already accumulated the sums (ConvL.attach_bn)."""
         ops, m = self.eng.ops, self.mod
         if training:
             eng = self.eng
-            if eng.fused_stats():
+            if in_epilogue:
+                w = eng.peer_world()
+                ops.bn_finalize_reset(w, self.sums, count * (w.size if w else 1), m.weight, m.bias, m.running_mean,
+                                      m.running_var, BN_MOM, BN_EPS, self.C, self.coef, self.save)
+            elif eng.fused_stats():
                 # one launch: sums -> (peer exchange) -> coefficients; self.sums returns to zero
                 w = eng.peer_world()
                 ops.bn_stats_finalize(w, raw, rows, ld, self.C, self.sums, eng.ticket, count * (w.size if w else 1),
@@ -354,10 +371,20 @@ class EngineBase:
             self._unpack_table = self.ops.make_param_jobs([c.unpack_job() for c in self.convs() if c.has_wgrad])
         self.ops.run_param_jobs(self._unpack_table)
 
+    def epilogue_stats(self, conv: ConvL, bn: BNL, training):
+        """BatchNorm statistics inside the convolution's epilogue? (training, one-launch statistics available, bias-free
+        bf16 convolution; see CONV_STATS.)"""
+        if not (training and CONV_STATS and self.fused_stats() and conv.bias is None and not conv.out_f32):
+            return False
+        if CONV_STATS == 2 and conv.T * conv.Cin_p < 2304:
+            return False
+        return conv.attach_bn(bn)
+
     def _stage_fwd(self, conv: ConvL, bn: BNL, training):
-        conv.run_fwd()
+        fused = self.epilogue_stats(conv, bn, training)
+        conv.run_fwd(stats=fused)
         ol = conv.g.out_lay
-        bn.forward(conv.raw, ol.rows, ol.ld, self.B * ol.H * ol.W, training)
+        bn.forward(conv.raw, ol.rows, ol.ld, self.B * ol.H * ol.W, training, in_epilogue=fused)
 
     def _stage_bwd(self, conv: ConvL, bn: BNL, srcs, relu, dropout, key, trunk=None, want_wgrad=True, want_dx=True,
                    dz_out_f32=None):
@@ -492,10 +519,13 @@ class GeneratorEngine(EngineBase):
                 drop = training and self.use_dropout
                 key = KeyRef(self.seed, net_id * 1000 + 3 * i + s) if drop else 0
                 ops.norm_act(c1.raw, c1.g.out_lay, bn1.coef, True, drop, key, c2.x, c2.g.in_lay, 1, 1, True)
-                c2.run_fwd()
+                fused2 = s == 0 and self.epilogue_stats(c2, b["bn2"], training)
+                c2.run_fwd(stats=fused2)
+                if s == 0:
+                    bn2_fused = fused2
             c2s = b["c2"]
             ol = c2s[0].g.out_lay
-            b["bn2"].forward(c2s[0].raw, ol.rows, ol.ld, B * ol.H * ol.W, training)
+            b["bn2"].forward(c2s[0].raw, ol.rows, ol.ld, B * ol.H * ol.W, training, in_epilogue=bn2_fused)
             if i + 1 < self.nb:
                 n = self.blocks[i + 1]["c1"]
                 d1b, d1l = n[0].x, n[0].g.in_lay

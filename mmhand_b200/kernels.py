@@ -259,6 +259,12 @@ class Ops:
                                               self.st()))
         self._run(self.lib.mmh_bn_stats_finalize, args, patch)
 
+    def bn_finalize_reset(self, world, sums, count_global, gamma, beta, rm, rv, momentum, eps, Cc, coef, save):
+        """Finalisation of statistics accumulated by a convolution epilogue; ``sums`` returns to zero."""
+        args, patch = self._peer_args(world, (_p(sums), float(count_global), _p(gamma), _p(beta), _p(rm), _p(rv),
+                                              momentum, eps, Cc, _p(coef), _p(save), self.st()))
+        self._run(self.lib.mmh_bn_finalize_reset, args, patch)
+
     def bn_bwd_reduce_finalize(self, world, dz, dz_f32, relu, dropout, key, x, xl, coef, save, sums, k, counter,
                                count_global, dgamma, dbeta):
         p, patch = self._bn_bwd(dz, dz_f32, relu, dropout, key, x, xl, coef, save, sums=sums, k=k)

@@ -30,6 +30,7 @@ class ConvDesc(C.Structure):
         ("out_h0", C.c_int32), ("out_w0", C.c_int32),
         ("zero_invalid", C.c_int32),
         ("bias", C.c_void_p), ("act", C.c_int32), ("n_store", C.c_int32),
+        ("bn_sums", C.c_void_p), ("bn_C", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -182,6 +183,7 @@ _SIMPLE_SIGS = {
     "mmh_bn_bwd_finalize_sync": [_vp, C.c_uint32, _vp, _vp, _f32, _vp, _vp, _vp, _i32, _vp],
     "mmh_bn_stats_finalize": [_vp, C.c_uint32, _vp, _i64, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _f32, _f32, _vp,
                               _vp, _vp],
+    "mmh_bn_finalize_reset": [_vp, C.c_uint32, _vp, _f32, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _vp, _vp, _vp],
     "mmh_bn_bwd_reduce_finalize": [_vp, C.c_uint32, C.POINTER(BnBwd), _vp, _f32, _vp, _vp, _vp],
     "mmh_gate_bwd_reduce_finalize": [_vp, C.c_uint32, C.POINTER(GateBwd), _vp, _f32, _vp, _vp, _vp],
     "mmh_event_create": [C.POINTER(_vp)],
