@@ -376,7 +376,7 @@ class EngineBase:
         bf16 convolution; see CONV_STATS.)"""
         if not (training and CONV_STATS and self.fused_stats() and conv.bias is None and not conv.out_f32):
             return False
-        if CONV_STATS == 2 and conv.T * conv.Cin_p < 2304:
+        if CONV_STATS == 2 and (conv.T * conv.Cin_p < 2304 or conv.g.kind == 'up'):
             return False
         return conv.attach_bn(bn)
 

@@ -94,15 +94,16 @@ def test_peer_syncbn_matches_nccl_on_two_gpus():
                 assert torch.equal(a, b), k
                 continue
             d = (a - b).abs()
-            # same arithmetic up to the order of fp32 atomics inside the reduction kernels (Adam normalises the
-            # update: a weight whose gradient is ~0 may move by up to ~2 lr per step in either run)
-            assert d.max().item() <= 2 * 3 * lr + 1e-3 * a.abs().max().item(), (part, k, d.max().item())
-            # (measured: a scale-invariant stem weight differs by 0.36 lr on average after three steps between two
-            # runs that only differ in the order of fp32 atomics -- sign flips of noise-dominated Adam updates)
-            assert d.mean().item() <= 1.5 * lr + 1e-3 * a.abs().mean().item() + 1e-6, (part, k, d.mean().item())
             if k.endswith("running_mean") or k.endswith("running_var"):
-                # the exchanged statistics themselves: tight
-                assert d.max().item() <= 2e-2 * a.abs().max().item() + 1e-4, (part, k, d.max().item())
+                # the exchanged statistics themselves (after three steps of slightly diverging weights and bf16
+                # activations; the two modes also sum in different orders: conv-epilogue vs statistics kernel)
+                assert d.max().item() <= 3e-2 * a.abs().max().item() + 1e-4, (part, k, d.max().item())
+                continue
+            # same arithmetic up to the order of fp32 atomics inside the reduction kernels (Adam normalises the
+            # update: a weight whose gradient is ~0 may move by up to ~2 lr per step in either run; measured: a
+            # scale-invariant stem weight differs by 0.36 lr on average after three steps between two such runs)
+            assert d.max().item() <= 2 * 3 * lr + 1e-3 * a.abs().max().item(), (part, k, d.max().item())
+            assert d.mean().item() <= 1.5 * lr + 1e-3 * a.abs().mean().item() + 1e-6, (part, k, d.mean().item())
     for ea, eb in zip(peer[0]["errs"], nccl[0]["errs"]):
         for k in ea:
             assert abs(ea[k] - eb[k]) <= 2e-2 * max(abs(eb[k]), 1e-3), (k, ea[k], eb[k])
