@@ -533,6 +533,7 @@ extern "C" int mmh_bn_stats_finalize(MmhPeer* peer, uint32_t seq, const void* x,
 #ifndef MMH_HOST_EMU
 template <class Fin>
 __global__ void __launch_bounds__(256) fin_reset_kernel(const Fin fin, float* sums, const int C) {
+  pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   fin(c);
@@ -555,8 +556,7 @@ extern "C" int mmh_bn_finalize_reset(MmhPeer* peer, uint32_t seq, float* sums, f
   (void)stream;
   for (int c = 0; c < C; ++c) { fin(c); sums[c] = 0.f; sums[C + c] = 0.f; }
 #else
-  fin_reset_kernel<<<(C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(fin, sums, C);
-  MMH_CUDA(cudaGetLastError());
+  MMH_CUDA(launch_k(fin_reset_kernel<BnFwdFin>, dim3((C + 255) / 256), dim3(256), 0, stream, fin, sums, C));
 #endif
   return 0;
 }

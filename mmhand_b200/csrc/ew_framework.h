@@ -16,6 +16,7 @@
 #pragma once
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #ifndef MMH_HOST_EMU
 #include <cuda_bf16.h>
@@ -244,8 +245,39 @@ int launch_reduce_scalar(const F& f, int64_t n, float* out, void*) {
 
 #else  // CUDA
 
+// Programmatic dependent launch: every kernel of the library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and starts with pdl_sync() -- wait until the preceding grid of the
+// stream has completed and flushed (griddepcontrol.wait), then allow the next grid of the stream to be scheduled
+// (griddepcontrol.launch_dependents). The next kernel's launch latency, block scheduling and prologue thus overlap
+// this kernel's execution; at most two grids of a stream are in flight. ~800 dependent launches per training step.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MMH_PDL");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return on;
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, void* stream, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 template <class F>
 __global__ void __launch_bounds__(256) map_kernel(const F f, const int64_t n) {
+  pdl_sync();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
     f(i);
@@ -256,8 +288,7 @@ int launch_map(const F& f, int64_t n, void* stream) {
   const int64_t want = (n + 255) / 256;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 16;   // multiples of the SM count, grid-stride
   const int blocks = static_cast<int>(want < cap ? want : cap);
-  map_kernel<F><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(f, n);
-  MMH_CUDA(cudaGetLastError());
+  MMH_CUDA(launch_k(map_kernel<F>, dim3(blocks), dim3(256), 0, stream, f, n));
   return 0;
 }
 
@@ -291,6 +322,7 @@ inline int pg_threads(int groups) {
 
 template <class F>
 __global__ void __launch_bounds__(256, 2) pg_kernel(const F f, const RowGeom rg, const int groups, const int chunks) {
+  pdl_sync();
   constexpr int U = F::kUnroll;
   const int ppb = blockDim.x / groups;                       // pixels per block and sweep
   const int g = threadIdx.x % groups;
@@ -323,8 +355,7 @@ int launch_pg(const F& f, const RowGeom& rg, int groups, void* stream) {
   const int ppb = threads / groups;
   const int chunks = (rg.n_cols + ppb * F::kUnroll - 1) / (ppb * F::kUnroll);
   const dim3 grid = row_grid(rg, chunks, 8);
-  pg_kernel<F><<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(f, rg, groups, chunks);
-  MMH_CUDA(cudaGetLastError());
+  MMH_CUDA(launch_k(pg_kernel<F>, grid, dim3(threads), 0, stream, f, rg, groups, chunks));
   return 0;
 }
 
@@ -380,6 +411,7 @@ template <int NV, class F>
 __global__ void __launch_bounds__(256, 2) reduce_ch_kernel(const F f, const RowGeom rg, const int groups, const int chunks,
                                                            const int C, float* __restrict__ out) {
   extern __shared__ float red[];   // [ppb][groups][NV*8]
+  pdl_sync();
   reduce_ch_body<NV>(f, rg, groups, chunks, C, out, red);
 }
 // Same reduction; the block that finishes last (ticket counter) finalises: fin(c) reads the accumulators of channel
@@ -391,6 +423,7 @@ __global__ void __launch_bounds__(256, 2) reduce_ch_fin_kernel(const F f, const 
                                                                const int chunks, const int C, float* out,
                                                                const Fin fin, uint32_t* counter) {
   extern __shared__ float red[];
+  pdl_sync();
   reduce_ch_body<NV>(f, rg, groups, chunks, C, out, red);
   __shared__ int is_last;
   __threadfence();
@@ -418,8 +451,7 @@ int launch_reduce_ch(const F& f, const RowGeom& rg, int groups, int C, float* ou
   MMH_CHECK(units < (int64_t(1) << 31), "too many work units");
   const int64_t wave = static_cast<int64_t>(num_sms()) * (512 / ew_block_threads());
   const int blocks = static_cast<int>(units < wave ? units : wave);
-  reduce_ch_kernel<NV, F><<<blocks, threads, smem, static_cast<cudaStream_t>(stream)>>>(f, rg, groups, chunks, C, out);
-  MMH_CUDA(cudaGetLastError());
+  MMH_CUDA(launch_k(reduce_ch_kernel<NV, F>, dim3(blocks), dim3(threads), smem, stream, f, rg, groups, chunks, C, out));
   return 0;
 }
 
@@ -437,14 +469,14 @@ int launch_reduce_ch_fin(const F& f, const RowGeom& rg, int groups, int C, float
   MMH_CHECK(units < (int64_t(1) << 31), "too many work units");
   const int64_t wave = static_cast<int64_t>(num_sms()) * (512 / ew_block_threads());
   const int blocks = static_cast<int>(units < wave ? units : wave);
-  reduce_ch_fin_kernel<NV, F, Fin><<<blocks, threads, smem, static_cast<cudaStream_t>(stream)>>>(f, rg, groups, chunks, C,
-                                                                                             out, fin, counter);
-  MMH_CUDA(cudaGetLastError());
+  MMH_CUDA(launch_k(reduce_ch_fin_kernel<NV, F, Fin>, dim3(blocks), dim3(threads), smem, stream, f, rg, groups, chunks,
+                    C, out, fin, counter));
   return 0;
 }
 
 template <class F>
 __global__ void __launch_bounds__(256) reduce_scalar_kernel(const F f, const int64_t n, float* __restrict__ out) {
+  pdl_sync();
   float s = 0.f;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
@@ -467,8 +499,7 @@ int launch_reduce_scalar(const F& f, int64_t n, float* out, void* stream) {
   const int64_t want = (n + 256 * 4 - 1) / (256 * 4);
   const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
   const int blocks = static_cast<int>(want < cap ? (want < 1 ? 1 : want) : cap);
-  reduce_scalar_kernel<F><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(f, n, out);
-  MMH_CUDA(cudaGetLastError());
+  MMH_CUDA(launch_k(reduce_scalar_kernel<F>, dim3(blocks), dim3(256), 0, stream, f, n, out));
   return 0;
 }
 

@@ -57,6 +57,7 @@ struct RasterF {
 // One block walks over maps (grid-stride); its 256 threads sweep the H*W/4 items of a map with consecutive
 // 16-byte stores. Map index, centre and bounding box are block-uniform.
 __global__ void __launch_bounds__(256) raster_kernel(const RasterF f, const int64_t n_maps) {
+  pdl_sync();
   const int per_map = f.H * f.wq;
   for (int64_t m = blockIdx.x; m < n_maps; m += gridDim.x) {
     RasterF::Ctx c;
@@ -93,8 +94,7 @@ extern "C" int mmh_heatmap_rasterize(const double* uv, int64_t n_maps, int32_t H
 #else
   const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
   const int blocks = static_cast<int>(n_maps < cap ? n_maps : cap);
-  raster_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(f, n_maps);
-  MMH_CUDA(cudaGetLastError());
+  MMH_CUDA(launch_k(raster_kernel, dim3(blocks), dim3(256), 0, stream, f, n_maps));
   return 0;
 #endif
 }

@@ -270,6 +270,10 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (NCTA == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: barriers, TMEM and descriptors above were set up while the preceding kernel of the
+  // stream was still running; its results are visible past this point, and the next kernel may start its own prologue
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int n_tiles = p.tiles_m * p.tiles_n;
   const int first_tile = blockIdx.x / NCTA;
@@ -563,14 +567,18 @@ int mmh_conv2_run(const MmhConv2* plan, void* stream) {
   cfg.blockDim = dim3(kC2Threads, 1, 1);
   cfg.dynamicSmemBytes = plan->smem;
   cfg.stream = static_cast<cudaStream_t>(stream);
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  static const bool pdl = [] { const char* e = getenv("MMH_PDL"); return e == nullptr || atoi(e) != 0; }();
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (plan->ncta == 2) {
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
     MMH_CUDA(cudaLaunchKernelEx(&cfg, conv2_kernel<2>, plan->tmA, plan->tmW, plan->kp));
   } else {
     MMH_CUDA(cudaLaunchKernelEx(&cfg, conv2_kernel<1>, plan->tmA, plan->tmW, plan->kp));

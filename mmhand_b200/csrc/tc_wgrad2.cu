@@ -116,6 +116,10 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ 
   if (NCTA == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: barriers, TMEM and descriptors above were set up while the preceding kernel of the
+  // stream was still running; its results are visible past this point, and the next kernel may start its own prologue
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // channel origins of this CTA's operand slices
   const int dy_c0 = (p.mode == 0 ? tn * p.dy_cols * NCTA + static_cast<int>(cta) * p.dy_cols : 0);
@@ -493,14 +497,18 @@ int mmh_wgrad2_run(const MmhWgrad2* plan, void* stream) {
   cfg.blockDim = dim3(kW2Threads, 1, 1);
   cfg.dynamicSmemBytes = plan->smem;
   cfg.stream = static_cast<cudaStream_t>(stream);
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  static const bool pdl = [] { const char* e = getenv("MMH_PDL"); return e == nullptr || atoi(e) != 0; }();
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (plan->ncta == 2) {
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
     MMH_CUDA(cudaLaunchKernelEx(&cfg, wgrad2_kernel<2>, plan->tmDy, plan->tmA, plan->kp));
   } else {
     MMH_CUDA(cudaLaunchKernelEx(&cfg, wgrad2_kernel<1>, plan->tmDy, plan->tmA, plan->kp));
