@@ -26,7 +26,7 @@ def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None, help="default: 20 (train, infer), 245 (raster: ~1M poses)")
-    ap.add_argument("--workload", default="train", choices=["train", "infer", "raster"],
+    ap.add_argument("--workload", default="train", choices=["train", "infer", "raster", "jointsmap"],
                     help="train = configs[2] (the headline metric); infer = configs[1] (generator-only inference, "
                          "batch 32); raster = configs[3] (keypoint -> heatmap rasteriser, 4096 poses per step)")
     ap.add_argument("--poses-per-step", type=int, default=4096)
@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     a = ap.parse_args()
     if a.steps is None:
-        a.steps = 245 if a.workload == "raster" else 20
+        a.steps = 245 if a.workload == "raster" else (25 if a.workload == "jointsmap" else 20)
     if a.batch is None:
         a.batch = 32 if (a.workload == "infer" and a.impl == "ours") else 16
     return a
@@ -494,7 +494,11 @@ def run_raster(a):
                 "note": "maps stay in HBM for the training step that consumes them; the host reads one checksum"},
         "gpu_launches": launches, "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "kernel": "raster_kernel (csrc/raster.cu)", "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one 4096-pose launch, ncu --set full
+                     # (profiles/r01_raster_ncu_full_v6.txt): 5.37 MB read + 22.4897 GB written
+                     "traffic": 22495045672 if (P == 4096 and S == 256) else None,
+                     "algorithmic_bytes_per_launch": bytes_per_pose * P,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback",
                      "bytes_per_pose": bytes_per_pose},
     }
@@ -511,6 +515,87 @@ def run_raster(a):
     print(json.dumps(line))
 
 
+def run_jointsmap(a):
+    """configs[3], second half: depth-ordered part maps (mmh_jointsmap_rasterize), K steps of P poses, compact uint8
+    maps. Integer scan conversion per bone: bounded by instruction issue / latency, not by HBM (64 KB per pose)."""
+    import numpy as np
+    import torch
+
+    world, rank, local = _dist_setup()
+    from mmhand_b200 import runtime
+    from mmhand_b200.rasterize import generate_jointsmap
+    P, S = a.poses_per_step, a.size
+    dev = torch.device("cuda", local)
+    ops = runtime.get_ops(dev)
+    rng = np.random.RandomState(49 + rank)
+    uv_host = torch.from_numpy(rng.uniform(16.0, 240.0 * S / 256.0, size=(2, P, 21, 2))).pin_memory()
+    z_host = torch.from_numpy(rng.uniform(200.0, 700.0, size=(2, P, 21))).pin_memory()
+    uv_dev, z_dev = uv_host.to(dev), z_host.to(dev)
+    chk_host = torch.zeros(1, dtype=torch.float64).pin_memory()
+
+    def dev_step(i):
+        return generate_jointsmap(uv_dev[i % 2], z_dev[i % 2], S, S, dtype=torch.uint8)
+
+    def e2e_step(i):
+        o = generate_jointsmap(uv_host[i % 2].to(dev, non_blocking=True), z_host[i % 2].to(dev, non_blocking=True), S, S,
+                               dtype=torch.uint8)
+        chk_host.copy_(o[:, S // 2, :].sum(dtype=torch.float64).reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    warm = max(a.warmup, 3)
+    for i in range(warm):
+        dev_step(i)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ops.launches
+    ms = _timed_loop(a.steps, dev_step, world)
+    launches = ops.launches - l0
+    ms_e2e = _timed_loop(a.steps, e2e_step, world)
+    sampler.stop_flag = True
+    sampler.join(timeout=3)
+    value = P * world * a.steps / (ms / 1000.0)
+    e2e = P * world * a.steps / (ms_e2e / 1000.0)
+    bytes_per_pose = S * S + 21 * 3 * 8
+    peaks = _peaks()
+    peak = peaks.get("hbm_gbs", 6500.0)
+    achieved = bytes_per_pose * P * a.steps / (ms / 1000.0) / 1e9
+    if rank != 0:
+        return
+    line = {
+        "metric": "joints->part-map rasterisation poses/sec @256x256", "value": value, "unit": "poses/s",
+        "n_gpus": world, "steps": a.steps, "warmup": warm, "ms_per_step": ms / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+        "config": {"workload": "configs[3]: depth-ordered part maps (generate_jointsmap), 20 bones, uint8 maps",
+                   "poses_per_step": P, "poses_total": P * a.steps * world, "frame": S,
+                   "parallelism": "dp%d (independent poses, no collective)" % world,
+                   "l2": "outputs of consecutive steps alternate; 64 KB per pose"},
+        "e2e": {"value": e2e, "unit": "poses/s", "h2d_bytes_per_step": P * 21 * 3 * 8, "d2h_bytes_per_step": 8,
+                "ms_per_step": ms_e2e / a.steps},
+        "gpu_launches": launches, "clocks": sampler.summary(),
+        "roofline": {"bound": "hbm", "kernel": "jointsmap_kernel (csrc/jointsmap.cu)", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "note": "integer scan conversion: issue/latency-bound, far below the HBM roofline by nature",
+                     "bytes_per_pose": bytes_per_pose},
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        from oracle.jointsmap_ref import generate_jointsmap_cv2
+        try:
+            import cv2  # noqa: F401
+            ref, kind = generate_jointsmap_cv2, "reference lines on the real cv2"
+        except Exception:
+            from oracle.jointsmap_ref import generate_jointsmap as ref
+            kind = "pure-Python restatement (cv2 not importable)"
+        uvn, zn = uv_host[0].numpy(), z_host[0].numpy()
+        n, t0 = 0, time.time()
+        while time.time() - t0 < min(a.cpu_seconds, 10.0):
+            ref(uvn[n % P], zn[n % P], S, S)
+            n += 1
+        rate = n / (time.time() - t0)
+        line["cpu_baseline"] = {"value": rate, "unit": "poses/s", "cores": 1, "kind": "port",
+                                "sample": "%d poses, generate_jointsmap (%s), one DataLoader worker" % (n, kind)}
+    print(json.dumps(line))
+
+
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
@@ -519,5 +604,7 @@ if __name__ == "__main__":
         run_infer(args)
     elif args.workload == "raster":
         run_raster(args)
+    elif args.workload == "jointsmap":
+        run_jointsmap(args)
     else:
         run_ours(args)

@@ -302,6 +302,16 @@ int mmh_memset(void* p, int32_t byte, int64_t bytes, void* stream);
 int mmh_heatmap_rasterize(const double* uv, int64_t n_maps, int32_t H, int32_t W, double sigma, double thresh,
                           float* out, void* stream);
 
+/* ---- joints -> depth-ordered part map (generate_jointsmap, data/generic_dataset.py:30-78) ------------
+ * uv: float64 [n_pose][21][2] (x, y); depth: float64 [n_pose][21]. Per bone (:33-54): ellipse polygon
+ * cv2.ellipse2Poly((int(mx), int(my)), (int(len/2), 5), int(angle), 0, 360, 1) filled with cv2.fillConvexPoly
+ * (OpenCV's integer arithmetic restated: sine table, cvRound, LineIterator outline, XY_SHIFT=16 scan conversion);
+ * a pixel gets the colour (10..200) of the last bone whose mean joint depth equals the running minimum there, 0 where
+ * no bone covers it. out_f64: [n_pose][H][W][3] float64 (the reference's canvas) and / or out_u8: [n_pose][H][W];
+ * either may be NULL. H <= 512. */
+int mmh_jointsmap_rasterize(const double* uv, const double* depth, int64_t n_pose, int32_t H, int32_t W,
+                            double* out_f64, uint8_t* out_u8, void* stream);
+
 /* ---- synchronised BatchNorm over NVLink peer memory ------------------------------------------------
  * Replaces apex.parallel.convert_syncbn_model + its per-layer NCCL all-reduces (models/MMHandModel.py:109-116):
  * the BN finalise kernels exchange their 2*C partial sums through mailboxes mapped into every peer GPU of the box

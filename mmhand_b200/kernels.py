@@ -447,6 +447,11 @@ class Ops:
         self._run(self.lib.mmh_adam, (_p(p), _p(g), _p(m), _p(v), p.numel(), lr, b1, b2, eps, step, grad_scale,
                                       self.st()), patch)
 
+    def jointsmap(self, uv, depth, H, W, out_f64, out_u8):
+        n = uv.numel() // 42
+        self._run(self.lib.mmh_jointsmap_rasterize, (_p(uv), _p(depth), n, H, W, _p(out_f64), _p(out_u8), self.st()),
+                  keep=(uv, depth, out_f64, out_u8))
+
     def heatmaps(self, uv, H, W, sigma, thresh, out):
         n = uv.numel() // 2
         self._run(self.lib.mmh_heatmap_rasterize, (_p(uv), n, H, W, float(sigma), float(thresh), _p(out), self.st()))

@@ -25,3 +25,26 @@ def get_heatmaps(uv_coords, shape=(256, 256), sigma=SIGMA, thresh=THRESH, out=No
         out = torch.empty(lead + (H, W), dtype=torch.float32, device=ops.device)
     ops.heatmaps(uv, H, W, sigma, thresh, out)
     return out
+
+
+def generate_jointsmap(uv_coord, depth, width, height, channel=3, dtype=torch.float64, device=None):
+    """``generate_jointsmap`` of the reference (data/generic_dataset.py:30-78) on the GPU (mmh_jointsmap_rasterize).
+
+    uv_coord: [..., 21, 2] (x, y), depth: [..., 21] -> the part map. ``dtype=torch.float64`` returns the reference's
+    canvas ``[..., height, width, 3]`` float64; ``dtype=torch.uint8`` the compact ``[..., height, width]`` map (the
+    three channels are equal). Same argument order as the reference (width before height)."""
+    assert channel == 3, "the reference's canvas has three equal channels"
+    uv = torch.as_tensor(uv_coord)
+    ops = runtime.get_ops(device if device is not None else (uv.device if uv.is_cuda else None))
+    uv = uv.to(ops.device, torch.float64).contiguous()
+    z = torch.as_tensor(depth).to(ops.device, torch.float64).contiguous()
+    lead = tuple(uv.shape[:-2])
+    assert uv.shape[-2:] == (21, 2) and tuple(z.shape) == lead + (21,)
+    H, W = int(height), int(width)
+    if dtype == torch.uint8:
+        out = torch.empty(lead + (H, W), dtype=torch.uint8, device=ops.device)
+        ops.jointsmap(uv, z, H, W, None, out)
+    else:
+        out = torch.empty(lead + (H, W, 3), dtype=torch.float64, device=ops.device)
+        ops.jointsmap(uv, z, H, W, out, None)
+    return out

@@ -220,3 +220,31 @@ def test_heatmap_rasteriser():
     nan = get_heatmaps(torch.tensor([[[float("nan"), 3.0]]], dtype=torch.float64), (256, 256))
     assert torch.isnan(nan).all()
     assert get_heatmaps(torch.zeros(0, 21, 2, dtype=torch.float64), (256, 256)).shape == (0, 21, 256, 256)
+
+
+def test_jointsmap_rasteriser():
+    """generate_jointsmap on the GPU: pixel-exact against the golden vectors made with the real cv2 calls and against
+    the oracle's integer restatement on fresh random poses (inside, partly and far outside the frame)."""
+    from mmhand_b200.rasterize import generate_jointsmap
+    from oracle import jointsmap_ref as J
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jointsmap.npz"))
+    got = generate_jointsmap(torch.from_numpy(g["uv"]), torch.from_numpy(g["depth"]), 256, 256, dtype=torch.uint8)
+    got = got.cpu().numpy()
+    for i in range(len(got)):
+        assert np.array_equal(got[i], g["maps"][i]), (i, int((got[i] != g["maps"][i]).sum()))
+    rng = np.random.RandomState(11)
+    uv = rng.uniform(16, 240, size=(96, 21, 2))
+    uv[32:64] = rng.uniform(-40, 300, size=(32, 21, 2))
+    uv[64:80] = np.round(rng.uniform(0, 255, size=(16, 21, 2)))
+    z = rng.uniform(200, 700, size=(96, 21))
+    z[80:] = np.round(z[80:] / 100) * 100
+    full = generate_jointsmap(torch.from_numpy(uv), torch.from_numpy(z), 256, 256).cpu().numpy()
+    assert full.shape == (96, 256, 256, 3) and full.dtype == np.float64
+    for i in range(96):
+        want = J.generate_jointsmap(uv[i], z[i], 256, 256)
+        assert np.array_equal(full[i], want), (i, int((full[i] != want).sum()))
+    # a large batch runs through the grid-stride loop and stays consistent with the small one
+    big = generate_jointsmap(torch.from_numpy(np.tile(uv, (12, 1, 1))), torch.from_numpy(np.tile(z, (12, 1))), 256, 256,
+                             dtype=torch.uint8).cpu().numpy()
+    assert np.array_equal(big[:96].astype(np.float64), full[..., 0]) and np.array_equal(big[:96], big[-96:])
+    assert generate_jointsmap(torch.zeros(0, 21, 2), torch.zeros(0, 21), 256, 256, dtype=torch.uint8).shape == (0, 256, 256)
