@@ -596,8 +596,27 @@ def run_jointsmap(a):
     print(json.dumps(line))
 
 
+def _watchdog(seconds):
+    """Multi-GPU runs only: a rank that is still running after `seconds` prints what it knows and exits, so that a
+    collective that never completes costs a bounded time instead of the caller's whole time limit."""
+    def fire():
+        rank = int(os.environ.get("RANK", "0"))
+        sys.stderr.write("bench.py watchdog: rank %d still running after %d s -- giving up\n" % (rank, seconds))
+        sys.stderr.flush()
+        if rank == 0:
+            print(json.dumps({"error": "watchdog: multi-GPU run exceeded %d s" % seconds,
+                              "n_gpus": int(os.environ.get("WORLD_SIZE", "1"))}), flush=True)
+        os._exit(3)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
 if __name__ == "__main__":
     args = parse()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        _watchdog(int(os.environ.get("MMH_BENCH_WATCHDOG_S", "420")))
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "infer":

@@ -314,6 +314,15 @@ inline int ew_block_threads() {
   }();
   return t;
 }
+// resident wave of the persistent reduction kernels, in blocks per SM (MMH_REDUCE_WAVE; default: as many as fit alone)
+inline int reduce_wave_per_sm() {
+  static const int w = [] {
+    const char* e = getenv("MMH_REDUCE_WAVE");
+    const int v = e != nullptr ? atoi(e) : 0;
+    return v > 0 && v <= 8 ? v : 512 / ew_block_threads();
+  }();
+  return w;
+}
 inline int pg_threads(int groups) {
   const int t = groups > ew_block_threads() ? 256 : ew_block_threads();
   return (t / groups) * groups;
@@ -449,7 +458,7 @@ int launch_reduce_ch(const F& f, const RowGeom& rg, int groups, int C, float* ou
   const int chunks = (rg.n_cols + ppb * F::kUnroll - 1) / (ppb * F::kUnroll);
   const int64_t units = static_cast<int64_t>(rg.n_rows) * chunks;
   MMH_CHECK(units < (int64_t(1) << 31), "too many work units");
-  const int64_t wave = static_cast<int64_t>(num_sms()) * (512 / ew_block_threads());
+  const int64_t wave = static_cast<int64_t>(num_sms()) * reduce_wave_per_sm();
   const int blocks = static_cast<int>(units < wave ? units : wave);
   MMH_CUDA(launch_k(reduce_ch_kernel<NV, F>, dim3(blocks), dim3(threads), smem, stream, f, rg, groups, chunks, C, out));
   return 0;
@@ -467,7 +476,7 @@ int launch_reduce_ch_fin(const F& f, const RowGeom& rg, int groups, int C, float
   const int chunks = (rg.n_cols + ppb * F::kUnroll - 1) / (ppb * F::kUnroll);
   const int64_t units = static_cast<int64_t>(rg.n_rows) * chunks;
   MMH_CHECK(units < (int64_t(1) << 31), "too many work units");
-  const int64_t wave = static_cast<int64_t>(num_sms()) * (512 / ew_block_threads());
+  const int64_t wave = static_cast<int64_t>(num_sms()) * reduce_wave_per_sm();
   const int blocks = static_cast<int>(units < wave ? units : wave);
   MMH_CUDA(launch_k(reduce_ch_fin_kernel<NV, F, Fin>, dim3(blocks), dim3(threads), smem, stream, f, rg, groups, chunks,
                     C, out, fin, counter));

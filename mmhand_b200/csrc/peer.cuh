@@ -39,6 +39,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 __device__ __forceinline__ float peer_collect(const PeerDev& p, int w) {
   float s = 0.f;
   unsigned long long t0 = 0;
+  // a wait already timed out (a peer is gone): do not spend the time-out again on every later exchange
+  if (*reinterpret_cast<volatile int*>(p.status) != 0) return __int_as_float(0x7FC00000);
   for (int r = 0; r < p.world; ++r) {
     const unsigned long long* src = p.box[p.rank] + peer_off(p, r, w);
     unsigned long long word;

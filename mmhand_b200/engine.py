@@ -499,7 +499,10 @@ class GeneratorEngine(EngineBase):
         self.training, self.step, self.net_id = training, step, net_id
         self.ops.step = step
         b0 = self.blocks[0]
-        for s, (a, b_) in enumerate(((x1, None), (x2a, x2b), (x3a, x3b))):
+        # image and depth stems first: they run under the (much larger) host-to-device copy of the pose maps
+        for s, (a, b_) in ((0, (x1, None)), (2, (x3a, x3b)), (1, (x2a, x2b))):
+            for ev in getattr(self, "input_events", {}).get(s, ()):
+                ops.wait_event(ev)
             st = self.stem[s]
             c7, d1, d2 = st["c7"], st["d1"], st["d2"]
             ops.assemble(a, b_, c7.x, c7.g.in_lay, 3, 3, True)

@@ -138,6 +138,11 @@ class Ops:
         self._run(self.lib.mmh_stream_wait_event, (side, ev))
         self.launches -= 2
 
+    def wait_event(self, ev):
+        """The current launch stream waits for an event recorded elsewhere (e.g. by set_input's copy stream)."""
+        self._run(self.lib.mmh_stream_wait_event, (self.st(), ev))
+        self.launches -= 1
+
     def join(self, which=0):
         """The main stream waits for everything launched on side stream ``which`` so far."""
         side = C.c_void_p(self._sides[which].cuda_stream)

@@ -14,6 +14,7 @@ stays the caller's job), BatchNorm statistics and gradients all-reduced over NCC
 bf16 storage with fp32 accumulation / statistics / master weights replaces AMP (``--opt_level`` is accepted and ignored;
 ``overflow`` is always False).
 """
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -27,6 +28,11 @@ from .base_model import BaseModel
 from .Discriminator import Discriminator
 from .Generator import Generator
 from .network_utils import GANLoss, get_norm_layer, get_scheduler, init_weights, print_network
+
+
+# set_input copies on a copy stream with per-tensor events (see set_input). Off by default: written after this round's GPU
+# budget was spent, so it has only been exercised on the host emulation -- enable with MMH_ASYNC_INPUT=1.
+ASYNC_INPUT = os.environ.get("MMH_ASYNC_INPUT", "0") != "0"
 
 
 class MMHandModel(BaseModel):
@@ -118,8 +124,32 @@ class MMHandModel(BaseModel):
             self._in = {k: torch.empty(input[k].shape, dtype=torch.float32, device=dev) for k in names}
             self._in_shapes = shapes
             self._tapes = None
-        for k in names:
-            self._in[k].copy_(input[k], non_blocking=True)
+        if dev.type == 'cuda' and ASYNC_INPUT:
+            # Copies go to a copy stream in the order the step consumes them (image and depth stems first, the 42 pose
+            # channels = 78 % of the bytes next, the target last), one event per tensor; the recorded step waits for
+            # each tensor where it is first read, so the generator's first stems run under the pose-map copy.
+            ops = runtime.get_ops(dev)
+            main = torch.cuda.current_stream(dev)
+            if getattr(self, '_copy_stream', None) is None:
+                import ctypes
+                self._copy_stream = torch.cuda.Stream(dev)
+                self._in_ev = {}
+                for k in names:
+                    e = ctypes.c_void_p()
+                    if ops.lib.mmh_event_create(ctypes.byref(e)) != 0:
+                        raise RuntimeError(ops.lib.mmh_last_error().decode())
+                    self._in_ev[k] = e
+            cs = self._copy_stream
+            cs.wait_stream(main)              # the previous step is done with the buffers; sources are ready
+            with torch.cuda.stream(cs):
+                for k in ('H1', 'D1', 'D2', 'P1', 'P2', 'H2'):
+                    self._in[k].copy_(input[k], non_blocking=True)
+                    ops.lib.mmh_event_record(self._in_ev[k], cs.cuda_stream)
+            self._in_async = True
+        else:
+            for k in names:
+                self._in[k].copy_(input[k], non_blocking=True)
+            self._in_async = False
         self.input_H1, self.input_P1, self.input_D1 = self._in['H1'], self._in['P1'], self._in['D1']
         self.input_H2, self.input_P2, self.input_D2 = self._in['H2'], self._in['P2'], self._in['D2']
         if 'H1_path' in input:
@@ -127,7 +157,19 @@ class MMHandModel(BaseModel):
 
     def _g_engine(self):
         B, _, H, W = self.input_H1.shape
-        return self.netG.engine(B, H, W, self.world)
+        eng = self.netG.engine(B, H, W, self.world)
+        ev = getattr(self, '_in_ev', None)
+        # stem -> events of the input tensors it reads (set_input's copy stream)
+        eng.input_events = {0: (ev['H1'],), 1: (ev['P1'], ev['P2']), 2: (ev['D1'], ev['D2'])} if ev else {}
+        return eng
+
+    def _wait_input(self, *names):
+        """The current stream waits for set_input's copies of the named tensors (recorded on tapes like a launch)."""
+        ev = getattr(self, '_in_ev', None)
+        if ev:
+            ops = runtime.get_ops(self.device)
+            for k in names:
+                ops.wait_event(ev[k])
 
     def forward(self):
         eng = self._g_engine()
@@ -186,6 +228,7 @@ class MMHandModel(BaseModel):
             ops.input_grad_nchw(src, None, dfake, B, C3, H, W, True)
         n = fake.numel()
         crit = self.criterionL1
+        self._wait_input('H2')
         ops.l1(fake, self.input_H2, opt.lambda_A / n, opt.lambda_A / n, acc[2:3], dfake)
         crit.vgg_engine(B, H, W).loss_and_backward(fake, self.input_H2, opt.lambda_B, opt.percep_is_l1 != 1, acc[3:4],
                                                    dfake)
@@ -233,7 +276,10 @@ class MMHandModel(BaseModel):
         g_eng = self._g_engine()
         g_eng.store.zero_grad()
         self.backward_G()
-        if ops.side_stream is not None:
+        # (more than two ranks: kept on the main stream -- NCCL running next to the peer-exchange kernels has only been
+        #  validated on two GPUs)
+        if ops.side_stream is not None and (self.world is None or self.world.size <= 2 or
+                                            os.environ.get("MMH_G_UPDATE_STREAM", "") == "1"):
             # Nothing in the discriminator segments reads the generator's weights: its gradient all-reduce, Adam
             # update and operand repacking (bandwidth-bound) run on the side stream under the discriminators'
             # convolutions; _segment_D joins before the step ends.
@@ -331,6 +377,7 @@ class MMHandModel(BaseModel):
 
     def get_current_visuals(self):
         import util.util as util
+        self._wait_input('H1', 'P1', 'D1', 'H2', 'P2', 'D2')
         height, width = self.input_H1.size(2), self.input_H1.size(3)
         panels = [util.tensor2im(self.input_H1.data), util.draw_pose_from_map(self.input_P1.data)[0],
                   util.tensor2im(self.input_D1.data), util.tensor2im(self.input_H2.data),
