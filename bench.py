@@ -616,7 +616,7 @@ def _watchdog(seconds):
 if __name__ == "__main__":
     args = parse()
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        _watchdog(int(os.environ.get("MMH_BENCH_WATCHDOG_S", "420")))
+        _watchdog(int(os.environ.get("MMH_BENCH_WATCHDOG_S", "300")))
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "infer":

@@ -19,12 +19,13 @@ struct PeerDev {
   uint32_t seq;
 };
 
-#ifndef MMH_HOST_EMU
-constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
-
-__device__ __forceinline__ size_t peer_off(const PeerDev& p, int src, int w) {
+// word w of source rank `src` in the slot of exchange p.seq (same arithmetic on every rank's mailbox)
+MMH_HD size_t peer_off(const PeerDev& p, int src, int w) {
   return (static_cast<size_t>(p.seq & (kPeerSlots - 1)) * p.world + src) * kPeerWords + w;
 }
+
+#ifndef MMH_HOST_EMU
+constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
 __device__ __forceinline__ void peer_post(const PeerDev& p, float v, int w) {
   const unsigned long long word = (static_cast<unsigned long long>(p.seq) << 32) | __float_as_uint(v);
   const size_t off = peer_off(p, p.rank, w);

@@ -500,8 +500,12 @@ class GeneratorEngine(EngineBase):
         self.ops.step = step
         b0 = self.blocks[0]
         # image and depth stems first: they run under the (much larger) host-to-device copy of the pose maps
-        for s, (a, b_) in ((0, (x1, None)), (2, (x3a, x3b)), (1, (x2a, x2b))):
-            for ev in getattr(self, "input_events", {}).get(s, ()):
+        events = getattr(self, "input_events", {})
+        stems = ((0, (x1, None)), (1, (x2a, x2b)), (2, (x3a, x3b)))
+        if events:          # asynchronous input copies (MMHandModel.set_input): pose stem last, under its own copy
+            stems = (stems[0], stems[2], stems[1])
+        for s, (a, b_) in stems:
+            for ev in events.get(s, ()):
                 ops.wait_event(ev)
             st = self.stem[s]
             c7, d1, d2 = st["c7"], st["d1"], st["d2"]
