@@ -13,7 +13,7 @@
 //
 // Slot reuse: exchange k+2 may overwrite slot (k & 1) because a rank can only finish exchange k+1 once every peer
 // has *started* k+1, i.e. has finished reading k (launches of one rank are stream-ordered). Four slots are used.
-// A wait that exceeds kPeerTimeoutNs (a peer died) raises the group's status word instead of hanging the GPU.
+// A wait that exceeds kPeerTimeoutNs (60 s; a peer died) raises the group's status word instead of hanging the GPU.
 #include <stdint.h>
 #include <string.h>
 

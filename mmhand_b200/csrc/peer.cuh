@@ -25,7 +25,7 @@ MMH_HD size_t peer_off(const PeerDev& p, int src, int w) {
 }
 
 #ifndef MMH_HOST_EMU
-constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+constexpr unsigned long long kPeerTimeoutNs = 60ull * 1000ull * 1000ull * 1000ull;   // once: later waits fail fast
 __device__ __forceinline__ void peer_post(const PeerDev& p, float v, int w) {
   const unsigned long long word = (static_cast<unsigned long long>(p.seq) << 32) | __float_as_uint(v);
   const size_t off = peer_off(p, p.rank, w);
