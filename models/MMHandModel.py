@@ -119,6 +119,16 @@ class MMHandModel(BaseModel):
         launch tapes (fixed pointers) stay valid from step to step."""
         dev = self.device
         names = ('H1', 'P1', 'D1', 'H2', 'P2', 'D2')
+        # Device-side pose maps (SURVEY N2, opt-in): 'P1_uv' / 'P2_uv' ([B, 21, 2] keypoints, x then y) may replace
+        # 'P1' / 'P2'; the heatmaps are then rasterised on the device (mmh_heatmap_rasterize: the arithmetic of
+        # Genericdataset.get_heatmaps, sigma 6) straight into the step's input buffers -- 336 bytes per pose cross
+        # the bus instead of 5.5 MB.
+        uv = {k: input[k + '_uv'] for k in ('P1', 'P2') if k not in input and (k + '_uv') in input}
+        if uv:
+            input = dict(input)
+            hw = tuple(input['H1'].shape[2:])
+            for k, v in uv.items():
+                input[k] = torch.empty((v.shape[0], v.shape[1]) + hw, dtype=torch.float32, device='meta')
         shapes = tuple(tuple(input[k].shape) for k in names)
         if getattr(self, '_in_shapes', None) != shapes:
             self._in = {k: torch.empty(input[k].shape, dtype=torch.float32, device=dev) for k in names}
@@ -143,13 +153,19 @@ class MMHandModel(BaseModel):
             cs.wait_stream(main)              # the previous step is done with the buffers; sources are ready
             with torch.cuda.stream(cs):
                 for k in ('H1', 'D1', 'D2', 'P1', 'P2', 'H2'):
-                    self._in[k].copy_(input[k], non_blocking=True)
+                    if k not in uv:
+                        self._in[k].copy_(input[k], non_blocking=True)
                     ops.lib.mmh_event_record(self._in_ev[k], cs.cuda_stream)
             self._in_async = True
         else:
             for k in names:
-                self._in[k].copy_(input[k], non_blocking=True)
+                if k not in uv:
+                    self._in[k].copy_(input[k], non_blocking=True)
             self._in_async = False
+        if uv:
+            from mmhand_b200.rasterize import get_heatmaps
+            for k, v in uv.items():
+                get_heatmaps(v, self._in[k].shape[2:], sigma=float(input.get('sigma', 6.0)), out=self._in[k], device=dev)
         self.input_H1, self.input_P1, self.input_D1 = self._in['H1'], self._in['P1'], self._in['D1']
         self.input_H2, self.input_P2, self.input_D2 = self._in['H2'], self._in['P2'], self._in['D2']
         if 'H1_path' in input:

@@ -190,3 +190,29 @@ def test_train_steps_bf16_tolerance(emu_bf16):
     for a, b in zip(mine, ref):
         for k in b:
             assert abs(a[k] - b[k]) <= 1e-2 * abs(b[k]), (k, a[k], b[k])
+
+
+def test_set_input_with_keypoints_matches_pose_maps(emu_f32):
+    """P1_uv / P2_uv keypoints rasterised on the device give the step that the pose maps give."""
+    import numpy as np
+    from models.MMHandModel import MMHandModel
+    from oracle.raster_ref import get_heatmaps_batch
+    rng = np.random.RandomState(3)
+    B, S = 1, 32
+    uv1, uv2 = rng.uniform(2, S - 2, size=(B, 21, 2)), rng.uniform(2, S - 2, size=(B, 21, 2))
+    g = torch.Generator().manual_seed(9)
+    r = lambda *s: torch.rand(*s, generator=g)
+    base = dict(H1=r(B, 3, S, S) * 2 - 1, D1=r(B, 3, S, S) * 2 - 1, H2=r(B, 3, S, S) * 2 - 1, D2=r(B, 3, S, S) * 2 - 1)
+    maps = dict(base, P1=torch.from_numpy(get_heatmaps_batch(uv1, (S, S))), P2=torch.from_numpy(get_heatmaps_batch(uv2, (S, S))))
+    keys = dict(base, P1_uv=torch.from_numpy(uv1), P2_uv=torch.from_numpy(uv2))
+    errs = []
+    for feed in (maps, keys):
+        torch.manual_seed(4)
+        random.seed(4)
+        m = MMHandModel(make_opt(batchSize=B, fineSize=S, ngf=16, ndf=16, pool_size=0, local_rank='cpu', seed=3))
+        m.master = False
+        m.set_input(feed)
+        assert torch.equal(m.input_P1, maps['P1']) and torch.equal(m.input_P2, maps['P2'])
+        m.optimize_parameters()
+        errs.append({k: float(v) for k, v in m.get_current_errors().items()})
+    assert errs[0] == errs[1]
