@@ -26,6 +26,7 @@ def _worker(rank, world, port, mode, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     os.environ["MMH_SYNCBN"] = mode
+    os.environ.setdefault("WORLD_SIZE", str(world))      # as under torchrun (multi-process defaults of the library)
     torch.cuda.set_device(rank)
     import torch.distributed as dist
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -72,6 +73,7 @@ def _worker(rank, world, port, mode, out_dir):
     dist.destroy_process_group()
 
 
+@pytest.mark.timeout(600)
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_peer_syncbn_matches_nccl_on_two_gpus():
     with tempfile.TemporaryDirectory() as td:
