@@ -3,8 +3,9 @@
 
 The reference draws, per bone, ``cv2.ellipse2Poly((int(mX), int(mY)), (int(length / 2), 5), int(angle), 0, 360, 1)``
 and ``cv2.fillConvexPoly(temp, polygon, [avg_depth] * 3)`` on a float64 canvas, keeps the running minimum depth and
-colours every pixel whose running minimum equals this bone's depth (:60-76). Its dataset module cannot be imported
-here (``from cv2 import cv2``, easydict, ``np.math``: SURVEY.md Q12), so there are two restatements:
+colours every pixel whose running minimum equals this bone's depth (:60-76). The reference function itself runs here
+(oracle/ref_shims.py::load_reference_dataset_module) and produced tests/golden/jointsmap.npz
+(oracle/make_golden_raster.py); it cannot travel to the GPU box, so there are two restatements:
 
 * ``generate_jointsmap_cv2``  -- the reference's lines with the real OpenCV calls (cv2 4.13 in this image; the
   reference pins opencv-python 4.2.0.34) and ``np.math`` replaced by ``math``: the ground truth available here;
@@ -12,9 +13,8 @@ here (``from cv2 import cv2``, easydict, ``np.math``: SURVEY.md Q12), so there a
   (``ellipse2poly``: modules/imgproc/src/drawing.cpp ellipse2Poly / SinTable / cvRound; ``fill_convex_poly``:
   FillConvexPoly = outline with 8-connected LineIterator lines (clipLine) + XY_SHIFT=16 fixed-point scan
   conversion): what the CUDA kernel implements. tests/test_jointsmap.py pins it to the real cv2 calls on thousands
-  of random and adversarial polygons; tests/golden/jointsmap.npz holds outputs of ``generate_jointsmap_cv2``
-  (generated by oracle/make_golden_jointsmap.py). Parity is therefore pinned to OpenCV 4.13, not to a reference
-  test (the reference has none).
+  of random and adversarial polygons and to the golden vectors of the reference function (with the OpenCV of this
+  image, 4.13; the reference pins 4.2.0.34).
 """
 import math
 import sys

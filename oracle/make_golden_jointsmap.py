@@ -1,6 +1,6 @@
-"""Golden vectors of the part map: outputs of ``generate_jointsmap_cv2`` (the reference's lines on the real OpenCV of
-this image, cv2 4.13) for seeded poses -> tests/golden/jointsmap.npz. Run in the build container:
-    python oracle/make_golden_jointsmap.py
+"""Seeded + adversarial poses of the part-map golden vectors (``poses``). tests/golden/jointsmap.npz itself is written
+by oracle/make_golden_raster.py from the reference's own ``generate_jointsmap``; running this file writes the same
+maps from ``generate_jointsmap_cv2`` (the reference's lines on the real OpenCV) -- they are identical.
 """
 import os
 import sys

@@ -3,8 +3,10 @@
 Follows data/generic_dataset.py:191-199 (get_heatmaps: one map per joint, stacked, float32),
 :208-217 (gen_heatmap: clamp >1 to 1, then zero everything < 0.0099, in float64, cast last) and
 :238-242 (gaussian_kernel: mgrid over (height, width), exp(-D2 / 2.0 / sigma / sigma), same evaluation order).
-The reference module itself cannot be imported (``from cv2 import cv2``, easydict), so this
-restatement is pinned by known-answer tests (tests/test_raster_oracle.py): parity unpinned by reference tests.
+Pinned: the reference's dataset module imports with three shims (oracle/ref_shims.py::load_reference_dataset_module)
+and oracle/make_golden_raster.py stores outputs of its own ``Genericdataset.get_heatmaps`` for seeded and adversarial
+poses in tests/golden/heatmaps_ref.npz; tests/test_raster.py requires this restatement (and the kernel body) to
+reproduce them bit for bit, next to derived known answers.
 """
 import numpy as np
 

@@ -53,6 +53,26 @@ def load_reference_nets():
     return gen.Generator, dis.Discriminator, nu, pool.ImagePool, l1p.L1_plus_perceptualLoss
 
 
+def load_reference_dataset_module():
+    """data.generic_dataset of the reference (Genericdataset.get_heatmaps / gen_heatmap / gaussian_kernel,
+    generate_jointsmap), importable here with three shims: ``from cv2 import cv2`` (removed from OpenCV >= 4.6: alias
+    cv2.cv2 = cv2), ``easydict`` (stub, only used by the dataset constructors) and ``np.math`` (removed in numpy 2: alias
+    of the math module). The arithmetic itself runs unmodified."""
+    import math
+
+    import cv2
+    import numpy as np
+    cv2.cv2 = cv2
+    sys.modules.setdefault("cv2.cv2", cv2)
+    if "easydict" not in sys.modules:
+        _stub("easydict", EasyDict=dict)
+    if not hasattr(np, "math"):
+        np.math = math
+    with _RefImport():
+        gd = importlib.import_module("data.generic_dataset")
+    return gd
+
+
 def load_reference_model_class():
     """models.MMHandModel.MMHandModel of the reference, importable on CPU."""
     import torch

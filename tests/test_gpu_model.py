@@ -217,6 +217,9 @@ def test_heatmap_rasteriser():
         assert np.abs(got[c0:c0 + 64] - want).max() <= 1e-6
         assert np.array_equal(got[c0:c0 + 64] > 0, want > 0)   # identical threshold decisions
     assert (got[0, 5] > 0).sum() == 1041       # known answer: interior integer-centred joint
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "heatmaps_ref.npz"))
+    ref = get_heatmaps(torch.from_numpy(g["uv"]), (256, 256)).cpu().numpy()
+    assert np.array_equal(ref, g["maps"])          # the reference's own get_heatmaps (oracle/make_golden_raster.py)
     nan = get_heatmaps(torch.tensor([[[float("nan"), 3.0]]], dtype=torch.float64), (256, 256))
     assert torch.isnan(nan).all()
     assert get_heatmaps(torch.zeros(0, 21, 2, dtype=torch.float64), (256, 256)).shape == (0, 21, 256, 256)

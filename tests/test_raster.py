@@ -1,10 +1,34 @@
 """Heatmap rasteriser: known answers of the oracle restatement and the kernel body on the host emulation."""
+import os
+
 import numpy as np
 import torch
 
 import hostemu
 from mmhand_b200 import runtime
 from oracle.raster_ref import get_heatmaps, get_heatmaps_batch
+
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "heatmaps_ref.npz")
+
+
+def test_oracle_reproduces_reference_golden_vectors():
+    """tests/golden/heatmaps_ref.npz = Genericdataset.get_heatmaps of the reference itself (oracle/make_golden_raster.py)."""
+    g = np.load(GOLD)
+    for i in range(len(g["uv"])):
+        assert np.array_equal(get_heatmaps(g["uv"][i]), g["maps"][i]), i
+    assert np.array_equal(get_heatmaps_batch(g["uv"]), g["maps"])
+
+
+def test_kernel_body_reproduces_reference_golden_vectors():
+    runtime._TEST_OPS = hostemu.ops()
+    try:
+        from mmhand_b200.rasterize import get_heatmaps as gpu_heatmaps
+        g = np.load(GOLD)
+        got = gpu_heatmaps(torch.from_numpy(g["uv"]), (256, 256)).numpy()
+        assert np.array_equal(got, g["maps"])
+    finally:
+        runtime._TEST_OPS = None
 
 
 def test_oracle_known_answers():
