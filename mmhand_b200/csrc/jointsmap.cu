@@ -56,16 +56,22 @@ MMH_HD void jm_bone(int k, int& a, int& b, int& color) {
   a = A[k]; b = B[k]; color = Cc[k];
 }
 
-struct JmBone { int cx, cy, ax, angle; double depth; };
+struct JmBone { int cx, cy, ax, angle; double depth; bool skip; };
+constexpr double kJmMaxCoord = 1048576.0;   // 2^20
 
 // generic_dataset.py:56-70: centre, half length and angle truncated with int(), depth = mean of the two joints
 MMH_HD void jm_params(const double* uv, const double* z, int a, int b, JmBone& o) {
   const double x0 = uv[2 * a], y0 = uv[2 * a + 1], x1 = uv[2 * b], y1 = uv[2 * b + 1];
   o.depth = MMH_DIV(MMH_ADD(z[a], z[b]), 2.0);
-  o.cx = static_cast<int>(MMH_DIV(MMH_ADD(x0, x1), 2.0));
-  o.cy = static_cast<int>(MMH_DIV(MMH_ADD(y0, y1), 2.0));
+  const double mx = MMH_DIV(MMH_ADD(x0, x1), 2.0), my = MMH_DIV(MMH_ADD(y0, y1), 2.0);
   const double dx = MMH_SUB(x0, x1), dy = MMH_SUB(y0, y1);
   const double len = sqrt(MMH_ADD(MMH_MUL(dx, dx), MMH_MUL(dy, dy)));
+  // Joints millions of pixels away (or NaN) would overflow OpenCV's integer points and make the scan conversion walk
+  // millions of rows above the frame: such a bone is not drawn (the reference is not usable there either).
+  o.skip = !(fabs(mx) <= kJmMaxCoord && fabs(my) <= kJmMaxCoord && len <= kJmMaxCoord);
+  if (o.skip) { o.cx = o.cy = o.ax = o.angle = 0; return; }
+  o.cx = static_cast<int>(mx);
+  o.cy = static_cast<int>(my);
   o.ax = static_cast<int>(MMH_DIV(len, 2.0));
   double ang;
   const double adx = fabs(dx), ady = fabs(dy);
@@ -268,7 +274,7 @@ __global__ void __launch_bounds__(kJmThreads) jointsmap_kernel(const double* __r
     for (int i = lane; i <= 360; i += 32) jm_ellipse_point(bn, i, bx[i], by[i]);
     __syncwarp();
     int n = 0;
-    if (lane == 0) {                         // consecutive duplicates out; a single point = two copies of the centre
+    if (lane == 0 && !bn.skip) {                         // consecutive duplicates out; a single point = two copies of the centre
       int qx = 0x7FFFFFFF, qy = 0x7FFFFFFF;
       for (int i = 0; i <= 360; ++i) {
         const int x = bx[i], y = by[i];
@@ -278,7 +284,7 @@ __global__ void __launch_bounds__(kJmThreads) jointsmap_kernel(const double* __r
     }
     n = __shfl_sync(0xffffffffu, n, 0);
     __syncwarp();
-    for (int j = lane; j < n; j += 32) {     // outline: segment (j-1) -> j, closing segment first
+    for (int j = lane; j < n; j += 32) {     // outline: segment (j-1) -> j, closing segment first (n = 0: bone skipped)
       const int p = j == 0 ? n - 1 : j - 1;
       jm_line(W, H, bx[p], by[p], bx[j], by[j], blo, bhi);
     }
@@ -326,7 +332,7 @@ extern "C" int mmh_jointsmap_rasterize(const double* uv, const double* depth, in
       jm_params(uv + pose * 42, depth + pose * 21, a, b, bn);
       dep[k] = bn.depth;
       int n = 0, qx = 0x7FFFFFFF, qy = 0x7FFFFFFF;
-      for (int i = 0; i <= 360; ++i) {
+      for (int i = 0; i <= 360 && !bn.skip; ++i) {
         int x, y;
         jm_ellipse_point(bn, i, x, y);
         if (x != qx || y != qy) { px[n] = x; py[n] = y; ++n; qx = x; qy = y; }

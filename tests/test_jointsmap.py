@@ -76,3 +76,26 @@ def test_kernel_body_matches_oracle_pixel_exactly():
             assert np.array_equal(small[i].astype(np.float64), J.generate_jointsmap(uv[i], z[i], 128, 96)[:, :, 0])
     finally:
         runtime._TEST_OPS = None
+
+
+def test_far_away_and_nan_joints_do_not_draw(monkeypatch):
+    """A joint millions of pixels away (or NaN) drops its bones instead of walking millions of rows (kernel guard);
+    everything else is drawn as the oracle draws it without those bones."""
+    runtime._TEST_OPS = hostemu.ops()
+    try:
+        from mmhand_b200.rasterize import generate_jointsmap
+        rng = np.random.RandomState(8)
+        uv = rng.uniform(16, 240, size=(2, 21, 2))
+        z = rng.uniform(200, 700, size=(2, 21))
+        uv[0, 4] = (1e12, 3.0)                 # joint 4: only bone (3, 4)
+        uv[1, 8] = (float("nan"), 50.0)        # joint 8: only bone (7, 8)
+        got = generate_jointsmap(torch.from_numpy(uv), torch.from_numpy(z), 256, 256, dtype=torch.uint8).numpy()
+        for i, dead in ((0, (3, 4)), (1, (7, 8))):
+            monkeypatch.setattr(J, "BONES", tuple(b for b in J.BONES if b[0] != dead))
+            clean = uv[i].copy()
+            clean[dead[1]] = clean[dead[0]]
+            want = J.generate_jointsmap(clean, z[i], 256, 256)[:, :, 0]
+            monkeypatch.undo()
+            assert np.array_equal(got[i].astype(np.float64), want), i
+    finally:
+        runtime._TEST_OPS = None
