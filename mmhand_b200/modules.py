@@ -75,6 +75,16 @@ class Slot(nn.Module):
         return self.what
 
 
+def norm_params(norm_layer, c):
+    """The module that sits in the norm slot: BatchNorm2d parameters, or -- for the reference's
+    ``partial(InstanceNorm2d, affine=False)`` (network_utils.py get_norm_layer) -- a parameter-free placeholder: such a
+    model has the reference's state_dict (biased convolutions, no norm entries) and loads its checkpoints, but the
+    B200 path computes batch normalisation only and refuses to run it (forward raises)."""
+    if norm_kind(norm_layer) == 'instance':
+        return Slot('InstanceNorm2d(%d, affine=False)' % c)
+    return BatchNorm2dParams(c)
+
+
 def norm_kind(norm_layer):
     """'batch' | 'instance' from the reference's norm_layer argument (a class or a functools.partial)."""
     import functools

@@ -8,7 +8,7 @@ import torch.nn as nn
 
 from mmhand_b200 import runtime
 from mmhand_b200.engine import DiscriminatorEngine
-from mmhand_b200.modules import BatchNorm2dParams, Conv2dParams, Slot, norm_kind
+from mmhand_b200.modules import Conv2dParams, Slot, norm_kind, norm_params
 
 
 class ResnetBlock(nn.Module):
@@ -19,10 +19,10 @@ class ResnetBlock(nn.Module):
     def build_conv_block(self, dim, padding_type, norm_layer, use_dropout, use_bias):
         if padding_type != 'reflect':
             raise NotImplementedError('padding [%s] is not implemented' % padding_type)
-        seq = [Slot('ReflectionPad2d(1)'), Conv2dParams(dim, dim, 3, use_bias), BatchNorm2dParams(dim), Slot('ReLU')]
+        seq = [Slot('ReflectionPad2d(1)'), Conv2dParams(dim, dim, 3, use_bias), norm_params(norm_layer, dim), Slot('ReLU')]
         if use_dropout:
             seq.append(Slot('Dropout(0.5)'))
-        seq += [Slot('ReflectionPad2d(1)'), Conv2dParams(dim, dim, 3, use_bias), BatchNorm2dParams(dim)]
+        seq += [Slot('ReflectionPad2d(1)'), Conv2dParams(dim, dim, 3, use_bias), norm_params(norm_layer, dim)]
         return nn.Sequential(*seq)
 
     def forward(self, x):
@@ -63,20 +63,19 @@ class Discriminator(nn.Module):
                  padding_type='reflect', use_sigmoid=False, n_downsampling=2):
         assert (n_blocks >= 0)
         super().__init__()
-        if norm_kind(norm_layer) != 'batch':
-            raise NotImplementedError("only norm='batch' (the shipped configuration) is built on the B200 path")
+        self._norm = norm_kind(norm_layer)
         if use_sigmoid:
             raise NotImplementedError("use_sigmoid=True is never reached by the reference (MMHandModel.py:190)")
         self.input_nc, self.ngf, self.gpu_ids = input_nc, ngf, gpu_ids
         self.n_blocks, self.use_dropout, self.n_downsampling = n_blocks, use_dropout, n_downsampling
         f = norm_layer.func if isinstance(norm_layer, functools.partial) else norm_layer
         use_bias = f == nn.InstanceNorm2d
-        seq = [Slot('ReflectionPad2d(3)'), Conv2dParams(input_nc, ngf, 7, use_bias), BatchNorm2dParams(ngf), Slot('ReLU')]
+        seq = [Slot('ReflectionPad2d(3)'), Conv2dParams(input_nc, ngf, 7, use_bias), norm_params(norm_layer, ngf), Slot('ReLU')]
         if n_downsampling > 2:
             raise NotImplementedError("n_downsampling=3 is not built (the shipped configuration uses 2)")
         for i in range(n_downsampling):
             mult = 2 ** i
-            seq += [Conv2dParams(ngf * mult, ngf * mult * 2, 3, use_bias, stride=2), BatchNorm2dParams(ngf * mult * 2),
+            seq += [Conv2dParams(ngf * mult, ngf * mult * 2, 3, use_bias, stride=2), norm_params(norm_layer, ngf * mult * 2),
                     Slot('ReLU')]
         mult = 2 ** n_downsampling
         for i in range(n_blocks):
@@ -98,6 +97,9 @@ class Discriminator(nn.Module):
         return eng
 
     def forward(self, input):
+        if self._norm != 'batch':
+            raise NotImplementedError("only norm='batch' (the shipped configuration) is computed on the B200 path; "
+                                      "norm='instance' models are constructed for checkpoint compatibility only")
         x = input.contiguous().float()
         anchor = self.model[1].weight
         want_grad = self.training and torch.is_grad_enabled()

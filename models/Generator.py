@@ -11,7 +11,7 @@ import torch.nn as nn
 
 from mmhand_b200 import runtime
 from mmhand_b200.engine import GeneratorEngine
-from mmhand_b200.modules import BatchNorm2dParams, Conv2dParams, ConvTranspose2dParams, Slot, norm_kind
+from mmhand_b200.modules import Conv2dParams, ConvTranspose2dParams, Slot, norm_kind, norm_params
 
 
 def _use_bias(norm_layer):
@@ -20,8 +20,7 @@ def _use_bias(norm_layer):
 
 
 def _check(norm_layer, padding_type):
-    if norm_kind(norm_layer) != 'batch':
-        raise NotImplementedError("only norm='batch' (the shipped configuration) is built on the B200 path")
+    norm_kind(norm_layer)            # batch | instance (instance: accepted for checkpoint compatibility, forward raises)
     if padding_type != 'reflect':
         raise NotImplementedError('padding [%s] is not implemented' % padding_type)
 
@@ -42,14 +41,14 @@ class PATBlock(nn.Module):
     def build_conv_block(self, dim, padding_type, norm_layer, use_dropout, use_bias, cated_stream2=False,
                          cal_att=False):
         cin = dim * 2 if cated_stream2 else dim
-        seq = [Slot('ReflectionPad2d(1)'), Conv2dParams(cin, cin, 3, use_bias), BatchNorm2dParams(cin), Slot('ReLU')]
+        seq = [Slot('ReflectionPad2d(1)'), Conv2dParams(cin, cin, 3, use_bias), norm_params(norm_layer, cin), Slot('ReLU')]
         if use_dropout:
             seq.append(Slot('Dropout(0.5)'))
         seq.append(Slot('ReflectionPad2d(1)'))
         if cal_att:
             seq.append(Conv2dParams(cin, dim, 3, use_bias))
         else:
-            seq += [Conv2dParams(dim, dim, 3, use_bias), BatchNorm2dParams(dim)]
+            seq += [Conv2dParams(dim, dim, 3, use_bias), norm_params(norm_layer, dim)]
         return nn.Sequential(*seq)
 
     def forward(self, x1, x2, x3):
@@ -68,11 +67,11 @@ class PATNModel(nn.Module):
         use_bias = _use_bias(norm_layer)
 
         def down(cin):
-            seq = [Slot('ReflectionPad2d(3)'), Conv2dParams(cin, ngf, 7, use_bias), BatchNorm2dParams(ngf), Slot('ReLU')]
+            seq = [Slot('ReflectionPad2d(3)'), Conv2dParams(cin, ngf, 7, use_bias), norm_params(norm_layer, ngf), Slot('ReLU')]
             for i in range(n_downsampling):
                 mult = 2 ** i
                 seq += [Conv2dParams(ngf * mult, ngf * mult * 2, 3, use_bias, stride=2),
-                        BatchNorm2dParams(ngf * mult * 2), Slot('ReLU')]
+                        norm_params(norm_layer, ngf * mult * 2), Slot('ReLU')]
             return nn.Sequential(*seq)
 
         self.stream1_down = down(self.input_nc_s1)
@@ -86,7 +85,7 @@ class PATNModel(nn.Module):
         for i in range(n_downsampling):
             mult = 2 ** (n_downsampling - i)
             up += [ConvTranspose2dParams(ngf * mult, int(ngf * mult / 2), 3, use_bias),
-                   BatchNorm2dParams(int(ngf * mult / 2)), Slot('ReLU')]
+                   norm_params(norm_layer, int(ngf * mult / 2)), Slot('ReLU')]
         up += [Slot('ReflectionPad2d(3)'), Conv2dParams(ngf, output_nc, 7, True), Slot('Tanh')]
         self.stream1_up = nn.Sequential(*up)
 
@@ -123,6 +122,7 @@ class Generator(nn.Module):
                                n_downsampling=n_downsampling)
         self._engines = {}
         self._step = 0
+        self._norm = norm_kind(norm_layer)
 
     def engine(self, B, H, W, world=None):
         ops = runtime.get_ops(next(self.parameters()).device)
@@ -135,6 +135,9 @@ class Generator(nn.Module):
         return eng
 
     def forward(self, input):
+        if self._norm != 'batch':
+            raise NotImplementedError("only norm='batch' (the shipped configuration) is computed on the B200 path; "
+                                      "norm='instance' models are constructed for checkpoint compatibility only")
         x1, x2, x3 = [t.contiguous().float() for t in input]
         anchor = self.model.stream1_up[-2].bias
         want_grad = self.training and torch.is_grad_enabled()

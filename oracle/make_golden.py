@@ -91,6 +91,12 @@ def main():
     step["final_dpb_sum"] = {k: float(v.double().abs().sum()) for k, v in m.netD_PB.state_dict().items()
                              if v.is_floating_point()}
     torch.save(step, os.path.join(OUT, "step_ngf4.pt"))
+    # norm='instance' variants of the reference's own modules: checkpoint ABI only (tests/test_state_dict_compat.py)
+    RG, RD, nu, _, _ = ref_shims.load_reference_nets()
+    inorm = nu.get_norm_layer('instance')
+    torch.save({"g_in_sd": RG([3, 42, 6], 3, 4, inorm, True, 9).state_dict(),
+                "d_in_sd": RD(24, 4, inorm, True, 3, [], 'reflect', False, 2).state_dict()},
+               os.path.join(OUT, "nets_instance_ngf4.pt"))
     print("errors:", step["errors"])
     for f in os.listdir(OUT):
         print(f, os.path.getsize(os.path.join(OUT, f)))
