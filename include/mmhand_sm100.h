@@ -312,6 +312,11 @@ int mmh_heatmap_rasterize(const double* uv, int64_t n_maps, int32_t H, int32_t W
 int mmh_jointsmap_rasterize(const double* uv, const double* depth, int64_t n_pose, int32_t H, int32_t W,
                             double* out_f64, uint8_t* out_u8, void* stream);
 
+/* ---- aug.py write-out (aug.py:57-71) ---------------------------------------------------------------
+ * src: fp32 [n_img][3][H][W] (RGB planes, values in (-1, 1)); dst: uint8 [n_img][H][W][3] BGR =
+ * saturate_cast<uchar>(cvRound((x * 0.5f + 0.5f) * 255.f)) -- what cv2.imwrite stores for the reference's float image. */
+int mmh_image_pack_bgr8(const float* src_nchw, int64_t n_img, int32_t H, int32_t W, uint8_t* dst_nhwc, void* stream);
+
 /* ---- synchronised BatchNorm over NVLink peer memory ------------------------------------------------
  * Replaces apex.parallel.convert_syncbn_model + its per-layer NCCL all-reduces (models/MMHandModel.py:109-116):
  * the BN finalise kernels exchange their 2*C partial sums through mailboxes mapped into every peer GPU of the box

@@ -452,6 +452,10 @@ class Ops:
         self._run(self.lib.mmh_adam, (_p(p), _p(g), _p(m), _p(v), p.numel(), lr, b1, b2, eps, step, grad_scale,
                                       self.st()), patch)
 
+    def image_pack_bgr8(self, src, dst):
+        n, _, H, W = src.shape
+        self._run(self.lib.mmh_image_pack_bgr8, (_p(src), n, H, W, _p(dst), self.st()), keep=(src, dst))
+
     def jointsmap(self, uv, depth, H, W, out_f64, out_u8):
         n = uv.numel() // 42
         self._run(self.lib.mmh_jointsmap_rasterize, (_p(uv), _p(depth), n, H, W, _p(out_f64), _p(out_u8), self.st()),
