@@ -216,3 +216,36 @@ def test_set_input_with_keypoints_matches_pose_maps(emu_f32):
         m.optimize_parameters()
         errs.append({k: float(v) for k, v in m.get_current_errors().items()})
     assert errs[0] == errs[1]
+
+
+def test_odd_batch_non_square_and_shape_change(emu_f32):
+    """Ragged shapes: batch 3, 24 x 40 frame (forward + backward against the oracle), then another shape through the
+    same module (the engine is rebuilt); a frame that the two stride-2 stages cannot halve twice is refused."""
+    torch.manual_seed(6)
+    g = _gen()
+    sd = _sd(g)
+    gen = torch.Generator().manual_seed(8)
+    B, H, W = 3, 24, 40
+    x = [torch.rand(B, 3, H, W, generator=gen) * 2 - 1, torch.rand(B, 42, H, W, generator=gen),
+         torch.rand(B, 6, H, W, generator=gen) * 2 - 1]
+    g.train()
+    y = g(x)
+    assert y.shape == (B, 3, H, W)
+    gy = torch.randn(y.shape, generator=gen)
+    y.backward(gy)
+    sdo = _grad_sd(sd)
+    want = O.generator_forward(sdo, x, train=True, use_dropout=True, drop=O.DropCtx("hash", 0, 0, 0))
+    want.backward(gy)
+    assert torch.allclose(y.detach(), want.detach(), atol=5e-5)
+    for k, p in g.named_parameters():
+        r = sdo[k].grad
+        assert (p.grad - r).abs().max() <= 2e-4 * r.abs().max() + 1e-7, k
+    g.eval()
+    with torch.no_grad():
+        x2 = _x(B=1, S=16, seed=5)
+        y2 = g(x2)
+        want2 = O.generator_forward(_sd(g), x2, train=False)
+    assert y2.shape == (1, 3, 16, 16) and torch.allclose(y2, want2, atol=2e-5)
+    with pytest.raises(AssertionError):
+        with torch.no_grad():
+            g([torch.zeros(1, 3, 18, 16), torch.zeros(1, 42, 18, 16), torch.zeros(1, 6, 18, 16)])
