@@ -90,6 +90,13 @@ class World:
             warnings.warn("mmhand_b200: peer-memory SyncBN exchange unavailable (%s); using NCCL all-reduces" % why)
         return False
 
+    def close(self):
+        """Unmap the peers' mailboxes and free this rank's (collective in spirit: call it on every rank once no
+        exchange kernel is in flight, e.g. after a barrier)."""
+        if self.peer is not None:
+            self._lib.mmh_peer_destroy(self.peer)
+            self.peer = None
+
     def check(self):
         """Raise if a peer exchange timed out (a rank died): called once per optimisation step, no device sync."""
         if self.peer is not None and self._lib.mmh_peer_status(self.peer) != 0:
