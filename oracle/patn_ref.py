@@ -228,7 +228,7 @@ class OracleTrainer:
 
     def __init__(self, sd_g, sd_dpb, sd_dpp, sd_vgg, lambda_A=10.0, lambda_B=10.0, lambda_GAN=5.0, lr=2e-4,
                  beta1=0.5, pool_size=50, use_dropout_g=True, use_dropout_d=True, dropout="off", seed=49,
-                 device="cpu"):
+                 device="cpu", dg_ratio=1):
         def prep(sd):
             out = {}
             for k, v in sd.items():
@@ -243,6 +243,7 @@ class OracleTrainer:
         self.lA, self.lB, self.lG = lambda_A, lambda_B, lambda_GAN
         self.udg, self.udd = use_dropout_g, use_dropout_d
         self.dropout, self.seed, self.step_id = dropout, seed, 0
+        self.dg_ratio = dg_ratio          # MMHandModel.py:320-329: each discriminator is stepped DG_ratio times
         params = lambda sd: [v for v in sd.values() if v.requires_grad]
         self.opt_g = torch.optim.Adam(params(self.g), lr=lr, betas=(beta1, 0.999))
         self.opt_dpb = torch.optim.Adam(params(self.dpb), lr=lr, betas=(beta1, 0.999))
@@ -268,22 +269,24 @@ class OracleTrainer:
         pair_gan = (l_pb * self.lG + l_pp * self.lG) / 2
         (l1tot + pair_gan).backward()
         self.opt_g.step()
-        # ---- D_PP
-        self.opt_dpp.zero_grad()
-        real = torch.cat((H2, H1), 1)
-        fk = self.pool_pp.query(torch.cat((fake, H1), 1).detach())
-        loss_dpp = (gan_loss(self._d(self.dpp, real, 5), True) * self.lG +
-                    gan_loss(self._d(self.dpp, fk, 6), False) * self.lG) * 0.5
-        loss_dpp.backward()
-        self.opt_dpp.step()
+        # ---- D_PP (DG_ratio times, a fresh pool query each time)
+        for _ in range(self.dg_ratio):
+            self.opt_dpp.zero_grad()
+            real = torch.cat((H2, H1), 1)
+            fk = self.pool_pp.query(torch.cat((fake, H1), 1).detach())
+            loss_dpp = (gan_loss(self._d(self.dpp, real, 5), True) * self.lG +
+                        gan_loss(self._d(self.dpp, fk, 6), False) * self.lG) * 0.5
+            loss_dpp.backward()
+            self.opt_dpp.step()
         # ---- D_PB
-        self.opt_dpb.zero_grad()
-        real = torch.cat((H2, P2), 1)
-        fk = self.pool_pb.query(torch.cat((fake, P2), 1).detach())
-        loss_dpb = (gan_loss(self._d(self.dpb, real, 2), True) * self.lG +
-                    gan_loss(self._d(self.dpb, fk, 3), False) * self.lG) * 0.5
-        loss_dpb.backward()
-        self.opt_dpb.step()
+        for _ in range(self.dg_ratio):
+            self.opt_dpb.zero_grad()
+            real = torch.cat((H2, P2), 1)
+            fk = self.pool_pb.query(torch.cat((fake, P2), 1).detach())
+            loss_dpb = (gan_loss(self._d(self.dpb, real, 2), True) * self.lG +
+                        gan_loss(self._d(self.dpb, fk, 3), False) * self.lG) * 0.5
+            loss_dpb.backward()
+            self.opt_dpb.step()
         self.step_id += 1
         return {"pair_L1loss": l1tot.item(), "D_PP": loss_dpp.item(), "D_PB": loss_dpb.item(),
                 "pair_GANloss": pair_gan.item(), "origin_L1": l1.item(), "perceptual": lp.item()}

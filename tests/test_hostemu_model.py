@@ -155,7 +155,7 @@ def _run_steps(opt, n, seed):
     vsd = {k: v.detach().clone() for k, v in m.criterionL1.vgg_submodel.state_dict().items()}
     tr = O.OracleTrainer(_sd(m.netG), _sd(m.netD_PB), _sd(m.netD_PP), vsd, opt.lambda_A, opt.lambda_B, opt.lambda_GAN,
                          opt.lr, opt.beta1, opt.pool_size, not opt.no_dropout, not opt.no_dropout_D, dropout="hash",
-                         seed=opt.seed)
+                         seed=opt.seed, dg_ratio=opt.DG_ratio)
     gen = torch.Generator().manual_seed(seed)
     r = lambda *s: torch.rand(*s, generator=gen)
     B, S = opt.batchSize, opt.fineSize
@@ -249,3 +249,15 @@ def test_odd_batch_non_square_and_shape_change(emu_f32):
     with pytest.raises(AssertionError):
         with torch.no_grad():
             g([torch.zeros(1, 3, 18, 16), torch.zeros(1, 42, 18, 16), torch.zeros(1, 6, 18, 16)])
+
+
+def test_dg_ratio_two_steps_each_discriminator_twice(emu_f32):
+    """DG_ratio = 2 (reference :320-329: D_PP twice, then D_PB twice, a pool query before each): the un-taped path."""
+    opt = make_opt(batchSize=2, fineSize=32, ngf=16, ndf=16, pool_size=3, local_rank='cpu', seed=7, DG_ratio=2)
+    m, tr, mine, ref = _run_steps(opt, 2, 13)
+    for a, b in zip(mine, ref):
+        for k in b:
+            assert abs(a[k] - b[k]) <= 5e-5 * max(1.0, abs(b[k])), (k, a[k], b[k])
+    for net, sd in ((m.netD_PP, tr.dpp), (m.netD_PB, tr.dpb)):
+        for k, p in net.named_parameters():
+            assert (p.detach() - sd[k].detach()).abs().max() <= 4 * 2.5 * opt.lr, k        # four Adam steps at most
