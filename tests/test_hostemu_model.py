@@ -261,3 +261,42 @@ def test_dg_ratio_two_steps_each_discriminator_twice(emu_f32):
     for net, sd in ((m.netD_PP, tr.dpp), (m.netD_PB, tr.dpb)):
         for k, p in net.named_parameters():
             assert (p.detach() - sd[k].detach()).abs().max() <= 4 * 2.5 * opt.lr, k        # four Adam steps at most
+
+
+def test_learning_rate_schedule_reaches_the_replayed_adam(emu_f32):
+    """update_learning_rate() (base_model.py:66-70, LambdaLR of network_utils.py:61-65) between steps: the replayed
+    launch tape must pick the new learning rate up (lr and bias correction are patched per replay)."""
+    from models.MMHandModel import MMHandModel
+    opt = make_opt(batchSize=1, fineSize=32, ngf=16, ndf=16, pool_size=0, local_rank='cpu', seed=7, niter=1,
+                   niter_decay=3, no_dropout=True, no_dropout_D=True)
+    torch.manual_seed(5)
+    random.seed(5)
+    m = MMHandModel(opt)
+    m.master = False
+    vsd = {k: v.detach().clone() for k, v in m.criterionL1.vgg_submodel.state_dict().items()}
+    tr = O.OracleTrainer(_sd(m.netG), _sd(m.netD_PB), _sd(m.netD_PP), vsd, opt.lambda_A, opt.lambda_B, opt.lambda_GAN,
+                         opt.lr, opt.beta1, opt.pool_size, False, False, dropout="off", seed=opt.seed)
+    gen = torch.Generator().manual_seed(21)
+    r = lambda *s: torch.rand(*s, generator=gen)
+    lrs = [m.optimizers[0].param_groups[0]['lr']]         # LambdaLR already applied lambda(0) at construction
+    for o in (tr.opt_g, tr.opt_dpb, tr.opt_dpp):
+        for grp in o.param_groups:
+            grp['lr'] = lrs[0]
+    for it in range(4):
+        b = dict(H1=r(1, 3, 32, 32) * 2 - 1, P1=r(1, 21, 32, 32), D1=r(1, 3, 32, 32) * 2 - 1,
+                 H2=r(1, 3, 32, 32) * 2 - 1, P2=r(1, 21, 32, 32), D2=r(1, 3, 32, 32) * 2 - 1)
+        m.set_input(b)
+        m.optimize_parameters()          # step 0 records the tapes, steps 1.. replay them
+        mine = {k: float(v) for k, v in m.get_current_errors().items()}
+        ref = tr.step(b["H1"], b["P1"], b["D1"], b["H2"], b["P2"], b["D2"])
+        for k in ref:
+            assert abs(mine[k] - ref[k]) <= 5e-5 * max(1.0, abs(ref[k])), (it, k, mine[k], ref[k])
+        m.update_learning_rate()
+        lr = m.optimizers[0].param_groups[0]['lr']
+        lrs.append(lr)
+        for o in (tr.opt_g, tr.opt_dpb, tr.opt_dpp):
+            for grp in o.param_groups:
+                grp['lr'] = lr
+    assert lrs[0] > lrs[1] > lrs[2] > 0            # the schedule really decays inside the test
+    for k, p in m.netG.named_parameters():
+        assert (p.detach() - tr.g[k].detach()).abs().max() <= 4 * 2.5 * opt.lr, k
