@@ -3,6 +3,7 @@ ImagePool, loss bookkeeping) against the oracle, on the HOST EMULATION of the C 
 
 f32 emulation (activations stored as fp32): tight tolerances -- proves the calculus; bf16 emulation: the rounding
 the CUDA path applies -- sets expectations for the GPU tolerances. The product never loads these libraries."""
+import os
 import random
 
 import pytest
@@ -300,3 +301,37 @@ def test_learning_rate_schedule_reaches_the_replayed_adam(emu_f32):
     assert lrs[0] > lrs[1] > lrs[2] > 0            # the schedule really decays inside the test
     for k, p in m.netG.named_parameters():
         assert (p.detach() - tr.g[k].detach()).abs().max() <= 4 * 2.5 * opt.lr, k
+
+
+def test_checkpoint_files_and_continue_train(emu_f32, tmp_path, monkeypatch):
+    """save() writes the reference's files (<label>_net_netG.pth, ..._netD_PB.pth, ..._netD_PP.pth: plain fp32
+    state_dicts, base_model.py:47-57) and a model built with continue_train picks them up (load_network :59-72 reads
+    ./checkpoints/<name>); the reloaded generator produces the same image."""
+    from models.MMHandModel import MMHandModel
+    monkeypatch.chdir(tmp_path)
+    kw = dict(batchSize=1, fineSize=32, ngf=16, ndf=16, pool_size=0, local_rank='cpu', seed=7, name='exp1',
+              checkpoints_dir='checkpoints')
+    torch.manual_seed(3)
+    m = MMHandModel(make_opt(**kw))
+    m.master = True
+    gen = torch.Generator().manual_seed(2)
+    r = lambda *s: torch.rand(*s, generator=gen)
+    b = dict(H1=r(1, 3, 32, 32) * 2 - 1, P1=r(1, 21, 32, 32), D1=r(1, 3, 32, 32) * 2 - 1, H2=r(1, 3, 32, 32) * 2 - 1,
+             P2=r(1, 21, 32, 32), D2=r(1, 3, 32, 32) * 2 - 1)
+    m.set_input(b)
+    m.optimize_parameters()                                   # weights move, BN counters advance
+    m.save('latest')
+    files = sorted(os.listdir(os.path.join('checkpoints', 'exp1')))
+    assert files == ['latest_net_netD_PB.pth', 'latest_net_netD_PP.pth', 'latest_net_netG.pth']
+    sd = torch.load(os.path.join('checkpoints', 'exp1', 'latest_net_netG.pth'))
+    assert all(v.device.type == 'cpu' for v in sd.values()) and list(sd.keys()) == list(m.netG.state_dict().keys())
+    assert int(sd['model.stream1_down.2.num_batches_tracked']) == 1
+    torch.manual_seed(99)                                     # different init: everything must come from the files
+    m2 = MMHandModel(make_opt(continue_train=True, which_epoch='latest', **kw))
+    for net in ('netG', 'netD_PB', 'netD_PP'):
+        a, c = getattr(m, net).state_dict(), getattr(m2, net).state_dict()
+        assert all(torch.equal(a[k], c[k]) for k in a), net
+    m.netG.eval(); m2.netG.eval()
+    m.set_input(b); m2.set_input(b)
+    m.test(); m2.test()
+    assert torch.equal(m.fake_p2, m2.fake_p2)
