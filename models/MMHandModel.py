@@ -395,9 +395,9 @@ class MMHandModel(BaseModel):
         import util.util as util
         self._wait_input('H1', 'P1', 'D1', 'H2', 'P2', 'D2')
         height, width = self.input_H1.size(2), self.input_H1.size(3)
-        panels = [util.tensor2im(self.input_H1.data), util.draw_pose_from_map(self.input_P1.data)[0],
+        panels = [util.tensor2im(self.input_H1.data), util.draw_pose_from_map(self.input_P1.data),
                   util.tensor2im(self.input_D1.data), util.tensor2im(self.input_H2.data),
-                  util.draw_pose_from_map(self.input_P2.data)[0], util.tensor2im(self.input_D2.data),
+                  util.draw_pose_from_map(self.input_P2.data), util.tensor2im(self.input_D2.data),
                   util.tensor2im(self.fake_p2.data)]
         vis = np.zeros((height, width * 7, 3)).astype(np.uint8)
         for i, p in enumerate(panels):
