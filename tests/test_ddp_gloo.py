@@ -19,7 +19,7 @@ def _batches(n, B, S):
                  P2=r(B, 21, S, S), D2=r(B, 3, S, S) * 2 - 1) for _ in range(n)]
 
 
-def _run(rank, world, port, out_path):
+def _run(rank, world, port, out_path, total=2):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import hostemu
@@ -34,7 +34,7 @@ def _run(rank, world, port, out_path):
     torch.manual_seed(5)
     random.seed(5)
     torch.set_num_threads(2)
-    opt = make_opt(batchSize=2 // world, fineSize=32, ngf=16, ndf=16, pool_size=0, local_rank='cpu', seed=7,
+    opt = make_opt(batchSize=total // world, fineSize=32, ngf=16, ndf=16, pool_size=0, local_rank='cpu', seed=7,
                    no_dropout=True, no_dropout_D=True, distributed=(world > 1))
     import contextlib
     import io
@@ -42,7 +42,7 @@ def _run(rank, world, port, out_path):
         m = MMHandModel(opt)
     m.master = False
     errs = []
-    for b in _batches(3, 2, 32):
+    for b in _batches(3, total, 32):
         if world > 1:
             b = {k: v[rank:rank + 1] for k, v in b.items()}
         m.set_input(b)
@@ -55,14 +55,20 @@ def _run(rank, world, port, out_path):
         torch.distributed.destroy_process_group()
 
 
-def test_two_ranks_match_one_process():
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_ranks_match_one_process(world):
+    """world = 4 is the host-side collective sequence that 4- and 8-GPU groups run (NCCL exchanges): every rank must
+    issue the same collectives in the same order, or gloo hangs here just as NCCL would there."""
     with tempfile.TemporaryDirectory() as td:
         single, multi = os.path.join(td, "single.pt"), os.path.join(td, "multi.pt")
-        _run(0, 1, 0, single)
+        _run(0, 1, 0, single, world)
         from mmhand_b200 import runtime
         runtime._TEST_OPS = None
-        port = 29500 + (os.getpid() % 500)
-        mp.spawn(_run, args=(2, port, multi), nprocs=2, join=True)
+        port = 29500 + (os.getpid() % 500) + world
+        mp.spawn(_run, args=(world, port, multi, world), nprocs=world, join=True)
         a, b = torch.load(single), torch.load(multi)
         lr = 2e-4
         for part in ("g", "d"):
