@@ -4,9 +4,11 @@ with n(x) = ((x + 1) / 2 - mean) / std, returning ``(loss, loss_l1, loss_percept
 
 The VGG slice runs on the tcgen05 conv kernels (bias + ReLU in the epilogue), the two reductions and their
 gradients on the fused loss kernels. Only ``perceptual_layers == 3`` (conv1_1, ReLU, conv1_2, ReLU -- the value every
-shipped script uses) is built. ``torchvision``'s pretrained file cannot be downloaded here; weights are taken from
-``MMH_VGG19_WEIGHTS`` (a torchvision ``vgg19`` state_dict) when set, else from torchvision's cache, else they stay
-at their seeded random initialisation (parity tests give both sides the same tensors).
+shipped script uses) is built. Pretrained weights, in this order: ``MMH_VGG19_WEIGHTS`` (a torchvision ``vgg19``
+state_dict file), torchvision's hub cache, ``torchvision.models.vgg19(weights=IMAGENET1K_V1)`` (a download, what the
+reference does, :22). If none of them works the constructor RAISES -- a training run must not silently optimise against
+random features -- unless ``MMH_VGG19_RANDOM=1`` opts into the seeded random initialisation (tests, benchmarks and the
+smoke run: there is no network on the GPU boxes, and parity tests give both sides the same tensors).
 """
 import os
 import warnings
@@ -35,11 +37,21 @@ def _vgg_slice(perceptual_layers):
         cache = os.path.expanduser("~/.cache/torch/hub/checkpoints/vgg19-dcbb9e9d.pth")
         if os.path.exists(cache):
             sd = torch.load(cache, map_location="cpu")
+    random_ok = os.environ.get("MMH_VGG19_RANDOM", "0") == "1"
+    if sd is None and not random_ok:
+        try:                                    # the reference's own route (downloads into the hub cache)
+            import torchvision
+            sd = torchvision.models.vgg19(weights=torchvision.models.VGG19_Weights.IMAGENET1K_V1).state_dict()
+        except Exception as e:                  # no network / no torchvision
+            raise RuntimeError(
+                "pretrained VGG19 weights are not available (%s: %s). Point MMH_VGG19_WEIGHTS at a torchvision vgg19 "
+                "state_dict (vgg19-dcbb9e9d.pth), or set MMH_VGG19_RANDOM=1 to run the perceptual loss on seeded "
+                "random features (tests / benchmarks only)." % (type(e).__name__, e)) from e
     if sd is not None:
         seq.load_state_dict({k[len("features."):]: v for k, v in sd.items()
                              if k in ("features.0.weight", "features.0.bias", "features.2.weight", "features.2.bias")})
     else:
-        warnings.warn("VGG19 weights not found (set MMH_VGG19_WEIGHTS): the perceptual loss uses random-init features")
+        warnings.warn("MMH_VGG19_RANDOM=1: the perceptual loss uses random-init VGG19 features")
     return seq
 
 

@@ -33,7 +33,11 @@ def plain_lay(B, H, W, Cc):
 
 
 class ParamStore:
-    """Flat fp32 storage (values, grads, Adam moments) behind the nn.Parameters of one module."""
+    """Flat fp32 storage (values, grads, Adam moments, step count) behind the nn.Parameters of one module.
+
+    Owned by the *module* (``param_store``), not by an engine: engines are per (batch, frame size) and are rebuilt when
+    the batch shape changes (the ragged last batch of an epoch -- the reference's DataLoader has no drop_last), while
+    the optimiser state must survive, as torch.optim.Adam's does in the reference (models/MMHandModel.py:90-98)."""
 
     def __init__(self, ops: Ops, module):
         self.ops, self.module = ops, module
@@ -272,12 +276,21 @@ class BNL:
         ops.bn_bwd_apply(dz, dz_f32, relu, dropout, key, x, xl, self.coef, self.save, self.k, dy, yl)
 
 
+def param_store(ops: Ops, module) -> ParamStore:
+    """The module's one ParamStore (created on first use; re-created only when the module moved to another Ops)."""
+    st = module.__dict__.get("_mmh_store")
+    if st is None or st.ops is not ops:
+        st = ParamStore(ops, module)
+        module.__dict__["_mmh_store"] = st
+    return st
+
+
 class EngineBase:
     def __init__(self, ops: Ops, module, B, H, W, world=None):
         self.ops, self.module, self.B, self.H, self.W = ops, module, B, H, W
         self._scratch = {}
         self.world = world         # None or an object with all_reduce(tensor) and size
-        self.store = ParamStore(ops, module)
+        self.store = param_store(ops, module)
         self.ticket = ops.zeros(1, dtype=torch.int32)    # "last block" ticket of the one-launch statistics kernels
         self.packed_version = None
         self.seed = 0
@@ -288,6 +301,13 @@ class EngineBase:
             t = self.ops.zeros(rows, ld, dtype=dtype)
             self._scratch[key] = t
         return t
+
+    def drop_key(self, layer_id, lay):
+        """Dropout key of a layer whose output has layout ``lay``; data parallel: masks are those of the joint batch
+        (this rank's samples are rank*B ... rank*B + B - 1 of it), see KeyRef."""
+        w = self.world
+        rank = getattr(w, "rank", 0) if (w is not None and w.size > 1) else 0
+        return KeyRef(self.seed, layer_id, rank * self.B * lay.H * lay.W * ((lay.C + 7) // 8))
 
     def sync_stats(self, sums, count):
         if self.world is not None and self.world.size > 1:
@@ -524,7 +544,7 @@ class GeneratorEngine(EngineBase):
                 c1, c2, bn1 = b["c1"][s], b["c2"][s], b["bn1"][s]
                 self._stage_fwd(c1, bn1, training)
                 drop = training and self.use_dropout
-                key = KeyRef(self.seed, net_id * 1000 + 3 * i + s) if drop else 0
+                key = self.drop_key(net_id * 1000 + 3 * i + s, c1.g.out_lay) if drop else 0
                 ops.norm_act(c1.raw, c1.g.out_lay, bn1.coef, True, drop, key, c2.x, c2.g.in_lay, 1, 1, True)
                 fused2 = s == 0 and self.epilogue_stats(c2, b["bn2"], training)
                 c2.run_fwd(stats=fused2)
@@ -598,7 +618,7 @@ class GeneratorEngine(EngineBase):
                 c1, c2, bn1 = b["c1"][s], b["c2"][s], b["bn1"][s]
                 c2.run_bwd()
                 drop = self.use_dropout
-                key = KeyRef(self.seed, net_id * 1000 + 3 * i + s) if drop else 0
+                key = self.drop_key(net_id * 1000 + 3 * i + s, c1.g.out_lay) if drop else 0
                 self._stage_bwd(c1, bn1, [c2.dx_source()], True, drop, key)
         b0 = self.blocks[0]["c1"]
         for s in range(3):
@@ -681,7 +701,7 @@ class DiscriminatorEngine(EngineBase):
             c1, c2 = b["c1"], b["c2"]
             self._stage_fwd(c1, b["bn1"], training)
             drop = training and self.use_dropout
-            key = KeyRef(self.seed, net_id * 1000 + i) if drop else 0
+            key = self.drop_key(net_id * 1000 + i, c1.g.out_lay) if drop else 0
             ops.norm_act(c1.raw, c1.g.out_lay, b["bn1"].coef, True, drop, key, c2.x, c2.g.in_lay, 1, 1, True)
             self._stage_fwd(c2, b["bn2"], training)
             if i + 1 < self.nb:
@@ -711,7 +731,7 @@ class DiscriminatorEngine(EngineBase):
             b["bn2"].backward(dcur, True, False, False, 0, c2.raw, ol, c2.dy, ol, B * h4 * w4, want_wgrad)
             c2.run_bwd(want_wgrad)
             drop = self.use_dropout
-            key = KeyRef(self.seed, net_id * 1000 + i) if drop else 0
+            key = self.drop_key(net_id * 1000 + i, c1.g.out_lay) if drop else 0
             self._stage_bwd(c1, b["bn1"], [c2.dx_source()], True, drop, key, want_wgrad=want_wgrad)
             # d x_k = d x_{k+1} + fold(d pad(x_k))
             ops.grad_gather([c1.dx_source()], B, h4, w4, dim, self.dtrunk, plain_lay(B, h4, w4, dim), True, trunk=dcur)

@@ -34,13 +34,18 @@ def dropout_key(seed, layer_id, step):
 
 
 class KeyRef:
-    """Dropout key of one layer as a function of the training step (resolved at launch / replay time)."""
+    """Dropout key of one layer as a function of the training step (resolved at launch / replay time).
 
-    def __init__(self, seed, layer_id):
-        self.seed, self.layer_id = seed, layer_id
+    ``first_word``: hash-word index of this rank's first element in the *global* batch (data parallel: rank * local
+    batch * H * W * ceil(C/8)). The kernels hash ``word * 0x9E3779B1 + key`` with the local word index, so adding
+    ``first_word * 0x9E3779B1`` to the key gives exactly the mask the joint batch would get: N ranks drop the same
+    elements as one process on the joint batch (and not the same pattern on every rank's own samples)."""
+
+    def __init__(self, seed, layer_id, first_word=0):
+        self.seed, self.layer_id, self.first_word = seed, layer_id, first_word
 
     def resolve(self, step):
-        return dropout_key(self.seed, self.layer_id, step)
+        return (dropout_key(self.seed, self.layer_id, step) + self.first_word * 0x9E3779B1) & M32
 
 
 class GradSource:

@@ -60,6 +60,10 @@ class BatchNorm2dParams(nn.Module):
             self._pending = 0
         super()._save_to_state_dict(destination, prefix, keep_vars)
 
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        self._pending = 0           # batches counted before the load belong to the overwritten value
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
     def extra_repr(self):
         return "%d" % self.num_features
 

@@ -80,6 +80,7 @@ class MMHandModel(BaseModel):
             self.schedulers = [get_scheduler(o, opt) for o in self.optimizers]
             self._step = 0
             self._acc = None
+        self._sync_initial_state()
         if self.master:
             print('---------- Networks initialized -------------')
             print_network(self.netG)
@@ -88,6 +89,22 @@ class MMHandModel(BaseModel):
                 print_network(self.netD_PP)
                 print(opt.local_rank)
             print('-----------------------------------------------')
+
+    def _sync_initial_state(self):
+        """Data parallel: every replica starts from rank 0's parameters and BatchNorm buffers, as apex
+        DistributedDataParallel does at construction (reference :110-116) -- the reference never seeds its ranks, so
+        identical random initialisation cannot be assumed. Includes the (frozen) VGG slice of the perceptual loss."""
+        if self.world is None or self.world.size <= 1:
+            return
+        nets = [self.netG]
+        if self.isTrain:
+            nets += [self.netD_PB, self.netD_PP]
+            if hasattr(self.criterionL1, 'vgg_submodel'):
+                nets.append(self.criterionL1.vgg_submodel)
+        with torch.no_grad():
+            for net in nets:
+                for t in list(net.parameters()) + list(net.buffers()):
+                    self.world.dist.broadcast(t.data, 0)
 
     def _device(self):
         lr = self.opt.local_rank
@@ -346,6 +363,13 @@ class MMHandModel(BaseModel):
             self._tapes = None
         use_tape = getattr(self, 'use_tape', True) and self.opt.DG_ratio == 1
         tapes = getattr(self, '_tapes', None)
+        # what a recorded sequence bakes in besides pointers: train / eval mode of the networks and the loss scales
+        opt = self.opt
+        tape_key = (self.netG.training, self.netD_PB.training, self.netD_PP.training, opt.lambda_A, opt.lambda_B,
+                    opt.lambda_GAN, opt.percep_is_l1, getattr(opt, 'seed', 0))
+        if tapes is not None and getattr(self, '_tape_key', None) != tape_key:
+            tapes = self._tapes = None
+        self._tape_key = tape_key
         if use_tape and tapes is not None and tapes[0].stream == ops._stream():
             tapes[0].replay(self._step)
             self._pool_inputs()

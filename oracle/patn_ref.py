@@ -14,9 +14,8 @@ the CUDA path:
                          :310-330 (optimize_parameters: G, then D_PP, then D_PB), Adam at :90-98
   ImagePoolRef           util/image_pool.py:14-34
 
-Pinned against the reference modules themselves by tests/test_oracle_vs_reference.py (live import of
-/root/reference when present) and by the golden vectors in tests/golden/ generated from the reference by
-oracle/make_golden.py.
+Pinned against the reference modules themselves by the golden vectors in tests/golden/ generated from the live
+reference by oracle/make_golden.py (tests/test_oracle_golden.py).
 
 Dropout: the reference draws nn.Dropout masks from torch's global generator (Generator.py:76-77,
 Discriminator.py:33-34); for a reproducible three-way comparison the oracle takes the masks from
@@ -93,19 +92,24 @@ def _rpad(x, p):
 # conv operands (activations, weights) and raw conv outputs exactly where the CUDA path stores bf16,
 # keeping fp32 accumulation, statistics and residual trunks. None = the reference's plain fp32 arithmetic.
 QUANT = None
+# Selective rounding points for the ablation of tests/diag_quant_ablation.py: any subset of {"act", "w", "raw"}
+# (conv input activations / weights / raw conv outputs). None = all three.
+QUANT_POINTS = None
 
 
-def _q(t):
-    return t if QUANT is None else QUANT(t)
+def _q(t, point=None):
+    if QUANT is None or (QUANT_POINTS is not None and point not in QUANT_POINTS):
+        return t
+    return QUANT(t)
 
 
 def _conv(x, w, bias=None, stride=1, padding=0, q_out=True):
-    y = F.conv2d(_q(x), _q(w), bias, stride=stride, padding=padding)
-    return _q(y) if q_out else y
+    y = F.conv2d(_q(x, "act"), _q(w, "w"), bias, stride=stride, padding=padding)
+    return _q(y, "raw") if q_out else y
 
 
 def _convT(x, w):
-    return _q(F.conv_transpose2d(_q(x), _q(w), stride=2, padding=1, output_padding=1))
+    return _q(F.conv_transpose2d(_q(x, "act"), _q(w, "w"), stride=2, padding=1, output_padding=1), "raw")
 
 
 def _down_stream(sd, p, x, train):

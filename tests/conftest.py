@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# no network / no pretrained file in the test environments: the perceptual loss runs on seeded random VGG features,
+# identical on both sides of every parity comparison (losses/L1_plus_perceptualLoss.py raises without this opt-in)
+os.environ.setdefault("MMH_VGG19_RANDOM", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:

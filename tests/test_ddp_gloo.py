@@ -1,6 +1,8 @@
 """Data-parallel path on CPU: world_size 2 over gloo with the host emulation. Two ranks with one sample each
 (synchronised BatchNorm statistics + gradient all-reduce) must take the same optimisation steps as one process
-with both samples (dropout off: the hash masks are indexed by the local sample id)."""
+with both samples -- dropout ON: the hash masks are indexed by the sample's position in the joint batch
+(mmhand_b200.kernels.KeyRef), so N ranks drop the same elements as one process. The ranks are seeded DIFFERENTLY:
+MMHandModel broadcasts rank 0's initial parameters and buffers (apex DDP semantics)."""
 import os
 import random
 import sys
@@ -31,11 +33,11 @@ def _run(rank, world, port, out_path, total=2):
         os.environ["MASTER_PORT"] = str(port)
         torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
     from models.MMHandModel import MMHandModel
-    torch.manual_seed(5)
+    torch.manual_seed(5 + 1000 * rank)       # rank-dependent initialisation: rank 0's must win
     random.seed(5)
     torch.set_num_threads(2)
     opt = make_opt(batchSize=total // world, fineSize=32, ngf=16, ndf=16, pool_size=0, local_rank='cpu', seed=7,
-                   no_dropout=True, no_dropout_D=True, distributed=(world > 1))
+                   distributed=(world > 1))
     import contextlib
     import io
     with contextlib.redirect_stdout(io.StringIO()):
