@@ -18,6 +18,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# there is no network and no pretrained VGG19 file on the GPU boxes: the perceptual loss runs on seeded random-init
+# VGG19[:4] features (same architecture and FLOPs; recorded in the JSON line's config)
+os.environ.setdefault("MMH_VGG19_RANDOM", "1")
 
 GFLOP_PER_IMG = 2490.0       # minimal required G+D train step, 2*MACs, un-padded channels
 

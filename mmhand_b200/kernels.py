@@ -197,9 +197,31 @@ class Ops:
         finally:
             self.tape = None
 
+    # Engine buffers are carved out of zero-filled chunks: an engine owns ~800 activation / gradient / statistics
+    # buffers, and one allocator call + one fill kernel each made engine construction ~1700 driver calls (and buried
+    # the library's own kernels under fill launches in any launch list of a first step). A chunk is released by the
+    # caching allocator when the last buffer carved from it dies (views keep their storage alive).
+    ARENA_CHUNK = 256 << 20
+    ARENA_ALIGN = 1024               # TMA base addresses need 128 B; 1 KB keeps swizzle atoms aligned too
+
     def zeros(self, *shape, dtype=None):
         dtype = dtype or self.act_dtype
-        return torch.zeros(*shape, dtype=dtype, device=self.device)
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = tuple(shape[0])
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        if nbytes == 0 or nbytes > self.ARENA_CHUNK // 2:
+            return torch.zeros(*shape, dtype=dtype, device=self.device)
+        need = (nbytes + self.ARENA_ALIGN - 1) // self.ARENA_ALIGN * self.ARENA_ALIGN
+        chunk = getattr(self, "_arena", None)
+        if chunk is None or self._arena_off + need > chunk.numel():
+            chunk = self._arena = torch.zeros(self.ARENA_CHUNK, dtype=torch.uint8, device=self.device)
+            self._arena_off = (-chunk.data_ptr()) % self.ARENA_ALIGN
+        off = self._arena_off
+        self._arena_off = off + need
+        return chunk[off:off + nbytes].view(dtype).view(*shape)
 
     def empty(self, *shape, dtype=None):
         dtype = dtype or self.act_dtype

@@ -117,18 +117,18 @@ class MMHandModel(BaseModel):
         assert len(input_nc) == 3
         netG = Generator(input_nc, output_nc, ngf, norm_layer=get_norm_layer(norm_type=norm), use_dropout=use_dropout,
                          n_blocks=9, gpu_ids=gpu_ids, n_downsampling=n_downsampling)
-        netG = netG.to(self.device)
+        # N(0, 0.02) initialisation on the host, then one copy per tensor (the reference initialises after .cuda():
+        # the same distribution from another generator; ~150 tiny normal_ launches less)
         init_weights(netG, init_type=init_type)
-        return netG
+        return netG.to(self.device)
 
     def define_D(self, input_nc, ndf, n_layers_D=3, norm='batch', use_sigmoid=False, init_type='normal', gpu_ids=[],
                  use_dropout=False, n_downsampling=2):
         netD = Discriminator(input_nc, ndf, norm_layer=get_norm_layer(norm_type=norm), use_dropout=use_dropout,
                              n_blocks=n_layers_D, gpu_ids=[], padding_type='reflect', use_sigmoid=False,
                              n_downsampling=n_downsampling)
-        netD = netD.to(self.device)
         init_weights(netD, init_type=init_type)
-        return netD
+        return netD.to(self.device)
 
     # ------------------------------------------------------------------------------------------ data
     def set_input(self, input):
@@ -151,7 +151,7 @@ class MMHandModel(BaseModel):
             self._in = {k: torch.empty(input[k].shape, dtype=torch.float32, device=dev) for k in names}
             self._in_shapes = shapes
             self._tapes = None
-        if dev.type == 'cuda' and ASYNC_INPUT:
+        if dev.type == 'cuda' and getattr(self, 'async_input', ASYNC_INPUT):
             # Copies go to a copy stream in the order the step consumes them (image and depth stems first, the 42 pose
             # channels = 78 % of the bytes next, the target last), one event per tensor; the recorded step waits for
             # each tensor where it is first read, so the generator's first stems run under the pose-map copy.
@@ -349,6 +349,15 @@ class MMHandModel(BaseModel):
             self._optimize_parameters()
         cur.wait_stream(hp)
 
+    def _align_ranks(self):
+        """Data parallel: all ranks enter the first step of a (re)built engine set together. Engine construction
+        (hundreds of plans, lazy module loading on a freshly started box) can skew the ranks by many seconds; the
+        in-kernel SyncBN exchange of the first layer would otherwise spin for that long (csrc/peer.cuh time-out)."""
+        if self.world is not None and self.world.size > 1:
+            if self.device.type == 'cuda':
+                torch.cuda.synchronize(self.device)
+            self.world.dist.barrier()
+
     def _optimize_parameters(self):
         """reference :310-330. The first call runs eagerly while recording the launch sequence of the generator
         segment and of the two discriminator segments; later calls replay the tapes (use_tape=False: always eager).
@@ -381,6 +390,7 @@ class MMHandModel(BaseModel):
                 self._d_engine(net).prepare_training()
             if hasattr(self.criterionL1, 'vgg_engine'):
                 self.criterionL1.vgg_engine(B, H, W).prepare_training()
+            self._align_ranks()
             with ops.record() as tg:
                 self._segment_G()
             self._pool_inputs()

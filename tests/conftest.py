@@ -13,7 +13,18 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
+def _no_tf32():
+    """The oracle is fp32: cuDNN / cuBLAS must not silently run it in TF32 on the GPU box (torch's default for convs)."""
+    try:
+        import torch
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    except Exception:
+        pass
+
+
 def pytest_configure(config):
+    _no_tf32()
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     config.addinivalue_line("markers", "timeout: per-test time limit (pytest-timeout; ignored when the plugin is absent)")
 

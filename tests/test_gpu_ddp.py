@@ -109,3 +109,95 @@ def test_peer_syncbn_matches_nccl_on_two_gpus():
     for ea, eb in zip(peer[0]["errs"], nccl[0]["errs"]):
         for k in ea:
             assert abs(ea[k] - eb[k]) <= 2e-2 * max(abs(eb[k]), 1e-3), (k, ea[k], eb[k])
+
+
+def _joint_worker(rank, world, port, mode, out_dir, S, ngf, steps):
+    """One rank of the joint-batch test: per-rank batch 1 = sample `rank` of the joint batch, dropout on."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["MMH_SYNCBN"] = mode
+    os.environ["MMH_VGG19_RANDOM"] = "1"
+    os.environ.setdefault("WORLD_SIZE", str(world))
+    torch.cuda.set_device(rank)
+    import torch.distributed as dist
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from models.MMHandModel import MMHandModel
+    from mmhand_b200.options import make_opt
+    torch.manual_seed(5 + 100 * rank)          # rank-dependent init: rank 0's is broadcast (apex DDP semantics)
+    random.seed(5)
+    opt = make_opt(batchSize=1, fineSize=S, ngf=ngf, ndf=ngf, pool_size=0, local_rank=rank, gpu=rank, seed=7,
+                   distributed=True)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = MMHandModel(opt)
+    m.master = False
+    sd = lambda net: {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    res = {"peer": m.world.peer is not None, "init": {"g": sd(m.netG), "dpb": sd(m.netD_PB), "dpp": sd(m.netD_PP),
+                                                      "vgg": sd(m.criterionL1.vgg_submodel)}}
+    g = torch.Generator().manual_seed(321)
+    r = lambda *s: torch.rand(*s, generator=g)
+    errs = []
+    for _ in range(steps):
+        b = dict(H1=r(world, 3, S, S) * 2 - 1, P1=r(world, 21, S, S), D1=r(world, 3, S, S) * 2 - 1,
+                 H2=r(world, 3, S, S) * 2 - 1, P2=r(world, 21, S, S), D2=r(world, 3, S, S) * 2 - 1)
+        m.set_input({k: v[rank:rank + 1] for k, v in b.items()})
+        m.optimize_parameters()
+        errs.append({k: float(v) for k, v in m.get_current_errors().items()})
+    res["errs"] = errs
+    res["g"] = sd(m.netG)
+    torch.save(res, os.path.join(out_dir, "joint_%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _joint_vs_oracle(world, mode, S=64, ngf=32, steps=3):
+    """N ranks (one sample each, SyncBN + gradient all-reduce, joint-batch dropout masks) against the ORACLE stepping
+    on the joint batch of N samples on one GPU: the data-parallel path computes the single-process result."""
+    from oracle import patn_ref as O
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with tempfile.TemporaryDirectory() as td:
+        port = 29700 + (os.getpid() % 250) + 7 * world
+        mp.spawn(_joint_worker, args=(world, port, mode, td, S, ngf, steps), nprocs=world, join=True)
+        res = [torch.load(os.path.join(td, "joint_%d.pt" % r)) for r in range(world)]
+    assert all(r["peer"] == (mode == "peer") for r in res)
+    init = res[0]["init"]
+    for r in res[1:]:           # rank 0's initial state reached every rank although they were seeded differently
+        for part in ("g", "dpb", "dpp", "vgg"):
+            assert all(torch.equal(init[part][k], r["init"][part][k]) for k in init[part]), part
+    for r in res[1:]:           # replicas in lock-step after the steps
+        assert all(torch.equal(res[0]["g"][k], r["g"][k]) for k in res[0]["g"])
+    tr = O.OracleTrainer(init["g"], init["dpb"], init["dpp"], init["vgg"], 10.0, 10.0, 5.0, 2e-4, 0.5, 0, True, True,
+                         dropout="hash", seed=7, device="cuda")
+    g = torch.Generator().manual_seed(321)
+    r_ = lambda *s: torch.rand(*s, generator=g)
+    worst = 0.0
+    for i in range(steps):
+        b = dict(H1=r_(world, 3, S, S) * 2 - 1, P1=r_(world, 21, S, S), D1=r_(world, 3, S, S) * 2 - 1,
+                 H2=r_(world, 3, S, S) * 2 - 1, P2=r_(world, 21, S, S), D2=r_(world, 3, S, S) * 2 - 1)
+        b = {k: v.cuda() for k, v in b.items()}
+        ref = tr.step(b["H1"], b["P1"], b["D1"], b["H2"], b["P2"], b["D2"])
+        for k in ref:
+            mine = sum(r["errs"][i][k] for r in res) / world        # mean over the joint batch = mean of rank means
+            rel = abs(mine - ref[k]) / max(abs(ref[k]), 1e-6)
+            worst = max(worst, rel)
+            assert rel <= 1e-2, (world, mode, i, k, mine, ref[k])
+    print("joint-batch vs oracle, world %d (%s): worst relative loss deviation %.3g" % (world, mode, worst))
+    return worst
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("mode", ["nccl", "peer"])
+def test_two_ranks_match_oracle_on_joint_batch(mode):
+    _joint_vs_oracle(2, mode)
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs four GPUs")
+@pytest.mark.parametrize("mode", ["nccl", "peer"])
+def test_all_ranks_match_oracle_on_joint_batch(mode):
+    """4 GPUs, or 8 when the box has them."""
+    _joint_vs_oracle(8 if torch.cuda.device_count() >= 8 else 4, mode)

@@ -4,6 +4,8 @@ rasteriser 1e-6 abs (fp32), network outputs 2e-2 max-abs (bf16), per-step losses
 import os
 import random
 
+import json
+
 import numpy as np
 import pytest
 import torch
@@ -11,6 +13,19 @@ import torch
 pytestmark = pytest.mark.gpu
 
 DEV = "cuda"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _note(**kw):
+    """Measured parity figures of this run -> gpurun_out/parity_metrics.json (copied to profiles/ per round)."""
+    path = os.path.join(ROOT, "gpurun_out", "parity_metrics.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        cur = json.load(open(path)) if os.path.exists(path) else {}
+        cur.update(kw)
+        json.dump(cur, open(path, "w"), indent=1, sort_keys=True)
+    except Exception:
+        pass
 
 
 def _sd(net):
@@ -75,15 +90,21 @@ def test_generator_eval_256(nets):
     print("G eval vs bf16-storage oracle max-abs", err_q, "| vs fp32 oracle max-abs", err, "mean-abs", mean_err,
           "| bf16-storage oracle vs fp32 oracle max-abs", (want_q - want).abs().max().item())
     floor = (want_q - want).abs().max().item()
-    # The north-star asks for 2e-2 max-abs "in bf16". That bound is not reachable by ANY implementation that stores
-    # activations in bf16: the fp32 oracle re-run with bf16 storage at the same points (conv operands and raw conv
-    # outputs; fp32 accumulation, statistics, trunk) deviates from itself by `floor` = 5-6e-2 max over 393k outputs,
-    # and stock torch bf16 autocast does the same (profiles/r01_layer_errors_vs_bf16_autocast.txt). What is asserted:
-    #  (1) the CUDA path is no further from the fp32 oracle than that bf16-storage floor (+25 %), mean-abs <= 1e-2;
+    mean_q = (y - want_q).abs().mean().item()
+    _note(g_eval_max_abs=err, g_eval_mean_abs=mean_err, g_eval_bf16_floor=floor, g_eval_vs_bf16_oracle_max=err_q,
+          g_eval_vs_bf16_oracle_mean=mean_q)
+    # The north-star asks for 2e-2 max-abs "in bf16". profiles/r02_quant_ablation.txt (tests/diag_quant_ablation.py):
+    # rounding ANY ONE of the three bf16 storage points of the fp32 oracle -- conv input activations 3.2e-2, weights
+    # 3.3e-2, raw conv outputs 3.1e-2 -- already exceeds it; all three give `floor` = 5.5e-2 (they add in quadrature
+    # over ~60 layers), the same as stock torch bf16 autocast (5.8e-2). No single tensor kept in fp32 recovers the
+    # bound; it is the price of bf16 tensor-core operands, which the north-star also prescribes. What is asserted
+    # (measured on B200 + 20 %):
+    #  (1) the CUDA path is no further from the fp32 oracle than that bf16-storage floor (+20 %): 6.5e-2 max-abs
+    #      (measured 5.2e-2), mean-abs <= 7e-3 (measured 5.6e-3);
     #  (2) against the bf16-storage oracle (same rounding points; residual = accumulation-order ulp flips that
     #      propagate through ~60 layers) max-abs <= 4e-2 and mean-abs <= 5e-3.
-    assert err <= 1.25 * floor and err <= 8e-2 and mean_err <= 1e-2
-    assert err_q <= 4e-2 and (y - want_q).abs().mean().item() <= 5e-3
+    assert err <= 1.2 * floor and err <= 6.5e-2 and mean_err <= 7e-3
+    assert err_q <= 4e-2 and mean_q <= 5e-3
 
 
 def test_generator_train_forward_backward(nets):
@@ -107,9 +128,11 @@ def test_generator_train_forward_backward(nets):
     err = (y.detach() - want.detach()).abs().max().item()
     mean_err = (y.detach() - want.detach()).abs().mean().item()
     print("G train max-abs err", err, "mean-abs err", mean_err)
-    # batch-statistics BN + dropout through 9 PAT blocks in bf16: the 2e-2 north-star bound holds for the mean
-    # error by a wide margin and for eval mode in max-abs; the train-mode max over 393k outputs is looser
-    assert mean_err <= 1e-2 and err <= 1e-1
+    _note(g_train_max_abs=err, g_train_mean_abs=mean_err)
+    # batch-statistics BN + dropout through 9 PAT blocks with bf16 operands: measured 5.2e-2 max-abs / 5.6e-3 mean-abs
+    # on B200 (the bf16-storage floor of the oracle itself in train mode is 5.3e-2, profiles/r02_quant_ablation.txt);
+    # asserted at measured + 20 %
+    assert mean_err <= 7e-3 and err <= 6.5e-2
     cos = sorted((torch.nn.functional.cosine_similarity(p.grad.flatten(), sdo[k].grad.flatten(), dim=0).item(), k)
                  for k, p in g.named_parameters())
     mine = torch.cat([p.grad.flatten() for _, p in g.named_parameters()])
@@ -143,6 +166,8 @@ def test_discriminator_train(nets):
     lo.backward()
     err = (y.detach() - yo.detach()).abs().max().item()
     print("D train max-abs err", err, "ref max", yo.abs().max().item(), "loss", loss.item(), lo.item())
+    _note(d_train_max_abs=err, d_train_mean_abs=(y.detach() - yo.detach()).abs().mean().item(),
+          d_logit_max=yo.abs().max().item(), d_logit_std=yo.std().item())
     assert err <= 2e-2 * yo.abs().max().item()      # logits are unbounded (|x| ~ 10): 2e-2 relative to their range
     assert abs(loss.item() - lo.item()) <= 1e-3 * abs(lo.item())
     c = torch.nn.functional.cosine_similarity(x.grad.flatten(), xo.grad.flatten(), dim=0).item()
@@ -159,9 +184,10 @@ def test_known_answers():
     assert abs(GANLoss()(z, True).item() - 0.6931471805599453) < 1e-6
 
 
-@pytest.mark.parametrize("steps,B,S", [(50, 1, 256)])
+@pytest.mark.parametrize("steps,B,S", [(50, 1, 256), (12, 16, 256)])
 def test_train_losses_match_oracle(steps, B, S):
-    """Per-step G/D losses within 1e-2 relative of the oracle over 50 steps (dropout on, identical hash masks)."""
+    """Per-step G/D losses within 1e-2 relative of the oracle (dropout on, identical hash masks): 50 steps at batch 1
+    and 12 steps at batch 16 -- the per-GPU batch BASELINE.json's configs[2] is quoted on."""
     from models.MMHandModel import MMHandModel
     from oracle import patn_ref as O
     from oracle.ref_shims import make_opt
@@ -190,12 +216,80 @@ def test_train_losses_match_oracle(steps, B, S):
             per_step[i] = max(per_step.get(i, 0.0), rel)
     print("per-step worst relative loss deviation:", ["%.4f" % per_step[i] for i in range(steps)])
     print("worst relative loss deviation over %d steps: %.3g" % (steps, worst))
+    _note(**{"loss_rel_dev_B%d_%dsteps" % (B, steps): worst,
+             "loss_rel_dev_B%d_per_step" % B: [round(per_step[i], 5) for i in range(steps)]})
     # north-star: 1e-2 relative. Two optimisers that differ only by bf16 rounding drift apart step by step
     # (Adam normalises the update, so tiny gradient differences move weights by ~lr); the bound is asserted where it
-    # is a statement about the arithmetic (first 20 steps) and a looser one over the whole horizon.
+    # is a statement about the arithmetic (first 20 steps) and measured + 20 % (round 1: 1.6e-2) over the whole horizon.
     assert max(per_step[i] for i in range(min(20, steps))) <= 1e-2
-    assert worst <= 3e-2
+    assert worst <= 2e-2
     print("last step:", mine[-1])
+
+
+def test_set_input_keypoints_and_async_copies():
+    """SURVEY N2 on the GPU: (1) 'P1_uv' / 'P2_uv' keypoints rasterised on the device give bit-identical pose maps to
+    feeding the maps (mmh_heatmap_rasterize == the oracle's get_heatmaps); (2) the copy-stream input path (per-tensor
+    events, pose stem last) takes the same steps as the plain one."""
+    from models.MMHandModel import MMHandModel
+    from oracle.raster_ref import get_heatmaps_batch
+    from oracle.ref_shims import make_opt
+    rng = np.random.RandomState(3)
+    B, S = 2, 256
+    steps = []
+    for it in range(3):
+        uv1, uv2 = rng.uniform(8, S - 8, size=(B, 21, 2)), rng.uniform(8, S - 8, size=(B, 21, 2))
+        g = torch.Generator().manual_seed(90 + it)
+        r = lambda *s: torch.rand(*s, generator=g)
+        base = dict(H1=r(B, 3, S, S) * 2 - 1, D1=r(B, 3, S, S) * 2 - 1, H2=r(B, 3, S, S) * 2 - 1, D2=r(B, 3, S, S) * 2 - 1)
+        maps = dict(base, P1=torch.from_numpy(get_heatmaps_batch(uv1, (S, S))),
+                    P2=torch.from_numpy(get_heatmaps_batch(uv2, (S, S))))
+        keys = dict(base, P1_uv=torch.from_numpy(uv1), P2_uv=torch.from_numpy(uv2))
+        steps.append((maps, keys))
+    runs = {}
+    for name, feed, async_in in (("maps", 0, False), ("uv", 1, False), ("uv_async", 1, True), ("maps_async", 0, True)):
+        torch.manual_seed(4)
+        random.seed(4)
+        m = MMHandModel(make_opt(batchSize=B, fineSize=S, pool_size=0, local_rank=0, gpu=0, seed=3))
+        m.master = False
+        m.async_input = async_in
+        errs = []
+        for st in steps:
+            src = {k: (v.pin_memory() if async_in else v) for k, v in st[feed].items()}
+            m.set_input(src)
+            torch.cuda.synchronize()
+            assert torch.equal(m.input_P1.cpu(), st[0]["P1"]) and torch.equal(m.input_P2.cpu(), st[0]["P2"]), name
+            m.optimize_parameters()
+            errs.append({k: float(v) for k, v in m.get_current_errors().items()})
+        runs[name] = errs
+        del m
+        torch.cuda.empty_cache()
+    for name in ("uv", "uv_async", "maps_async"):
+        for a, b in zip(runs["maps"], runs[name]):
+            for k in a:
+                # identical inputs and launch sequence; fp32 atomics order inside the reduction kernels is the only
+                # difference between two runs
+                assert abs(a[k] - b[k]) <= 2e-3 * max(abs(a[k]), 1e-3), (name, k, a[k], b[k])
+
+
+def test_image_pack_bgr8_matches_cv2_imwrite(tmp_path):
+    """aug.py's write-out (aug.py:57-71) on the GPU: mmh_image_pack_bgr8 gives the bytes cv2.imwrite stores."""
+    cv2 = pytest.importorskip("cv2")
+    from mmhand_b200.augment import images_to_bgr8
+    g = torch.Generator().manual_seed(7)
+    fake = torch.tanh(torch.randn(5, 3, 256, 256, generator=g) * 2)
+    fake[0, :, 0, :8] = torch.tensor([-1.0, 1.0, 0.0, 1.5, -1.5, 0.00392157, -0.00392157, 0.5])
+    k = torch.arange(0, 256).float()
+    fake[1, 0, 1, :256] = (k + 0.5) / 127.5 - 1.0                # values that land on x.5 before rounding
+    got = images_to_bgr8(fake.to(DEV)).cpu().numpy()
+    assert got.shape == (5, 256, 256, 3) and got.dtype == np.uint8
+    for i in range(5):
+        ref = fake[i].permute(1, 2, 0).numpy()
+        ref = (ref * 0.5 + 0.5) * 255.
+        ref = cv2.cvtColor(ref, cv2.COLOR_RGB2BGR)
+        path = str(tmp_path / ("img%d.png" % i))
+        cv2.imwrite(path, ref)
+        back = cv2.imread(path, cv2.IMREAD_COLOR)
+        assert np.array_equal(got[i], back), (i, int((got[i] != back).sum()))
 
 
 def test_heatmap_rasteriser():
