@@ -78,12 +78,33 @@ typedef struct MmhConvDesc {
   float* bn_sums;
   int32_t bn_C;
   int32_t reserved0;
+  /* Fused BatchNorm-BACKWARD statistics and masks (replaces mmh_bn_bwd_reduce_finalize's pass over dz and x), for a
+   * data-gradient launch whose output grid is the (padded) input of a convolution fed by
+   *     conv_p -> BatchNorm -> [ReLU] -> [Dropout(0.5)] -> reflect padding        (models/Generator.py:62-77,
+   *                                                                                 models/Discriminator.py:28-35).
+   * Output row q = grid position (hp, wp) of image b is the gradient of logical pixel (hp - bs_pad, wp - bs_pad),
+   * mirrored into [0, bs_H) x [0, bs_W) (torch ReflectionPad2d), whose raw conv_p output x is row
+   * (b*bs_xHg + hs)*bs_xWg + ws of bs_x (bf16, bs_x_ld elements per row). With a = bs_coef[c], b = bs_coef[C + c],
+   * mean = bs_save[c], rstd = bs_save[C + c] (C = bs_C) the launch STORES
+   *     dze = out * [a*x + b > 0 (bs_relu)] * [2 if kept else 0 (bs_dropout; hash of mmh_norm_act with bs_drop_key)]
+   * and accumulates bs_sums[0][c] += sum dze, bs_sums[1][c] += sum dze * (x - mean) * rstd over all rows -- summed
+   * over the halo positions too, which is the reflect-fold of the gradient. Finish with mmh_bn_bwd_finalize_reset, then
+   * mmh_bn_bwd_apply with relu = dropout = 0 on the stored dze. bs_x == NULL = off. Needs bias == NULL, act == 0,
+   * bf16 output, Hv == Hg, Wv == Wg, bn_sums == NULL. */
+  const void* bs_x;
+  const float* bs_coef;
+  const float* bs_save;
+  float* bs_sums;
+  int32_t bs_x_ld, bs_xHg, bs_xWg, bs_H, bs_W, bs_pad, bs_C, bs_relu, bs_dropout;
+  uint32_t bs_drop_key;
 } MmhConvDesc;
 
 typedef struct MmhConvPlan MmhConvPlan;
 int mmh_conv_plan_create(const MmhConvDesc* desc, MmhConvPlan** plan);
 int mmh_conv_plan_destroy(MmhConvPlan* plan);
 int mmh_conv_run(const MmhConvPlan* plan, void* stream);
+/* Same launch with another dropout key (bs_drop_key changes every training step; everything else is fixed). */
+int mmh_conv_run_key(const MmhConvPlan* plan, uint32_t drop_key, void* stream);
 
 /*
  * Weight gradient (cuDNN bwd-filter in the reference; autograd of the same call sites):
@@ -362,6 +383,11 @@ int mmh_bn_finalize_reset(MmhPeer* peer, uint32_t seq, float* sums, float count_
                           int32_t C, float* coef, float* save, void* stream);
 int mmh_bn_bwd_reduce_finalize(MmhPeer* peer, uint32_t seq, const MmhBnBwd* p, uint32_t* counter, float count_global,
                                float* dgamma, float* dbeta, void* stream);
+/* Finalisation alone, for backward statistics accumulated by a data-gradient epilogue (MmhConvDesc.bs_sums):
+ * (exchange,) k[0][c] = sum dze / count, k[1][c] = sum dze*xhat / count over all ranks, dgamma / dbeta += the local
+ * sums (NULL to skip), sums reset to zero. */
+int mmh_bn_bwd_finalize_reset(MmhPeer* peer, uint32_t seq, float* sums, float count_global, float* k, float* dgamma,
+                              float* dbeta, int32_t C, void* stream);
 int mmh_gate_bwd_reduce_finalize(MmhPeer* peer, uint32_t seq, const MmhGateBwd* p, uint32_t* counter,
                                  float count_global, float* dgamma, float* dbeta, void* stream);
 

@@ -104,8 +104,12 @@ def fwd_plans(lib, g: ConvGeom, a_buf, w_packed, out_buf, Cin_p, Cout_p, bias=No
     return plans
 
 
-def dgrad_plans(lib, g: ConvGeom, dy_buf, wd_packed, dx_buf, Cin_p, Cout_p, dx_ld=None):
-    """Plans of the data gradient: A = dY (layout g.out_lay), output = gradient of g.in_lay (every row)."""
+def dgrad_plans(lib, g: ConvGeom, dy_buf, wd_packed, dx_buf, Cin_p, Cout_p, dx_ld=None, bn_bwd=None):
+    """Plans of the data gradient: A = dY (layout g.out_lay), output = gradient of g.in_lay (every row).
+
+    bn_bwd: optional dict(x, xl, coef, save, sums, C, relu, dropout) -- the convolution's input came from
+    conv_p -> BatchNorm -> [ReLU] -> [Dropout] -> reflect padding: the launch stores the masked gradient and accumulates the
+    BatchNorm-backward sums of that producer (MmhConvDesc.bs_*; stride-1 reflect geometries only)."""
     plans = []
     il, ol = g.in_lay, g.out_lay
     M = il.plane_rows
@@ -114,6 +118,16 @@ def dgrad_plans(lib, g: ConvGeom, dy_buf, wd_packed, dx_buf, Cin_p, Cout_p, dx_l
         d = conv_desc(dy_buf, ol.rows, ol.ld, Cout_p, wd_packed, g.k * g.k, Cin_p, ln.taps, M, il.Hg, il.Wg, il.Hg,
                       il.Wg, dx_buf, ld, out_row_off=ln.out_plane * il.plane_rows if g.kind == 's2' else 0,
                       zero_invalid=False)
+        if bn_bwd is not None:
+            assert g.kind == 's1' and g.pad_mode == 'reflect' and len(g.bwd) == 1
+            xl = bn_bwd["xl"]
+            assert not xl.phase and xl.h0 == 0 and xl.w0 == 0 and xl.c0 == 0 and (xl.H, xl.W) == (il.H, il.W)
+            d.bs_x = bn_bwd["x"].data_ptr()
+            d.bs_coef, d.bs_save = bn_bwd["coef"].data_ptr(), bn_bwd["save"].data_ptr()
+            d.bs_sums = bn_bwd["sums"].data_ptr()
+            d.bs_x_ld, d.bs_xHg, d.bs_xWg = xl.ld, xl.Hg, xl.Wg
+            d.bs_H, d.bs_W, d.bs_pad, d.bs_C = il.H, il.W, g.pad, bn_bwd["C"]
+            d.bs_relu, d.bs_dropout, d.bs_drop_key = int(bn_bwd["relu"]), int(bn_bwd["dropout"]), 0
         plans.append(ConvPlan(lib, d))
     return plans
 

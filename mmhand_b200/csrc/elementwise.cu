@@ -685,6 +685,19 @@ extern "C" int mmh_bn_bwd_reduce_finalize(MmhPeer* peer, uint32_t seq, const Mmh
   return tr ? bn_bwd_reduce_fin_t<2, true>(p, fin, counter, stream)
             : bn_bwd_reduce_fin_t<2, false>(p, fin, counter, stream);
 }
+extern "C" int mmh_bn_bwd_finalize_reset(MmhPeer* peer, uint32_t seq, float* sums, float count_global, float* k,
+                                         float* dgamma, float* dbeta, int32_t C, void* stream) {
+  MMH_CHECK(sums && k && C > 0, "bad argument");
+  BnBwdFin fin = bwd_fin(sums, count_global, k, dgamma, dbeta, C);
+  if (peer_dev(peer, seq, 2 * C, &fin.px)) return 1;
+#ifdef MMH_HOST_EMU
+  (void)stream;
+  for (int c = 0; c < C; ++c) { fin(c); sums[c] = 0.f; sums[C + c] = 0.f; }
+#else
+  MMH_CUDA(launch_k(fin_reset_kernel<BnBwdFin>, dim3((C + 255) / 256), dim3(256), 0, stream, fin, sums, C));
+#endif
+  return 0;
+}
 extern "C" int mmh_bn_bwd_apply(const MmhBnBwd* p, void* stream) {
   if (bn_bwd_check(p)) return 1;
   MMH_CHECK(p->k && p->dy, "null argument");

@@ -30,8 +30,21 @@ extern "C" int mmh_conv_plan_create(const MmhConvDesc* d, MmhConvPlan** plan) {
 }
 extern "C" int mmh_conv_plan_destroy(MmhConvPlan* p) { delete p; return 0; }
 
-extern "C" int mmh_conv_run(const MmhConvPlan* plan, void*) {
-  const MmhConvDesc& d = plan->d;
+static inline uint32_t emu_mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return x;
+}
+static inline int emu_reflect(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+static int conv_run(const MmhConvDesc& d, uint32_t drop_key);
+extern "C" int mmh_conv_run(const MmhConvPlan* plan, void*) { return conv_run(plan->d, plan->d.bs_drop_key); }
+extern "C" int mmh_conv_run_key(const MmhConvPlan* plan, uint32_t drop_key, void*) { return conv_run(plan->d, drop_key); }
+
+static int conv_run(const MmhConvDesc& d, uint32_t drop_key) {
   const act_t* a = static_cast<const act_t*>(d.a);
   const act_t* w = static_cast<const act_t*>(d.w);
   const int w_taps = d.w_taps > 0 ? d.w_taps : d.T;
@@ -41,6 +54,7 @@ extern "C" int mmh_conv_run(const MmhConvPlan* plan, void*) {
   std::vector<float> acc(d.N);
   std::vector<float> arow(d.C);
   std::vector<double> bn_acc(d.bn_sums != nullptr ? 2 * d.bn_C : 0, 0.0);
+  std::vector<double> bs_acc(d.bs_x != nullptr ? 2 * d.bs_C : 0, 0.0);
   for (int64_t q = 0; q < d.M; ++q) {
     const int64_t img = q / hw, rem = q % hw;
     const int h = static_cast<int>(rem / d.Wg), x = static_cast<int>(rem % d.Wg);
@@ -77,6 +91,33 @@ extern "C" int mmh_conv_run(const MmhConvPlan* plan, void*) {
       for (int n = 0; n < n_store && n < d.N; ++n) o[n] = acc[n];
     } else {
       act_t* o = static_cast<act_t*>(d.out) + orow * d.out_ld;
+      if (d.bs_x != nullptr && valid) {
+        // fused BN-backward masks + statistics (MmhConvDesc.bs_*): the row is the gradient of a mirrored logical pixel
+        const int hs = emu_reflect(h - d.bs_pad, d.bs_H), ws = emu_reflect(x - d.bs_pad, d.bs_W);
+        const act_t* xr = static_cast<const act_t*>(d.bs_x) +
+                          ((img * d.bs_xHg + hs) * d.bs_xWg + ws) * static_cast<int64_t>(d.bs_x_ld);
+        const uint32_t G = static_cast<uint32_t>((d.bs_C + 7) / 8);
+        const uint32_t word0 = ((static_cast<uint32_t>(img) * d.bs_H + hs) * d.bs_W + ws) * G;
+        for (int n = 0; n < d.N; ++n) {
+          float v = 0.f;
+          if (n < d.bs_C) {
+            const float xv = mmh::act2f(xr[n]);
+            const float a = d.bs_coef[n], b = d.bs_coef[d.bs_C + n];
+            bool on = !d.bs_relu || (a * xv + b > 0.f);
+            float keep = 1.f;
+            if (d.bs_dropout) {
+              const uint32_t bits = emu_mix32((word0 + static_cast<uint32_t>(n >> 3)) * 0x9E3779B1u + drop_key);
+              on = on && ((bits >> (n & 7)) & 1u);
+              keep = 2.f;
+            }
+            v = on ? keep * acc[n] : 0.f;
+            const double st = mmh::act2f(mmh::f2act(v));
+            bs_acc[n] += st;
+            bs_acc[d.bs_C + n] += st * ((xv - d.bs_save[n]) * d.bs_save[d.bs_C + n]);
+          }
+          acc[n] = v;
+        }
+      }
       for (int n = 0; n < n_store && n < d.N; ++n) o[n] = mmh::f2act(acc[n]);
       if (d.bn_sums != nullptr && valid) {          // fused BN statistics of the values as stored
         for (int n = 0; n < d.bn_C && n < n_store; ++n) {
@@ -89,6 +130,8 @@ extern "C" int mmh_conv_run(const MmhConvPlan* plan, void*) {
   }
   if (d.bn_sums != nullptr)
     for (int n = 0; n < 2 * d.bn_C; ++n) d.bn_sums[n] += static_cast<float>(bn_acc[n]);
+  if (d.bs_x != nullptr)
+    for (int n = 0; n < 2 * d.bs_C; ++n) d.bs_sums[n] += static_cast<float>(bs_acc[n]);
   return 0;
 }
 

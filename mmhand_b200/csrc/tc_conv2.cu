@@ -59,6 +59,13 @@ struct Conv2Params {
   float* bn_sums;                  // fused BatchNorm statistics: [2][bn_C] += (sum, sum of squares) of the stored values
   int32_t bn_C;
   uint32_t stat_off;               // shared-memory accumulators [2][N] (only when bn_sums != nullptr)
+  // fused BatchNorm-BACKWARD statistics of a data-gradient launch (MmhConvDesc.bs_*): bn_sums / bn_C / stat_off are the
+  // accumulators [2][C] += (sum dze, sum dze * xhat); par_off = shared-memory copy of (a, b, mean, rstd) [N][4]
+  const void* bs_x;
+  const float* bs_coef;
+  const float* bs_save;
+  int32_t bs_x_ld, bs_xHg, bs_xWg, bs_H, bs_W, bs_pad, bs_relu, bs_dropout;
+  uint32_t bs_key, par_off;
   int32_t g_first[kC2MaxGroups + 1];
   int32_t g_min[kC2MaxGroups];
   int32_t rel16[MMH_MAX_TAPS + 1];  // byte offset / 16 of the tap's first row inside its group's window (+1: prefetch)
@@ -158,6 +165,113 @@ __device__ __forceinline__ void epilogue_row(const Conv2Params& p, uint32_t t_ad
   }
 }
 
+__device__ __forceinline__ uint32_t c2_mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ int c2_reflect(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+// Epilogue of a data-gradient launch that feeds  conv_p -> BatchNorm -> [ReLU] -> [Dropout]  (MmhConvDesc.bs_*): the
+// output row q is the gradient of the (mirrored) logical pixel whose raw conv_p output is the row `xrow` of bs_x. Per
+// 16-channel chunk: TMEM accumulators -> ReLU / dropout masks recomputed from x (the kernels' counter hash) ->
+// dze rounded to bf16 and stored (the BN-backward apply kernel then needs no masks) -> (sum dze, sum dze * xhat) by the
+// same 32-value butterfly reduce-scatter as the forward statistics. The raw activations come in 64-byte pieces, two
+// chunks ahead of their use (the caller prefetched the row into L2 one tile earlier); the BN-backward reduction pass over
+// dz and x (two full HBM reads) disappears.
+__device__ __forceinline__ void epilogue_row_bwd(const Conv2Params& p, uint32_t t_addr, int nchunks, int n0,
+                                                 int64_t orow, bool in_range, const __nv_bfloat16* xrow,
+                                                 uint32_t hash_word0, float* s_stats, const float4* s_par) {
+  const int lane = threadIdx.x & 31;
+  auto load_x = [&](int j, uint4 (&x)[4]) {          // chunks j, j + 1 (32 channels)
+    if (in_range && j < nchunks) {
+      const uint4* src = reinterpret_cast<const uint4*>(xrow + n0 + j * 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[i] = ldg_nc_v4(src + i);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  auto emit = [&](const uint32_t (&v)[16], const uint4& xa, const uint4& xb, int j) {
+    const int nc = n0 + j * 16;
+    const uint32_t xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+    float r[32];
+    uint32_t pk[8];
+    uint32_t bits = 0xFFFFu;
+    if (p.bs_dropout) {
+      const uint32_t g = static_cast<uint32_t>(nc >> 3);
+      bits = (c2_mix32((hash_word0 + g) * 0x9E3779B1u + p.bs_key) & 0xFFu) |
+             ((c2_mix32((hash_word0 + g + 1u) * 0x9E3779B1u + p.bs_key) & 0xFFu) << 8);
+    }
+    const float keep = p.bs_dropout ? 2.0f : 1.0f;
+    float xh[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float4 c = s_par[nc - n0 + i];                         // (a, b, mean, rstd) of channel nc + i
+      const float x = __uint_as_float((i & 1) ? (xw[i >> 1] & 0xFFFF0000u) : (xw[i >> 1] << 16));
+      float d = __uint_as_float(v[i]);
+      const bool on = in_range && (!p.bs_relu || (c.x * x + c.y > 0.f)) && ((bits >> i) & 1u);
+      d = on ? keep * d : 0.f;
+      r[i] = d;
+      xh[i] = (x - c.z) * c.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      pk[i] = pack2(r[2 * i], r[2 * i + 1]);
+      r[2 * i] = __uint_as_float(pk[i] << 16);                     // the statistics are those of the stored values
+      r[2 * i + 1] = __uint_as_float(pk[i] & 0xFFFF0000u);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[16 + i] = r[i] * xh[i];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool up = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < off; ++i) {
+        const float send = up ? r[i] : r[i + off];
+        const float kept = up ? r[i + off] : r[i];
+        r[i] = kept + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    atomicAdd(s_stats + (lane >> 4) * p.N + nc + (lane & 15), r[0]);
+    if (in_range && !(p.dbg & 8))
+      st_global_v8(static_cast<__nv_bfloat16*>(p.out) + orow * p.out_ld + nc, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5],
+                   pk[6], pk[7]);
+  };
+  uint32_t va[16], vb[16];
+  uint4 x0[4], x1[4];
+  load_x(0, x0);
+  tmem_ld16(t_addr, va);
+  for (int j = 0; j < nchunks; j += 4) {
+    load_x(j + 2, x1);
+    tmem_ld_wait();
+    tmem_ld16(t_addr + (j + 1) * 16, vb);
+    emit(va, x0[0], x0[1], j);
+    tmem_ld_wait();
+    if (j + 2 < nchunks) tmem_ld16(t_addr + (j + 2) * 16, va);
+    emit(vb, x0[2], x0[3], j + 1);
+    if (j + 2 < nchunks) {
+      load_x(j + 4, x0);
+      tmem_ld_wait();
+      tmem_ld16(t_addr + (j + 3) * 16, vb);
+      emit(va, x1[0], x1[1], j + 2);
+      tmem_ld_wait();
+      if (j + 4 < nchunks) tmem_ld16(t_addr + (j + 4) * 16, va);
+      emit(vb, x1[2], x1[3], j + 3);
+    }
+  }
+}
+
 // MMA issue loop of one CTA (pair). KS = MMAs of K = 16 per (tap, 64/32/16-channel chunk), MB = 128-row blocks per
 // tile; both compile-time so that one MMA costs two uniform adds and nothing else. With run-time bounds the
 // compiler emitted a 4 x 4 predicated unroll and ~25 uniform-datapath instructions per MMA: invisible behind
@@ -229,7 +343,9 @@ __device__ __forceinline__ void mma_issue(const Conv2Params& p, uint8_t* a_ring,
   }
 }
 
-template <int NCTA>
+// BS: the data-gradient variant with the fused BatchNorm-backward epilogue (its own instantiation: the extra registers
+// of that epilogue must not spill the plain kernel)
+template <int NCTA, bool BS = false>
 __global__ void __launch_bounds__(kC2Threads, 1)
 conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
              const __grid_constant__ Conv2Params p) {
@@ -262,6 +378,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   float* s_stats = reinterpret_cast<float*>(smem + p.stat_off);
   if (p.bn_sums != nullptr)
     for (int i = threadIdx.x; i < 2 * p.N; i += kC2Threads) s_stats[i] = 0.f;
+  float4* s_par = reinterpret_cast<float4*>(smem + p.par_off);
   if (warp == 1) {
     if (NCTA == 2) { tmem_alloc2(tmem_slot, kC2TmemCols); tmem_relinquish2(); }
     else { tmem_alloc(tmem_slot, kC2TmemCols); tmem_relinquish(); }
@@ -278,6 +395,16 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int n_tiles = p.tiles_m * p.tiles_n;
   const int first_tile = blockIdx.x / NCTA;
   const int tile_step = gridDim.x / NCTA;
+  if (BS) {
+    // per-channel BatchNorm parameters of the producer (written by the kernel that precedes this one in the stream:
+    // read past griddepcontrol.wait): (a, b, mean, rstd) per output channel; padded channels get a = 0, rstd = 0
+    for (int i = threadIdx.x; i < p.N; i += kC2Threads) {
+      const bool on = i < p.bn_C;
+      s_par[i] = make_float4(on ? p.bs_coef[i] : 0.f, on ? p.bs_coef[p.bn_C + i] : 0.f, on ? p.bs_save[i] : 0.f,
+                             on ? p.bs_save[p.bn_C + i] : 0.f);
+    }
+    __syncthreads();
+  }
 
   if (warp == 0) {
     if (elect_one()) {
@@ -358,9 +485,52 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int nchunks = p.BN / 16;
     const uint32_t empty_remote = NCTA == 2 ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : 0u;
     uint32_t acc = 0, acc_phase = 0;
+    // fused BN-backward statistics (MB == 1): row -> mirrored logical pixel -> row of the producer's raw output
+    auto bs_row = [&](int tile, int64_t& xrow, uint32_t& word0, bool& in_range, int64_t& orow) {
+      const int tm = tile / p.tiles_n;
+      const int q = (tm * NCTA + static_cast<int>(cta)) * 128 + row;
+      const int img = q / hw;
+      const int rem = q - img * hw;
+      const int h = rem / p.Wg;
+      const int x = rem - h * p.Wg;
+      in_range = q < p.M;
+      const int hs = c2_reflect(h - p.bs_pad, p.bs_H), ws = c2_reflect(x - p.bs_pad, p.bs_W);
+      xrow = (static_cast<int64_t>(img) * p.bs_xHg + hs) * p.bs_xWg + ws;
+      word0 = ((static_cast<uint32_t>(img) * p.bs_H + hs) * p.bs_W + ws) * static_cast<uint32_t>((p.bn_C + 7) / 8);
+      orow = static_cast<int64_t>(img) * p.out_img_rows + static_cast<int64_t>(h * p.out_sh + p.out_h0) * p.out_wg +
+             (x * p.out_sw + p.out_w0);
+    };
+    auto bs_prefetch = [&](int tile) {
+      if (tile >= n_tiles) return;
+      int64_t xrow, orow; uint32_t w0; bool in_range;
+      bs_row(tile, xrow, w0, in_range, orow);
+      if (!in_range) return;
+      const int tn = tile % p.tiles_n;
+      const char* base = reinterpret_cast<const char*>(p.bs_x) + (xrow * p.bs_x_ld + tn * p.BN) * 2;
+      for (int b = 0; b < p.BN * 2; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + b));
+    };
+    if (BS) bs_prefetch(first_tile);
     for (int tile = first_tile; tile < n_tiles; tile += tile_step) {
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
       const int n0 = tn * p.BN;
+      if (BS) {
+        int64_t xrow, orow; uint32_t w0; bool in_range;
+        bs_row(tile, xrow, w0, in_range, orow);
+        bs_prefetch(tile + tile_step);                  // the next tile's rows travel to L2 under this tile's work
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + acc * kC2AccStride + (static_cast<uint32_t>(quad * 32) << 16);
+        epilogue_row_bwd(p, t_addr, nchunks, n0, orow, in_range,
+                         static_cast<const __nv_bfloat16*>(p.bs_x) + xrow * p.bs_x_ld, w0, s_stats, s_par + n0);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (NCTA == 2) mbar_arrive_cluster(empty_remote + acc * 8);
+          else mbar_arrive(&tmem_empty[acc]);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       for (int mb = 0; mb < p.MB; ++mb) {
@@ -452,6 +622,7 @@ int mmh_conv2_create(const MmhConvDesc* d, MmhConv2** out_plan) {
   // pairs: worth it when the weight tile dominates the traffic and there are enough row tiles to fill 74 pairs
   int ncta = env_int("MMH_CONV_NCTA", 0);
   if (ncta == 0) ncta = (k.BN >= 128 && (k.BN % 32) == 0 && d->M >= 148 * 128) ? 2 : 1;
+  if (d->bs_x != nullptr && k.BN > 128) ncta = 2;          // the fused BN-backward epilogue handles one row block per CTA
   if (ncta == 2 && (k.BN % 32) != 0) ncta = 1;
   plan->ncta = ncta;
   k.tiles_m = (k.M + 128 * ncta - 1) / (128 * ncta);
@@ -471,7 +642,22 @@ int mmh_conv2_create(const MmhConvDesc* d, MmhConv2** out_plan) {
       return fail();
     }
   }
-  const uint32_t stat_bytes = d->bn_sums != nullptr ? ((2u * d->N * 4u + 1023u) & ~1023u) : 0u;
+  const bool bs = d->bs_x != nullptr;
+  if (bs) {
+    if (d->bn_sums != nullptr || d->bias != nullptr || d->act != 0 || d->out_f32 || d->bs_sums == nullptr ||
+        d->bs_coef == nullptr || d->bs_save == nullptr || d->bs_C <= 0 || d->bs_C > d->N || (k.BN % 32) != 0 ||
+        d->Hv != d->Hg || d->Wv != d->Wg || (d->bs_x_ld % 8) != 0 || d->bs_pad < 0 || d->bs_pad >= d->bs_H ||
+        d->bs_pad >= d->bs_W) {
+      set_error("fused BN-backward statistics need a bias-free linear bf16 data-gradient launch over the whole grid "
+                "(bs_C=%d, N=%d, BN=%d)", d->bs_C, d->N, k.BN);
+      return fail();
+    }
+    k.bn_sums = d->bs_sums; k.bn_C = d->bs_C;
+    k.bs_x = d->bs_x; k.bs_coef = d->bs_coef; k.bs_save = d->bs_save;
+    k.bs_x_ld = d->bs_x_ld; k.bs_xHg = d->bs_xHg; k.bs_xWg = d->bs_xWg; k.bs_H = d->bs_H; k.bs_W = d->bs_W;
+    k.bs_pad = d->bs_pad; k.bs_relu = d->bs_relu; k.bs_dropout = d->bs_dropout; k.bs_key = d->bs_drop_key;
+  }
+  const uint32_t stat_bytes = (d->bn_sums != nullptr || bs) ? ((2u * d->N * 4u + (bs ? 16u * d->N : 0u) + 1023u) & ~1023u) : 0u;
 
   // ---- tap groups: sort by shift, start a new group at a gap of >= 128 rows or when the window would
   // outgrow its slot
@@ -514,7 +700,7 @@ int mmh_conv2_create(const MmhConvDesc* d, MmhConv2** out_plan) {
       mb >>= 1;
   }
   mb = env_int("MMH_CONV_MB", mb);
-  if ((mb != 1 && mb != 2 && mb != 4) || mb * k.BN > 256 || ncta != 1) mb = 1;
+  if ((mb != 1 && mb != 2 && mb != 4) || mb * k.BN > 256 || ncta != 1 || d->bs_x != nullptr) mb = 1;
   k.MB = mb;
   k.dbg = env_int("MMH_C2_DEBUG", 0);
   k.tiles_m = (k.M + 128 * ncta * mb - 1) / (128 * ncta * mb);
@@ -540,6 +726,7 @@ int mmh_conv2_create(const MmhConvDesc* d, MmhConv2** out_plan) {
   k.b_ring_off = k.nA * k.a_slot_bytes;
   k.bar_off = k.b_ring_off + k.nB * k.b_slot_bytes;
   k.stat_off = k.bar_off + 512;
+  k.par_off = k.stat_off + 2u * d->N * 4u;                 // 16-byte aligned: N is a multiple of 16
   plan->smem = k.bar_off + 512 + stat_bytes + 1024;
 
   const CUtensorMapSwizzle swz = k.KC == 64   ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -551,8 +738,11 @@ int mmh_conv2_create(const MmhConvDesc* d, MmhConv2** out_plan) {
   const int tiles = k.tiles_m * k.tiles_n;
   const int units = num_sms() / ncta;
   plan->grid = (tiles < units ? tiles : units) * ncta;
-  cudaError_t e = ncta == 2 ? cudaFuncSetAttribute(conv2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-                            : cudaFuncSetAttribute(conv2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e;
+  if (bs) e = ncta == 2 ? cudaFuncSetAttribute(conv2_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                        : cudaFuncSetAttribute(conv2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  else e = ncta == 2 ? cudaFuncSetAttribute(conv2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                     : cudaFuncSetAttribute(conv2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv2_kernel): %s", cudaGetErrorString(e)); return fail(); }
   *out_plan = plan;
   return 0;
@@ -560,7 +750,10 @@ int mmh_conv2_create(const MmhConvDesc* d, MmhConv2** out_plan) {
 
 void mmh_conv2_destroy(MmhConv2* plan) { delete plan; }
 
-int mmh_conv2_run(const MmhConv2* plan, void* stream) {
+int mmh_conv2_run_key(const MmhConv2* plan, uint32_t drop_key, void* stream);
+int mmh_conv2_run(const MmhConv2* plan, void* stream) { return mmh_conv2_run_key(plan, plan->kp.bs_key, stream); }
+
+int mmh_conv2_run_key(const MmhConv2* plan, uint32_t drop_key, void* stream) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(plan->grid, 1, 1);
@@ -573,15 +766,25 @@ int mmh_conv2_run(const MmhConv2* plan, void* stream) {
   attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  const bool bs = plan->kp.bs_x != nullptr;
+  Conv2Params kp_key;
+  const Conv2Params* kp = &plan->kp;
+  if (bs && drop_key != plan->kp.bs_key) {
+    kp_key = plan->kp;                       // launch parameters are copied at launch: per-step dropout key
+    kp_key.bs_key = drop_key;
+    kp = &kp_key;
+  }
   if (plan->ncta == 2) {
     attr[1].id = cudaLaunchAttributeClusterDimension;
     attr[1].val.clusterDim.x = 2;
     attr[1].val.clusterDim.y = 1;
     attr[1].val.clusterDim.z = 1;
     cfg.numAttrs = 2;
-    MMH_CUDA(cudaLaunchKernelEx(&cfg, conv2_kernel<2>, plan->tmA, plan->tmW, plan->kp));
+    if (bs) MMH_CUDA(cudaLaunchKernelEx(&cfg, conv2_kernel<2, true>, plan->tmA, plan->tmW, *kp));
+    else MMH_CUDA(cudaLaunchKernelEx(&cfg, conv2_kernel<2>, plan->tmA, plan->tmW, *kp));
   } else {
-    MMH_CUDA(cudaLaunchKernelEx(&cfg, conv2_kernel<1>, plan->tmA, plan->tmW, plan->kp));
+    if (bs) MMH_CUDA(cudaLaunchKernelEx(&cfg, conv2_kernel<1, true>, plan->tmA, plan->tmW, *kp));
+    else MMH_CUDA(cudaLaunchKernelEx(&cfg, conv2_kernel<1>, plan->tmA, plan->tmW, *kp));
   }
   return 0;
 }

@@ -26,6 +26,11 @@ FUSE_GATHER = os.environ.get("MMH_FUSE_GATHER", "1") != "0"
 # longer epilogue (contraction length taps * channels >= 2304: the 256/512-channel 3x3 layers; measured on the 7x7
 # stems and the stride-2 layers the epilogue is the bottleneck and the fused statistics cost more than their kernel)
 CONV_STATS = int(os.environ.get("MMH_CONV_STATS", "2"))
+# BatchNorm-backward sums (and the ReLU / dropout masks) inside the data-gradient epilogue of the consumer convolution
+# (conv_p -> BN -> ReLU -> dropout -> reflect pad -> conv_c: conv_c's dgrad stores the masked gradient and accumulates
+# sum dze, sum dze * xhat of conv_p's BatchNorm): the reduction pass over dz and x disappears. 0 = off (A/B measurements).
+FUSE_BN_BWD = os.environ.get("MMH_FUSE_BN_BWD", "1") != "0"
+FUSE_BN_BWD_MIN_K = int(os.environ.get("MMH_FUSE_BN_BWD_MIN_K", "2304"))    # taps * channels of the contraction
 
 
 def plain_lay(B, H, W, Cc):
@@ -114,6 +119,7 @@ class ConvL:
         self.fwd = convops.fwd_plans(ops.lib, geom, self.x, self.wp, self.raw, self.Cin_p, self.Cout_p,
                                      bias=self.bias_p, act=act, out_f32=out_f32)
         self.fwd_stats = None
+        self.dgrad_fused = None
         self.bwd_ready = False
         self.has_wgrad = False
         self.own_dy = False
@@ -194,8 +200,25 @@ class ConvL:
                                                self.Cout_p, bn_sums=bn.sums, bn_C=bn.C)
         return True
 
-    def run_bwd(self, want_wgrad=True, want_dx=True):
-        """Consumes self.dy. Weight gradient accumulates into weight.grad; data gradient lands in self.dx."""
+    def fuse_bn_bwd(self, producer, bn, relu, dropout):
+        """Second set of data-gradient plans whose epilogue does the BatchNorm backward reduction of ``bn`` (the
+        BatchNorm behind ``producer``, whose ReLU / dropout output this convolution reads through reflect padding):
+        stride-1 reflect geometries with a contraction long enough to hide the epilogue (same rule as CONV_STATS)."""
+        g = self.g
+        if not (FUSE_BN_BWD and self.bwd_ready and self.need_dx and g.kind == 's1' and g.pad_mode == 'reflect'
+                and self.eng.fused_stats() and self.Cin_p % 64 == 0 and self.T * self.Cout_p >= FUSE_BN_BWD_MIN_K
+                and producer.g.out_lay.ld == self.Cin_p):
+            return False
+        if self.dgrad_fused is None:
+            self.dgrad_fused = convops.dgrad_plans(
+                self.eng.ops.lib, g, self.dy, self.wd, self.dx, self.Cin_p, self.Cout_p,
+                bn_bwd=dict(x=producer.raw, xl=producer.g.out_lay, coef=bn.coef, save=bn.save, sums=bn.bsums, C=bn.C,
+                            relu=relu, dropout=dropout))
+        return True
+
+    def run_bwd(self, want_wgrad=True, want_dx=True, fused_key=None):
+        """Consumes self.dy. Weight gradient accumulates into weight.grad; data gradient lands in self.dx.
+        fused_key: dropout key of the producer layer -> run the plans of fuse_bn_bwd (masked gradient + BN sums)."""
         ops = self.eng.ops
         do_w = want_wgrad and self.has_wgrad
         # The weight gradient is off the critical path (nothing before the optimiser reads it): it goes to the side
@@ -205,8 +228,12 @@ class ConvL:
         if overlap:
             ops.fork()
         if want_dx and self.need_dx:
-            for p in self.dgrad:
-                ops.run_conv(p, (self.name, "dgrad"))
+            if fused_key is not None:
+                for p in self.dgrad_fused:
+                    ops.run_conv_key(p, fused_key, (self.name, "dgrad"))
+            else:
+                for p in self.dgrad:
+                    ops.run_conv(p, (self.name, "dgrad"))
         if do_w:
             if overlap:
                 with ops.side():
@@ -274,6 +301,15 @@ class BNL:
             ops.bn_bwd_reduce(dz, dz_f32, relu, dropout, key, x, xl, self.coef, self.save, self.bsums)
             eng.bwd_finalize(self.bsums, self.bsums_g, count, self.k, dg, db, self.C)
         ops.bn_bwd_apply(dz, dz_f32, relu, dropout, key, x, xl, self.coef, self.save, self.k, dy, yl)
+
+    def backward_fused(self, srcs, x, xl, dy, yl, count, want_wgrad=True):
+        """The consumer's data-gradient epilogue already masked the gradient and accumulated self.bsums
+        (ConvL.fuse_bn_bwd): finalise (k, dgamma, dbeta; + exchange) and apply."""
+        ops, m, eng = self.eng.ops, self.mod, self.eng
+        dg, db = (m.weight.grad, m.bias.grad) if want_wgrad else (None, None)
+        w = eng.peer_world()
+        ops.bn_bwd_finalize_reset(w, self.bsums, count * (w.size if w else 1), self.k, dg, db, self.C)
+        ops.bn_bwd_apply((list(srcs), None), False, False, False, 0, x, xl, self.coef, self.save, self.k, dy, yl)
 
 
 def param_store(ops: Ops, module) -> ParamStore:
@@ -407,11 +443,16 @@ class EngineBase:
         bn.forward(conv.raw, ol.rows, ol.ld, self.B * ol.H * ol.W, training, in_epilogue=fused)
 
     def _stage_bwd(self, conv: ConvL, bn: BNL, srcs, relu, dropout, key, trunk=None, want_wgrad=True, want_dx=True,
-                   dz_out_f32=None):
-        """Backward of conv -> BN -> [ReLU] -> [dropout]: gather dz from the consumers, BN backward, conv backward."""
+                   dz_out_f32=None, fused=False):
+        """Backward of conv -> BN -> [ReLU] -> [dropout]: gather dz from the consumers, BN backward, conv backward.
+        fused: the (single) consumer's data gradient ran with ConvL.fuse_bn_bwd plans."""
         ops = self.ops
         ol = conv.g.out_lay
         B, H, W, Cc = ol.B, ol.H, ol.W, ol.C
+        if fused:
+            bn.backward_fused(srcs, conv.raw, ol, conv.dy, ol, B * H * W, want_wgrad)
+            conv.run_bwd(want_wgrad, want_dx)
+            return
         if dz_out_f32 is None and len(srcs) <= 2 and FUSE_GATHER:
             dz, f32 = (list(srcs), trunk), False          # gathered inside the two BN backward kernels
         else:
@@ -616,10 +657,11 @@ class GeneratorEngine(EngineBase):
                                c2s[0].dy, c2s[1].dy, c2s[2].dy, ol)
             for s in range(3):
                 c1, c2, bn1 = b["c1"][s], b["c2"][s], b["bn1"][s]
-                c2.run_bwd()
                 drop = self.use_dropout
                 key = self.drop_key(net_id * 1000 + 3 * i + s, c1.g.out_lay) if drop else 0
-                self._stage_bwd(c1, bn1, [c2.dx_source()], True, drop, key)
+                fused = c2.fuse_bn_bwd(c1, bn1, True, drop)
+                c2.run_bwd(fused_key=key if fused else None)
+                self._stage_bwd(c1, bn1, [c2.dx_source()], True, drop, key, fused=fused)
         b0 = self.blocks[0]["c1"]
         for s in range(3):
             st = self.stem[s]
@@ -729,10 +771,11 @@ class DiscriminatorEngine(EngineBase):
             c1, c2 = b["c1"], b["c2"]
             ol = c2.g.out_lay
             b["bn2"].backward(dcur, True, False, False, 0, c2.raw, ol, c2.dy, ol, B * h4 * w4, want_wgrad)
-            c2.run_bwd(want_wgrad)
             drop = self.use_dropout
             key = self.drop_key(net_id * 1000 + i, c1.g.out_lay) if drop else 0
-            self._stage_bwd(c1, b["bn1"], [c2.dx_source()], True, drop, key, want_wgrad=want_wgrad)
+            fused = c2.fuse_bn_bwd(c1, b["bn1"], True, drop)
+            c2.run_bwd(want_wgrad, fused_key=key if fused else None)
+            self._stage_bwd(c1, b["bn1"], [c2.dx_source()], True, drop, key, want_wgrad=want_wgrad, fused=fused)
             # d x_k = d x_{k+1} + fold(d pad(x_k))
             ops.grad_gather([c1.dx_source()], B, h4, w4, dim, self.dtrunk, plain_lay(B, h4, w4, dim), True, trunk=dcur)
             dcur = self.dtrunk

@@ -245,6 +245,19 @@ class Ops:
         else:
             self._run(self.lib.mmh_conv_run, (plan.handle, self.st()), keep=plan)
 
+    def run_conv_key(self, plan, key, tag=None):
+        """Data-gradient launch with fused BN-backward masks: ``key`` is the producer layer's dropout key (a KeyRef is
+        resolved now and again on every tape replay)."""
+        if isinstance(key, KeyRef):
+            k0 = key.resolve(self.step)
+            patch = lambda step, args, k=key: args.__setitem__(1, k.resolve(step))
+        else:
+            k0, patch = int(key) & M32, None
+        if self.conv_hook is not None and self.tape is None:
+            self.conv_hook("conv", tag, plan, lambda: self._run(self.lib.mmh_conv_run_key, (plan.handle, k0, self.st())))
+        else:
+            self._run(self.lib.mmh_conv_run_key, (plan.handle, k0, self.st()), patch, keep=plan)
+
     def run_wgrad(self, plan, tag=None):
         if self.conv_hook is not None and self.tape is None:
             self.conv_hook("wgrad", tag, plan, lambda: self._run(self.lib.mmh_wgrad_run, (plan.handle, self.st())))
@@ -310,6 +323,11 @@ class Ops:
         args, patch = self._peer_args(world, (C.byref(p), _p(counter), float(count_global), _p(dgamma), _p(dbeta),
                                               self.st()))
         self._run(self.lib.mmh_gate_bwd_reduce_finalize, args, patch, keep=p)
+
+    def bn_bwd_finalize_reset(self, world, sums, count_global, k, dgamma, dbeta, Cc):
+        """Finalisation of BN-backward sums accumulated by a data-gradient epilogue; ``sums`` returns to zero."""
+        args, patch = self._peer_args(world, (_p(sums), float(count_global), _p(k), _p(dgamma), _p(dbeta), Cc, self.st()))
+        self._run(self.lib.mmh_bn_bwd_finalize_reset, args, patch)
 
     def bn_finalize_sync(self, world, sums, count_global, gamma, beta, rm, rv, momentum, eps, Cc, coef, save):
         """Train-mode BN finalisation on the statistics of all ranks (exchange over NVLink peer memory inside the

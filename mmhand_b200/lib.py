@@ -31,6 +31,10 @@ class ConvDesc(C.Structure):
         ("zero_invalid", C.c_int32),
         ("bias", C.c_void_p), ("act", C.c_int32), ("n_store", C.c_int32),
         ("bn_sums", C.c_void_p), ("bn_C", C.c_int32), ("reserved0", C.c_int32),
+        ("bs_x", C.c_void_p), ("bs_coef", C.c_void_p), ("bs_save", C.c_void_p), ("bs_sums", C.c_void_p),
+        ("bs_x_ld", C.c_int32), ("bs_xHg", C.c_int32), ("bs_xWg", C.c_int32), ("bs_H", C.c_int32), ("bs_W", C.c_int32),
+        ("bs_pad", C.c_int32), ("bs_C", C.c_int32), ("bs_relu", C.c_int32), ("bs_dropout", C.c_int32),
+        ("bs_drop_key", C.c_uint32),
     ]
 
 
@@ -140,6 +144,7 @@ def _declare(lib):
     lib.mmh_conv_plan_create.argtypes = [C.POINTER(ConvDesc), C.POINTER(vp)]
     lib.mmh_conv_plan_destroy.argtypes = [vp]
     lib.mmh_conv_run.argtypes = [vp, vp]
+    lib.mmh_conv_run_key.argtypes = [vp, C.c_uint32, vp]
     lib.mmh_wgrad_plan_create.argtypes = [C.POINTER(WgradDesc), C.POINTER(vp)]
     lib.mmh_wgrad_plan_destroy.argtypes = [vp]
     lib.mmh_wgrad_run.argtypes = [vp, vp]
@@ -191,6 +196,7 @@ _SIMPLE_SIGS = {
                               _vp, _vp],
     "mmh_bn_finalize_reset": [_vp, C.c_uint32, _vp, _f32, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _vp, _vp, _vp],
     "mmh_bn_bwd_reduce_finalize": [_vp, C.c_uint32, C.POINTER(BnBwd), _vp, _f32, _vp, _vp, _vp],
+    "mmh_bn_bwd_finalize_reset": [_vp, C.c_uint32, _vp, _f32, _vp, _vp, _vp, _i32, _vp],
     "mmh_gate_bwd_reduce_finalize": [_vp, C.c_uint32, C.POINTER(GateBwd), _vp, _f32, _vp, _vp, _vp],
     "mmh_event_create": [C.POINTER(_vp)],
     "mmh_event_destroy": [_vp],
@@ -199,7 +205,7 @@ _SIMPLE_SIGS = {
 }
 PEER_HANDLE_BYTES = 64
 EXPORTS = ["mmh_version", "mmh_last_error", "mmh_is_device_build", "mmh_conv_plan_create", "mmh_conv_plan_destroy",
-           "mmh_conv_run", "mmh_wgrad_plan_create", "mmh_wgrad_plan_destroy", "mmh_wgrad_run"] + list(_SIMPLE_SIGS)
+           "mmh_conv_run", "mmh_conv_run_key", "mmh_wgrad_plan_create", "mmh_wgrad_plan_destroy", "mmh_wgrad_run"] + list(_SIMPLE_SIGS)
 
 
 def check(lib, rc):

@@ -135,6 +135,18 @@ def _conv_setup(kind, B, H, W, Cin, Cout, k, mode, seed):
     return g, x, w, Cin_p, Cout_p
 
 
+def _ref_dev(*ts):
+    """Big cases: the torch fp32 reference runs on the GPU too (TF32 off), results come back to the host."""
+    if HOSTEMU or not BIG_ON_GPU or ts[0].numel() < (1 << 22):
+        return ts
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return tuple(t.to(DEV) for t in ts)
+
+
+BIG_ON_GPU = True
+
+
 def _ref_fwd(kind, x, w, k, mode):
     p = (k - 1) // 2
     if kind == 's1':
@@ -162,7 +174,7 @@ def case_conv_fwd(kind='s1', B=2, H=16, W=16, Cin=64, Cout=64, k=3, mode='reflec
     for p_ in plans:
         p_.run(_stream())
     _sync()
-    want = _ref_fwd(kind, x, w, k, mode)
+    want = _ref_fwd(kind, *_ref_dev(x, w), k, mode).cpu()
     if bt is not None:
         want = want + bt.view(1, -1, 1, 1)
     if act == 1:
@@ -187,16 +199,18 @@ def case_conv_dgrad(kind='s1', B=2, H=16, W=16, Cin=64, Cout=64, k=3, mode='refl
     dy = _rand(B, Cout, g.Ho, g.Wo, seed=seed + 2)
     # reference: gradient w.r.t. the *padded* input (the conv's A operand)
     p = (k - 1) // 2
+    xr, wr, dyr = _ref_dev(x, w, dy)
     if kind == 's1':
-        xp = F.pad(x, (p, p, p, p)).requires_grad_(True)
-        y = F.conv2d(xp, w)
+        xp = F.pad(xr, (p, p, p, p)).requires_grad_(True)
+        y = F.conv2d(xp, wr)
     elif kind == 's2':
-        xp = F.pad(x, (1, 1, 1, 1)).requires_grad_(True)
-        y = F.conv2d(xp, w, stride=2)
+        xp = F.pad(xr, (1, 1, 1, 1)).requires_grad_(True)
+        y = F.conv2d(xp, wr, stride=2)
     else:
-        xp = x.clone().requires_grad_(True)
-        y = F.conv_transpose2d(xp, w, stride=2, padding=1, output_padding=1)
-    (want,) = torch.autograd.grad(y, xp, dy)
+        xp = xr.clone().requires_grad_(True)
+        y = F.conv_transpose2d(xp, wr, stride=2, padding=1, output_padding=1)
+    (want,) = torch.autograd.grad(y, xp, dyr)
+    want = want.cpu()
     dy_buf = to_grid(dy, g.out_lay, Cout_p, 0, 0, 'zero')
     wd = pack_w(w, Cin_p, Cout_p, transposed=(kind == 'up'), swap=True)
     dx = torch.full((g.in_lay.rows, Cin_p), 7.0, dtype=torch.bfloat16, device=DEV)
@@ -211,13 +225,68 @@ def case_conv_dgrad(kind='s1', B=2, H=16, W=16, Cin=64, Cout=64, k=3, mode='refl
     return _cmp("dgrad_%s_B%d_%dx%d_%d-%d_k%d" % (kind, B, H, W, Cin, Cout, k), got, want)
 
 
+def case_conv_dgrad_bnbwd(B=2, H=16, W=16, Cin=64, Cout=64, relu=True, dropout=True, seed=11, key=0x1234ABCD):
+    """Data gradient of a 3x3 reflect convolution with the fused BatchNorm-backward epilogue (MmhConvDesc.bs_*): the
+    stored rows are the masked gradient of the mirrored pixel and bs_sums holds (sum dze, sum dze * xhat)."""
+    from oracle.patn_ref import dropout_mask
+    lib = _lib()
+    k, mode = 3, 'reflect'
+    g, _, w, Cin_p, Cout_p = _conv_setup('s1', B, H, W, Cin, Cout, k, mode, seed)
+    dy = _rand(B, Cout, H, W, seed=seed + 2)
+    xraw = _rand(B, Cin, H, W, seed=seed + 3)                 # raw output of the producer convolution
+    gen = torch.Generator().manual_seed(seed + 4)
+    a = torch.rand(Cin, generator=gen) + 0.5
+    b = torch.randn(Cin, generator=gen) * 0.5
+    mean = torch.randn(Cin, generator=gen) * 0.3
+    rstd = torch.rand(Cin, generator=gen) + 0.5
+    xp = F.pad(torch.zeros(B, Cin, H, W), (1, 1, 1, 1)).requires_grad_(True)
+    (dxp,) = torch.autograd.grad(F.conv2d(xp, w), xp, dy)    # gradient w.r.t. the padded input
+    mask = torch.ones(B, Cin, H, W)
+    if relu:
+        mask = mask * ((a.view(1, -1, 1, 1) * xraw + b.view(1, -1, 1, 1)) > 0).float()
+    if dropout:
+        mask = mask * 2.0 * dropout_mask((B, Cin, H, W), key)
+    rp = lambda t: F.pad(t, (1, 1, 1, 1), mode='reflect')
+    want = (dxp * rp(mask)).to(torch.bfloat16).float()
+    xhat = (xraw - mean.view(1, -1, 1, 1)) * rstd.view(1, -1, 1, 1)
+    want_s0 = want.sum(dim=(0, 2, 3))
+    want_s1 = (want * rp(xhat)).sum(dim=(0, 2, 3))
+    # producer's raw output on ITS output grid (same Hg x Wg, content at (0, 0)), statistics / coefficient vectors
+    gp = geom_s1(B, H, W, 3, 'reflect', Cin_p, Cin_p)
+    x_buf = to_grid(xraw, gp.out_lay, Cin_p, 0, 0, 'zero')
+    coef = torch.zeros(2 * Cin); coef[:Cin] = a; coef[Cin:] = b
+    save = torch.zeros(2 * Cin); save[:Cin] = mean; save[Cin:] = rstd
+    coef, save = coef.to(DEV), save.to(DEV)
+    sums = torch.zeros(2 * Cin, dtype=torch.float32, device=DEV)
+    dy_buf = to_grid(dy, g.out_lay, Cout_p, 0, 0, 'zero')
+    wd = pack_w(w, Cin_p, Cout_p, swap=True)
+    dx = torch.full((g.in_lay.rows, Cin_p), 7.0, dtype=torch.bfloat16, device=DEV)
+    plans = convops.dgrad_plans(lib, g, dy_buf, wd, dx, Cin_p, Cout_p,
+                                bn_bwd=dict(x=x_buf, xl=gp.out_lay, coef=coef, save=save, sums=sums, C=Cin, relu=relu,
+                                            dropout=dropout))
+    for p_ in plans:
+        L.check(lib, lib.mmh_conv_run_key(p_.handle, key, _stream()))
+    _sync()
+    got = from_grid(dx, g.in_lay, Cin, H + 2, W + 2, -1, -1)
+    r = _cmp("dgrad_bnbwd_B%d_%dx%d_%d-%d_r%d_d%d" % (B, H, W, Cin, Cout, relu, dropout), got, want)
+    s = sums.float().cpu()
+    # the masks must be decided identically (a flipped mask shows as an O(1) relative error on that element)
+    e0 = (s[:Cin] - want_s0).abs().max().item() / (want.abs().sum(dim=(0, 2, 3)).max().item() + 1e-6)
+    e1 = (s[Cin:] - want_s1).abs().max().item() / ((want * rp(xhat)).abs().sum(dim=(0, 2, 3)).max().item() + 1e-6)
+    r["sum_err"], r["sumx_err"] = e0, e1
+    r["ok"] = r["ok"] and e0 <= 2e-3 and e1 <= 2e-3
+    return r
+
+
 def case_conv_wgrad(kind='s1', B=2, H=16, W=16, Cin=64, Cout=64, k=3, mode='reflect', seed=7, split_k=0):
     lib = _lib()
     g, x, w, Cin_p, Cout_p = _conv_setup(kind, B, H, W, Cin, Cout, k, mode, seed)
     dy = _rand(B, Cout, g.Ho, g.Wo, seed=seed + 2)
-    wv = w.clone().requires_grad_(True)
-    y = _ref_fwd(kind, x, wv, k, mode)
-    (want,) = torch.autograd.grad(y, wv, dy)
+    xr, wr, dyr = _ref_dev(x, w, dy)
+    wv = wr.clone().requires_grad_(True)
+    y = _ref_fwd(kind, xr, wv, k, mode)
+    (want,) = torch.autograd.grad(y, wv, dyr)
+    want = want.cpu()
     a_buf = to_grid(x, g.in_lay, Cin_p, g.in_pad_lo, g.in_pad_hi, mode if kind == 's1' else 'zero')
     dy_buf = to_grid(dy, g.out_lay, Cout_p, 0, 0, 'zero')
     dw = torch.zeros(k * k, Cout, Cin, dtype=torch.float32, device=DEV)
@@ -293,6 +362,11 @@ CASES = {
     "dgrad_s1_7x7_out3": lambda: case_conv_dgrad('s1', 1, 32, 32, 64, 3, 7),
     "dgrad_s2": lambda: case_conv_dgrad('s2', 2, 32, 32, 64, 128),
     "dgrad_up": lambda: case_conv_dgrad('up', 2, 16, 16, 256, 128),
+    "dgrad_bnbwd_64": lambda: case_conv_dgrad_bnbwd(2, 16, 16, 64, 64),
+    "dgrad_bnbwd_256": lambda: case_conv_dgrad_bnbwd(2, 64, 64, 256, 256),
+    "dgrad_bnbwd_512": lambda: case_conv_dgrad_bnbwd(3, 64, 64, 512, 256),
+    "dgrad_bnbwd_256_norelu": lambda: case_conv_dgrad_bnbwd(1, 32, 32, 256, 256, relu=False, dropout=False),
+    "dgrad_bnbwd_128_nodrop": lambda: case_conv_dgrad_bnbwd(5, 24, 40, 128, 64, relu=True, dropout=False),
     "wgrad_s1_3x3": lambda: case_conv_wgrad('s1', 2, 16, 16, 64, 64, 3),
     "wgrad_s1_3x3_256": lambda: case_conv_wgrad('s1', 2, 32, 32, 256, 256, 3),
     "wgrad_s1_3x3_512": lambda: case_conv_wgrad('s1', 1, 32, 32, 512, 256, 3),
@@ -302,6 +376,35 @@ CASES = {
     "wgrad_s1_c32": lambda: case_conv_wgrad('s1', 1, 32, 32, 24, 64, 7),
     "wgrad_s2": lambda: case_conv_wgrad('s2', 2, 32, 32, 64, 128),
     "wgrad_up": lambda: case_conv_wgrad('up', 2, 16, 16, 256, 128),
+    # full-size cases: the batch-16 / 256 x 256 shapes of BASELINE configs[2] (M up to 1.1 M grid rows, deep split-K)
+    "big_fwd_stem_c3": lambda: case_conv_fwd('s1', 16, 256, 256, 3, 64, 7, 'reflect'),
+    "big_fwd_stem_c42": lambda: case_conv_fwd('s1', 16, 256, 256, 42, 64, 7, 'reflect'),
+    "big_fwd_out3": lambda: case_conv_fwd('s1', 16, 256, 256, 64, 3, 7, 'reflect', bias=True, act=2),
+    "big_fwd_s2": lambda: case_conv_fwd('s2', 16, 256, 256, 64, 128),
+    "big_fwd_s2_b": lambda: case_conv_fwd('s2', 16, 128, 128, 128, 256),
+    "big_fwd_3x3_256": lambda: case_conv_fwd('s1', 16, 64, 64, 256, 256, 3, 'reflect'),
+    "big_fwd_3x3_512": lambda: case_conv_fwd('s1', 16, 64, 64, 512, 512, 3, 'reflect'),
+    "big_fwd_up": lambda: case_conv_fwd('up', 16, 64, 64, 256, 128),
+    "big_fwd_up_b": lambda: case_conv_fwd('up', 16, 128, 128, 128, 64),
+    "big_dgrad_out3": lambda: case_conv_dgrad('s1', 16, 256, 256, 64, 3, 7),
+    "big_dgrad_stem_c24": lambda: case_conv_dgrad('s1', 16, 256, 256, 24, 64, 7),
+    "big_dgrad_s2": lambda: case_conv_dgrad('s2', 16, 256, 256, 64, 128),
+    "big_dgrad_s2_b": lambda: case_conv_dgrad('s2', 16, 128, 128, 128, 256),
+    "big_dgrad_3x3_512": lambda: case_conv_dgrad('s1', 16, 64, 64, 512, 256, 3),
+    "big_dgrad_up": lambda: case_conv_dgrad('up', 16, 64, 64, 256, 128),
+    "big_dgrad_up_b": lambda: case_conv_dgrad('up', 16, 128, 128, 128, 64),
+    "big_dgrad_bnbwd_512": lambda: case_conv_dgrad_bnbwd(16, 64, 64, 512, 256),
+    "big_dgrad_bnbwd_256": lambda: case_conv_dgrad_bnbwd(16, 64, 64, 256, 256),
+    "big_wgrad_stem_c3": lambda: case_conv_wgrad('s1', 16, 256, 256, 3, 64, 7),
+    "big_wgrad_stem_c42": lambda: case_conv_wgrad('s1', 16, 256, 256, 42, 64, 7),
+    "big_wgrad_stem_c24": lambda: case_conv_wgrad('s1', 16, 256, 256, 24, 64, 7),
+    "big_wgrad_out3": lambda: case_conv_wgrad('s1', 16, 256, 256, 64, 3, 7),
+    "big_wgrad_s2": lambda: case_conv_wgrad('s2', 16, 256, 256, 64, 128),
+    "big_wgrad_s2_b": lambda: case_conv_wgrad('s2', 16, 128, 128, 128, 256),
+    "big_wgrad_3x3_256": lambda: case_conv_wgrad('s1', 16, 64, 64, 256, 256, 3),
+    "big_wgrad_3x3_512": lambda: case_conv_wgrad('s1', 16, 64, 64, 512, 512, 3),
+    "big_wgrad_up": lambda: case_conv_wgrad('up', 16, 64, 64, 256, 128),
+    "big_wgrad_up_b": lambda: case_conv_wgrad('up', 16, 128, 128, 128, 64),
     "perf": lambda: case_perf(),
     "perf512": lambda: case_perf(16, 64, 64, 512, 512),
     "perf_stem": lambda: case_perf(16, 256, 256, 3, 64, k=7),

@@ -15,10 +15,17 @@ from oracle import patn_ref as O
 from oracle.ref_shims import make_opt
 
 
-@pytest.fixture
-def emu_f32():
+@pytest.fixture(params=["fused_bn_bwd", "plain_bn_bwd"])
+def emu_f32(request):
+    """Every test runs twice: with the BatchNorm-backward sums taken in the consumer's data-gradient epilogue
+    (MmhConvDesc.bs_*; the small test networks are below the product's contraction-length threshold, so it is lowered
+    here) and with the separate reduction kernels."""
+    from mmhand_b200 import engine
     runtime._TEST_OPS = hostemu.ops(f32=True)
+    saved = engine.FUSE_BN_BWD, engine.FUSE_BN_BWD_MIN_K
+    engine.FUSE_BN_BWD, engine.FUSE_BN_BWD_MIN_K = request.param == "fused_bn_bwd", 0
     yield
+    engine.FUSE_BN_BWD, engine.FUSE_BN_BWD_MIN_K = saved
     runtime._TEST_OPS = None
 
 
