@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: 16 train, 32 infer)")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="train workload on one GPU: skip the short infer / raster runs reported under 'secondary'")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     a = ap.parse_args()
     if a.steps is None:
@@ -48,7 +50,8 @@ def parse():
 
 
 def synth_batch(B, S, seed, pin=False):
-    """RHD/STB-shaped synthetic sample dict: images U(-1,1), sparse heatmaps in [0,1], depth x3."""
+    """RHD/STB-shaped synthetic sample dict in the reference loader's fp32 form: images U(-1,1), sparse
+    heatmaps in [0,1], depth x3."""
     import torch
     g = torch.Generator().manual_seed(seed)
     r = lambda *s: torch.rand(*s, generator=g)
@@ -58,6 +61,30 @@ def synth_batch(B, S, seed, pin=False):
                P2=(r(B, 21, S, S) > 0.984).float() * r(B, 21, S, S), D2=d2.expand(B, 3, S, S).contiguous())
     if pin:
         out = {k: v.pin_memory() for k, v in out.items()}
+    return out
+
+
+def synth_compact_batch(B, S, seed, pin=True):
+    """The same kind of sample as the device-side input pipeline delivers it (mmhand_b200/loader.py): uint8 colour and
+    depth frames as cv2.imread returns them (BGR; depth = 256*G + R in [200, 700) mm) and float64 keypoints inside the
+    frame. MMHandModel.set_input turns them into the six fp32 tensors on the device (21 Gaussian heatmaps per pose,
+    ~98.4 % zeros: the real distribution)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k in ("H1", "H2"):
+        out[k + "_u8"] = torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8)
+    for k in ("D1", "D2"):
+        d = torch.randint(200, 700, (B, S, S), generator=g, dtype=torch.int32)
+        f = torch.zeros(B, S, S, 3, dtype=torch.uint8)
+        f[..., 1] = (d // 256).to(torch.uint8)
+        f[..., 2] = (d % 256).to(torch.uint8)
+        out[k + "_u8"] = f
+    for k in ("P1", "P2"):
+        out[k + "_uv"] = (torch.rand(B, 21, 2, generator=g, dtype=torch.float64) * (S - 32) + 16)
+    if pin:
+        out = {k: v.pin_memory() for k, v in out.items()}
+    out["u8_bgr"] = True
     return out
 
 
@@ -88,8 +115,9 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def cpu_reference_rate(S, seconds, max_steps=None):
-    """Reference arithmetic (oracle port of MMHandModel.optimize_parameters) on the host cores, batch 1, fp32."""
+def cpu_reference_rate(S, seconds, max_steps=None, B=1):
+    """Reference arithmetic (oracle port of MMHandModel.optimize_parameters) on the host cores, fp32, batch B.
+    Returns (images per second, timed steps, threads)."""
     import random
 
     import torch
@@ -118,16 +146,18 @@ def cpu_reference_rate(S, seconds, max_steps=None):
     dpp = init({k: v.clone() for k, v in Discriminator(6, 64, norm, True, 3).state_dict().items()})
     vgg = torchvision.models.vgg19(weights=None).features[:4].state_dict()
     tr = O.OracleTrainer(g, dpb, dpp, vgg, dropout="hash", seed=49, device="cpu")
-    b = synth_batch(1, S, 7)
+    b = synth_batch(B, S, 7)
+    t_w = time.time()
     tr.step(b["H1"], b["P1"], b["D1"], b["H2"], b["P2"], b["D2"])       # warm-up
+    t_w = time.time() - t_w
     n, t0 = 0, time.time()
     while True:
         tr.step(b["H1"], b["P1"], b["D1"], b["H2"], b["P2"], b["D2"])
         n += 1
         el = time.time() - t0
-        if el >= seconds or (max_steps and n >= max_steps):
+        if el + t_w >= seconds or (max_steps and n >= max_steps):      # never start a step that overruns the budget
             break
-    return n / el, n, torch.get_num_threads()
+    return B * n / el, n, torch.get_num_threads()
 
 
 def run_reference(a):
@@ -135,16 +165,18 @@ def run_reference(a):
     if rank != 0:
         return
     budget = 150.0
-    rate, n, cores = cpu_reference_rate(a.size, budget, max_steps=max(1, a.steps))
+    rate, n, cores = cpu_reference_rate(a.size, budget, max_steps=max(1, a.steps), B=a.batch)
     line = {
         "impl": "reference", "metric": "G+D train-step images/sec @256x256", "value": rate, "unit": "images/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 / rate,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[2]: full G+D training, L1+VGG19 perceptual loss, 256x256, BN, dropout on",
-                   "per_gpu_batch": a.batch, "frame": a.size},
+                   "per_gpu_batch": a.batch, "global_batch": a.batch, "frame": a.size,
+                   "parallelism": "host cores (rank 0 only)"},
         "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": "%d step(s) of batch 1 (reference arithmetic restated in oracle/patn_ref.py, torch "
-                                   "fp32 CPU ops, all host threads; the reference is Python and cannot travel to the box)" % n},
+                         "sample": "%d timed step(s) of batch %d after one warm-up step, inside a 150 s budget (reference "
+                                   "arithmetic restated in oracle/patn_ref.py, torch fp32 CPU ops, all host threads; the "
+                                   "reference is Python + apex and cannot travel to the box)" % (n, a.batch)},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -177,9 +209,16 @@ def run_ours(a):
     with contextlib.redirect_stdout(io.StringIO()):
         model = MMHandModel(opt)
     ops = runtime.get_ops(torch.device("cuda", local))
-    host = [synth_batch(B, S, 1000 + 17 * rank + i, pin=True) for i in range(2)]
-    dev = [{k: v.cuda(non_blocking=True) for k, v in h.items()} for h in host]
-    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    # e2e feed: what the device-side input pipeline delivers (uint8 frames + keypoints, pinned); device-resident feed:
+    # the six fp32 tensors set_input makes of those very batches (already in HBM when the timed region starts)
+    host = [synth_compact_batch(B, S, 1000 + 17 * rank + i, pin=True) for i in range(2)]
+    dev = []
+    for h in host:
+        model.set_input(h)
+        dev.append({k: getattr(model, "input_" + k).clone() for k in ("H1", "P1", "D1", "H2", "P2", "D2")})
+    torch.cuda.synchronize()
+    model._in_shapes = None          # the timed feeds re-create the static input buffers once, in warm-up
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values() if isinstance(v, torch.Tensor))
 
     def barrier():
         if world > 1:
@@ -214,26 +253,30 @@ def run_ours(a):
     sampler = ClockSampler(local)
     sampler.start()
     ms, launches = timed(a.steps, dev, False)
+    for i in range(2):                                   # the compact feed's staging buffers / first launches
+        model.set_input(host[i])
+        model.optimize_parameters()
     ms_e2e, _ = timed(a.steps, host, True)
     sampler.stop_flag = True
     sampler.join(timeout=3)
     value = B * world * a.steps / (ms / 1000.0)
     e2e = B * world * a.steps / (ms_e2e / 1000.0)
 
-    # roofline of the dominant kernel (conv2_kernel: every forward / data-gradient convolution): one extra
-    # instrumented step with a CUDA-event pair around each of its launches on the launching stream
-    recs = []
+    # rooflines: one extra instrumented (eager, single-stream) step with a CUDA-event pair around every launch of the
+    # tensor-core kernels on the launching stream
+    recs = {"conv": [], "wgrad": []}
 
     def hook(kind, tag, plan, launch):
-        if kind != "conv":
-            launch()
-            return
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         launch()
         e1.record()
         d = plan.desc
-        recs.append((e0, e1, 2.0 * d.M * d.N * d.C * d.T * (d.Hv * d.Wv) / float(d.Hg * d.Wg)))
+        if kind == "conv":
+            fl = 2.0 * d.M * d.N * d.C * d.T * (d.Hv * d.Wv) / float(d.Hg * d.Wg)
+        else:
+            fl = 2.0 * d.M * d.N_store * d.C_store * d.T
+        recs[kind].append((e0, e1, fl))
 
     model.use_tape = False
     ops.conv_hook = hook
@@ -244,21 +287,32 @@ def run_ours(a):
     ops.side_stream = side
     ops.conv_hook = None
     model.use_tape = True
-    t_conv = sum(e0.elapsed_time(e1) for e0, e1, _ in recs) / 1000.0
-    f_conv = sum(f for _, _, f in recs)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
-    achieved = f_conv / t_conv / 1e12 if t_conv > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "conv2_kernel (tcgen05 implicit-GEMM fprop/dgrad, csrc/tc_conv2.cu)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PF sustained",
-                "launches_per_step": len(recs), "kernel_ms_per_step": t_conv * 1000.0,
-                "flops_note": "padded-grid rows excluded; padded channels included (stems only)",
-                "step_tensor_util": GFLOP_PER_IMG * 1e9 * value / world / (peak * 1e12)}
+    src = "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PF sustained"
+
+    def roof(kind, kernel, traffic, note):
+        t = sum(e0.elapsed_time(e1) for e0, e1, _ in recs[kind]) / 1000.0
+        f = sum(f for _, _, f in recs[kind])
+        ach = f / t / 1e12 if t > 0 else 0.0
+        return {"bound": "tensor", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "traffic": traffic, "peak_source": src, "launches_per_step": len(recs[kind]),
+                "kernel_ms_per_step": t * 1000.0, "flops_note": note}
+
+    roofline = roof("conv", "conv2_kernel (tcgen05 implicit-GEMM fprop/dgrad, csrc/tc_conv2.cu)",
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one 3x3 512->512 launch at batch 16 (ncu --set full,
+                    # profiles/r01_conv2_ncu_full_v6.txt): 76.3 MB read + 36.3 MB written, against 71.4 (activations) +
+                    # 4.7 (weights) + 71.4 (output) MB algorithmic -- the output stays in L2 for its consumer
+                    {"bytes_per_launch_3x3_512": 112.6e6, "algorithmic_bytes": 147.5e6} if (B == 16 and S == 256) else None,
+                    "algorithmic 2*MACs of the valid output positions (padded-grid rows excluded); the stems' channel "
+                    "padding (3/6/24/42 -> 16/16/32/48) is included")
+    roofline["step_tensor_util"] = GFLOP_PER_IMG * 1e9 * value / world / (peak * 1e12)
+    roofline_wgrad = roof("wgrad", "wgrad2_kernel (tcgen05 weight gradient, csrc/tc_wgrad2.cu)", None,
+                          "algorithmic 2*MACs over all grid rows with un-padded channel counts")
     if rank != 0:
         return
     line = {
@@ -268,18 +322,27 @@ def run_ours(a):
         "config": {"workload": "configs[2]: full G+D training, L1+VGG19 perceptual loss, 256x256, BN, dropout on",
                    "per_gpu_batch": B, "global_batch": B * world, "frame": S, "parallelism": "dp%d" % world,
                    "l2": "per-step working set (activations > 5 GB) far exceeds the 126 MB L2",
-                   "vgg_weights": "random-init (no network)"},
+                   "vgg_weights": "random-init (no network)",
+                   "syncbn": ("peer" if (model.world is not None and model.world.peer is not None) else
+                              ("nccl" if world > 1 else "local")),
+                   "pdl": os.environ.get("MMH_PDL", "1") != "0",
+                   "grad_allreduce": getattr(model, "grad_sync_mode", "none") if world > 1 else "none",
+                   "bn_bwd_in_dgrad_epilogue": os.environ.get("MMH_FUSE_BN_BWD", "1") != "0",
+                   "e2e_feed": "uint8 frames + float64 keypoints from pinned host memory (mmhand_b200/loader.py form); "
+                               "heatmaps rasterised and frames normalised on the device inside set_input"},
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 6 * 4,
                 "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline,
+        "rooflines_other": [roofline_wgrad],
     }
     if world == 1 and not a.no_cpu_baseline:
         rate, n, cores = cpu_reference_rate(S, a.cpu_seconds)
         line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
                                 "sample": "%d step(s) of batch 1, oracle port of the reference step, torch fp32 CPU" % n}
-    print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    return line
 
 
 # ======================================================================================= secondary workloads
@@ -432,7 +495,7 @@ def run_infer(a):
         rate = n / (time.time() - t0)
         line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": "%d eval forwards of batch 1, oracle port of Generator.forward, torch fp32 CPU" % n}
-    print(json.dumps(line))
+    return line
 
 
 def run_raster(a):
@@ -515,7 +578,7 @@ def run_raster(a):
         rate = n / (time.time() - t0)
         line["cpu_baseline"] = {"value": rate, "unit": "poses/s", "cores": 1, "kind": "port",
                                 "sample": "%d poses, numpy restatement of Genericdataset.get_heatmaps (one DataLoader worker)" % n}
-    print(json.dumps(line))
+    return line
 
 
 def run_jointsmap(a):
@@ -596,7 +659,7 @@ def run_jointsmap(a):
         rate = n / (time.time() - t0)
         line["cpu_baseline"] = {"value": rate, "unit": "poses/s", "cores": 1, "kind": "port",
                                 "sample": "%d poses, generate_jointsmap (%s), one DataLoader worker" % (n, kind)}
-    print(json.dumps(line))
+    return line
 
 
 def _watchdog(seconds):
@@ -622,11 +685,23 @@ if __name__ == "__main__":
         _watchdog(int(os.environ.get("MMH_BENCH_WATCHDOG_S", "300")))
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "infer":
-        run_infer(args)
-    elif args.workload == "raster":
-        run_raster(args)
-    elif args.workload == "jointsmap":
-        run_jointsmap(args)
-    else:
-        run_ours(args)
+        sys.exit(0)
+    fn = {"infer": run_infer, "raster": run_raster, "jointsmap": run_jointsmap, "train": run_ours}[args.workload]
+    line = fn(args)
+    if line is not None and args.workload == "train" and line["n_gpus"] == 1 and not args.no_secondary:
+        # the other BASELINE configs, short runs, so that the driver's record carries them next to the headline
+        import copy
+        sec = {}
+        for name, f, steps, batch in (("infer_configs1", run_infer, 10, 32), ("raster_configs3", run_raster, 60, None)):
+            b = copy.copy(args)
+            b.steps, b.warmup, b.no_cpu_baseline, b.workload = steps, 3, True, name.split("_")[0]
+            if batch:
+                b.batch = batch
+            try:
+                r = f(b)
+                sec[name] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "roofline", "config")}
+            except Exception as e:          # a failed side measurement must not cost the headline
+                sec[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+        line["secondary"] = sec
+    if line is not None:
+        print(json.dumps(line))

@@ -391,6 +391,18 @@ int mmh_bn_bwd_finalize_reset(MmhPeer* peer, uint32_t seq, float* sums, float co
 int mmh_gate_bwd_reduce_finalize(MmhPeer* peer, uint32_t seq, const MmhGateBwd* p, uint32_t* counter,
                                  float count_global, float* dgamma, float* dbeta, void* stream);
 
+/* ---- device side of the input pipeline ------------------------------------------------
+ * What the reference's dataset workers compute per sample on the CPU (data/generic_dataset.py:133-159), applied on the
+ * GPU to the uint8 frames cv2.imread returns, in the same float64 arithmetic with the fp32 cast last (bit-identical):
+ *   mmh_image_unpack_u8: dst[b][c][h][w] = float(((double)src[b][h][w][c'] / 255.0 - 0.5) / 0.5), c' = 2 - c when
+ *                        swap_rb (cv2.cvtColor(BGR2RGB), :140-143) -- NHWC uint8 -> NCHW fp32 in [-1, 1]
+ *   mmh_depth_unpack_u8: d = 256.0 * src[..][hi_ch] + src[..][lo_ch]; v = float((d / div - 0.5) / 0.5), written to the
+ *                        three channels of dst (:148-159: hi = 1 (G), lo = 2 (R) of the BGR frame, div = 700) */
+int mmh_image_unpack_u8(const uint8_t* src_nhwc, int64_t n_img, int32_t H, int32_t W, int32_t swap_rb, float* dst_nchw,
+                        void* stream);
+int mmh_depth_unpack_u8(const uint8_t* src_nhwc, int64_t n_img, int32_t H, int32_t W, int32_t hi_ch, int32_t lo_ch,
+                        double div, float* dst_nchw3, void* stream);
+
 /* ---- stream ordering (cudaEvent wrappers, so that recorded launch sequences can fork / join streams) ----
  * The weight-gradient kernels of a layer run on a side stream next to the bandwidth-bound BatchNorm-backward
  * kernels of the following layers (apex's delay_allreduce backward has no such overlap, MMHandModel.py:110-116). */

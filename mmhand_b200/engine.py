@@ -30,6 +30,9 @@ CONV_STATS = int(os.environ.get("MMH_CONV_STATS", "2"))
 # (conv_p -> BN -> ReLU -> dropout -> reflect pad -> conv_c: conv_c's dgrad stores the masked gradient and accumulates
 # sum dze, sum dze * xhat of conv_p's BatchNorm): the reduction pass over dz and x disappears. 0 = off (A/B measurements).
 FUSE_BN_BWD = os.environ.get("MMH_FUSE_BN_BWD", "1") != "0"
+# data parallel: all-reduce the generator's weight gradients bucket by bucket during its backward pass (0: one all-reduce
+# of the whole gradient after the pass)
+GRAD_BUCKETS = os.environ.get("MMH_GRAD_BUCKETS", "1") != "0"
 FUSE_BN_BWD_MIN_K = int(os.environ.get("MMH_FUSE_BN_BWD_MIN_K", "2304"))    # taps * channels of the contraction
 
 
@@ -46,7 +49,12 @@ class ParamStore:
 
     def __init__(self, ops: Ops, module):
         self.ops, self.module = ops, module
-        self.params = [p for p in module.parameters()]
+        # flat order: BatchNorm scales / shifts and biases first (one small contiguous region: in data-parallel runs
+        # with bucketed weight-gradient all-reduces it is the only part of ``grad`` that still has to be summed over
+        # the ranks at the end of a backward pass), then the convolution weights
+        ps = [p for p in module.parameters()]
+        self.params = [p for p in ps if p.dim() != 4] + [p for p in ps if p.dim() == 4]
+        self.n_small = sum(p.numel() for p in ps if p.dim() != 4)
         self.flat = None
         self.step = 0
         self.m = self.v = None
@@ -418,10 +426,27 @@ class EngineBase:
     def begin_wgrad(self):
         self.ops.memset0(self.dw_all)
 
+    def bucketed(self):
+        """Weight gradients of this engine are summed over the ranks bucket by bucket during backward."""
+        w = self.world
+        return bool(GRAD_BUCKETS and getattr(self, "buckets", None) and w is not None and w.size > 1
+                    and hasattr(w, "all_reduce_bucket"))
+
+    def reduce_bucket(self, name):
+        """The packed weight gradients of bucket ``name`` are complete (their kernels are enqueued): sum over ranks."""
+        if not self.bucketed():
+            return
+        lo, hi = self.buckets[name]
+        view, w, ops = self.dw_all[lo:hi], self.world, self.ops
+        ops.host(lambda: w.all_reduce_bucket(ops, view))
+
     def end_wgrad(self):
         if getattr(self, "side_pending", False):
             self.ops.join()            # weight gradients launched on the side stream are complete past this point
             self.side_pending = False
+        if self.bucketed():
+            w, ops = self.world, self.ops
+            ops.host(lambda: w.wait_buckets(ops))
         if getattr(self, "_unpack_table", None) is None:
             self.store.ensure()
             self._unpack_table = self.ops.make_param_jobs([c.unpack_job() for c in self.convs() if c.has_wgrad])
@@ -546,6 +571,22 @@ class GeneratorEngine(EngineBase):
         self.cout.prepare_backward("out", "out")
         self.dtrunk = self.ops.zeros(self.B * self.h4 * self.w4, self.dim, dtype=torch.float32)
         self.bind_wgrad()
+        # gradient buckets in the order backward completes them: [up path + last block], each earlier block, and
+        # [first block + stems] -- ranges of the packed buffer (bind order = convs(): stems, blocks, up path)
+        off, start = 0, {}
+        for c in self.convs():
+            start[c.name] = off
+            off += c.dw_numel()
+        first = lambda i: start[self.blocks[i]["c1"][0].name]
+        self.buckets = {}
+        nb = self.nb
+        if nb >= 2:
+            self.buckets["tail"] = (first(nb - 1), off)
+            for i in range(nb - 2, 0, -1):
+                self.buckets["b%d" % i] = (first(i), first(i + 1))
+            self.buckets["head"] = (0, first(1))
+        else:
+            self.buckets["head"] = (0, off)
         self.bwd_ready = True
         self.repack(force=True)
 
@@ -560,14 +601,7 @@ class GeneratorEngine(EngineBase):
         self.training, self.step, self.net_id = training, step, net_id
         self.ops.step = step
         b0 = self.blocks[0]
-        # image and depth stems first: they run under the (much larger) host-to-device copy of the pose maps
-        events = getattr(self, "input_events", {})
-        stems = ((0, (x1, None)), (1, (x2a, x2b)), (2, (x3a, x3b)))
-        if events:          # asynchronous input copies (MMHandModel.set_input): pose stem last, under its own copy
-            stems = (stems[0], stems[2], stems[1])
-        for s, (a, b_) in stems:
-            for ev in events.get(s, ()):
-                ops.wait_event(ev)
+        for s, (a, b_) in ((0, (x1, None)), (1, (x2a, x2b)), (2, (x3a, x3b))):
             st = self.stem[s]
             c7, d1, d2 = st["c7"], st["d1"], st["d2"]
             ops.assemble(a, b_, c7.x, c7.g.in_lay, 3, 3, True)
@@ -662,6 +696,8 @@ class GeneratorEngine(EngineBase):
                 fused = c2.fuse_bn_bwd(c1, bn1, True, drop)
                 c2.run_bwd(fused_key=key if fused else None)
                 self._stage_bwd(c1, bn1, [c2.dx_source()], True, drop, key, fused=fused)
+            if i >= 1 and self.nb >= 2:
+                self.reduce_bucket("tail" if i == self.nb - 1 else "b%d" % i)
         b0 = self.blocks[0]["c1"]
         for s in range(3):
             st = self.stem[s]
@@ -669,6 +705,7 @@ class GeneratorEngine(EngineBase):
                             trunk=self.dtrunk if s == 0 else None)
             self._stage_bwd(st["d1"], st["bn1"], [st["d2"].dx_source()], True, False, 0)
             self._stage_bwd(st["c7"], st["bn7"], [st["d1"].dx_source()], True, False, 0, want_dx=False)
+        self.reduce_bucket("head")
         self.end_wgrad()
 
 

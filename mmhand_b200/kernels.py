@@ -143,11 +143,6 @@ class Ops:
         self._run(self.lib.mmh_stream_wait_event, (side, ev))
         self.launches -= 2
 
-    def wait_event(self, ev):
-        """The current launch stream waits for an event recorded elsewhere (e.g. by set_input's copy stream)."""
-        self._run(self.lib.mmh_stream_wait_event, (self.st(), ev))
-        self.launches -= 1
-
     def join(self, which=0):
         """The main stream waits for everything launched on side stream ``which`` so far."""
         side = C.c_void_p(self._sides[which].cuda_stream)
@@ -500,6 +495,16 @@ class Ops:
     def image_pack_bgr8(self, src, dst):
         n, _, H, W = src.shape
         self._run(self.lib.mmh_image_pack_bgr8, (_p(src), n, H, W, _p(dst), self.st()), keep=(src, dst))
+
+    def image_unpack_u8(self, src, dst, swap_rb=False):
+        n, H, W, _ = src.shape
+        self._run(self.lib.mmh_image_unpack_u8, (_p(src), n, H, W, 1 if swap_rb else 0, _p(dst), self.st()),
+                  keep=(src, dst))
+
+    def depth_unpack_u8(self, src, dst, hi=1, lo=2, div=700.0):
+        n, H, W, _ = src.shape
+        self._run(self.lib.mmh_depth_unpack_u8, (_p(src), n, H, W, hi, lo, float(div), _p(dst), self.st()),
+                  keep=(src, dst))
 
     def jointsmap(self, uv, depth, H, W, out_f64, out_u8):
         n = uv.numel() // 42

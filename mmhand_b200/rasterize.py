@@ -19,7 +19,7 @@ def get_heatmaps(uv_coords, shape=(256, 256), sigma=SIGMA, thresh=THRESH, out=No
     H, W = int(shape[0]), int(shape[1])
     uv = torch.as_tensor(uv_coords)
     ops = runtime.get_ops(device if device is not None else (uv.device if uv.is_cuda else None))
-    uv = uv.to(ops.device, torch.float64).contiguous()
+    uv = uv.to(ops.device, torch.float64, non_blocking=True).contiguous()
     lead = tuple(uv.shape[:-1])
     if out is None:
         out = torch.empty(lead + (H, W), dtype=torch.float32, device=ops.device)

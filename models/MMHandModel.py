@@ -30,9 +30,6 @@ from .Generator import Generator
 from .network_utils import GANLoss, get_norm_layer, get_scheduler, init_weights, print_network
 
 
-# set_input copies on a copy stream with per-tensor events (see set_input). Off by default: written after this round's GPU
-# budget was spent, so it has only been exercised on the host emulation -- enable with MMH_ASYNC_INPUT=1.
-ASYNC_INPUT = os.environ.get("MMH_ASYNC_INPUT", "0") != "0"
 
 
 class MMHandModel(BaseModel):
@@ -133,56 +130,64 @@ class MMHandModel(BaseModel):
     # ------------------------------------------------------------------------------------------ data
     def set_input(self, input):
         """H2D of the six tensors (reference :200-213) straight into static device buffers, so that the recorded
-        launch tapes (fixed pointers) stay valid from step to step."""
+        launch tapes (fixed pointers) stay valid from step to step.
+
+        Besides the reference's fp32 tensors ('H1', 'P1', 'D1', 'H2', 'P2', 'D2': [B, C, H, W]) each input may arrive
+        in the compact form of the device-side input pipeline (mmhand_b200/loader.py), in which case the
+        arithmetic of the reference's dataset workers (data/generic_dataset.py:133-159) runs on the GPU, bit-identically:
+          'P1_uv' / 'P2_uv'  [B, 21, 2] keypoints (x, y) -> 21 Gaussian heatmaps (mmh_heatmap_rasterize, sigma 6):
+                             336 bytes per pose cross the bus instead of 5.5 MB;
+          'H1_u8' / 'H2_u8'  [B, H, W, 3] uint8 frames (RGB; BGR as cv2.imread returns them with input['u8_bgr'])
+                             -> ((x / 255) - 0.5) / 0.5 (mmh_image_unpack_u8);
+          'D1_u8' / 'D2_u8'  [B, H, W, 3] uint8 depth frames as cv2.imread returns them -> (256*G + R) / 700 mapped to
+                             [-1, 1], three equal channels (mmh_depth_unpack_u8)."""
         dev = self.device
         names = ('H1', 'P1', 'D1', 'H2', 'P2', 'D2')
-        # Device-side pose maps (SURVEY N2, opt-in): 'P1_uv' / 'P2_uv' ([B, 21, 2] keypoints, x then y) may replace
-        # 'P1' / 'P2'; the heatmaps are then rasterised on the device (mmh_heatmap_rasterize: the arithmetic of
-        # Genericdataset.get_heatmaps, sigma 6) straight into the step's input buffers -- 336 bytes per pose cross
-        # the bus instead of 5.5 MB.
-        uv = {k: input[k + '_uv'] for k in ('P1', 'P2') if k not in input and (k + '_uv') in input}
-        if uv:
-            input = dict(input)
-            hw = tuple(input['H1'].shape[2:])
-            for k, v in uv.items():
-                input[k] = torch.empty((v.shape[0], v.shape[1]) + hw, dtype=torch.float32, device='meta')
-        shapes = tuple(tuple(input[k].shape) for k in names)
+        src = {}
+        for k in names:
+            if k in input:
+                src[k] = ('f32', input[k])
+            elif k[0] == 'P' and (k + '_uv') in input:
+                src[k] = ('uv', input[k + '_uv'])
+            elif k[0] != 'P' and (k + '_u8') in input:
+                src[k] = ('u8', input[k + '_u8'])
+            else:
+                raise KeyError("set_input: no '%s' (nor its compact form) in the batch" % k)
+        kind, t = src['H1']
+        B, H, W = (t.shape[0], t.shape[2], t.shape[3]) if kind == 'f32' else (t.shape[0], t.shape[1], t.shape[2])
+
+        def shape_of(k):
+            kind, t = src[k]
+            if kind == 'f32':
+                return tuple(t.shape)
+            return (B, t.shape[1] if kind == 'uv' else 3, H, W)
+
+        shapes = tuple(shape_of(k) for k in names)
         if getattr(self, '_in_shapes', None) != shapes:
-            self._in = {k: torch.empty(input[k].shape, dtype=torch.float32, device=dev) for k in names}
+            self._in = {k: torch.empty(sh, dtype=torch.float32, device=dev) for k, sh in zip(names, shapes)}
+            self._in_stage = {}
             self._in_shapes = shapes
             self._tapes = None
-        if dev.type == 'cuda' and getattr(self, 'async_input', ASYNC_INPUT):
-            # Copies go to a copy stream in the order the step consumes them (image and depth stems first, the 42 pose
-            # channels = 78 % of the bytes next, the target last), one event per tensor; the recorded step waits for
-            # each tensor where it is first read, so the generator's first stems run under the pose-map copy.
+        for k in names:
+            if src[k][0] == 'f32':
+                self._in[k].copy_(src[k][1], non_blocking=True)
+        compact = [k for k in names if src[k][0] != 'f32']
+        if compact:
             ops = runtime.get_ops(dev)
-            main = torch.cuda.current_stream(dev)
-            if getattr(self, '_copy_stream', None) is None:
-                import ctypes
-                self._copy_stream = torch.cuda.Stream(dev)
-                self._in_ev = {}
-                for k in names:
-                    e = ctypes.c_void_p()
-                    if ops.lib.mmh_event_create(ctypes.byref(e)) != 0:
-                        raise RuntimeError(ops.lib.mmh_last_error().decode())
-                    self._in_ev[k] = e
-            cs = self._copy_stream
-            cs.wait_stream(main)              # the previous step is done with the buffers; sources are ready
-            with torch.cuda.stream(cs):
-                for k in ('H1', 'D1', 'D2', 'P1', 'P2', 'H2'):
-                    if k not in uv:
-                        self._in[k].copy_(input[k], non_blocking=True)
-                    ops.lib.mmh_event_record(self._in_ev[k], cs.cuda_stream)
-            self._in_async = True
-        else:
-            for k in names:
-                if k not in uv:
-                    self._in[k].copy_(input[k], non_blocking=True)
-            self._in_async = False
-        if uv:
             from mmhand_b200.rasterize import get_heatmaps
-            for k, v in uv.items():
-                get_heatmaps(v, self._in[k].shape[2:], sigma=float(input.get('sigma', 6.0)), out=self._in[k], device=dev)
+            for k in compact:
+                kind, t = src[k]
+                if kind == 'uv':
+                    get_heatmaps(t, (H, W), sigma=float(input.get('sigma', 6.0)), out=self._in[k], device=dev)
+                    continue
+                st = self._in_stage.get(k)
+                if st is None or st.shape != t.shape:
+                    st = self._in_stage[k] = torch.empty(tuple(t.shape), dtype=torch.uint8, device=dev)
+                st.copy_(t, non_blocking=True)
+                if k[0] == 'H':
+                    ops.image_unpack_u8(st, self._in[k], swap_rb=bool(input.get('u8_bgr', False)))
+                else:
+                    ops.depth_unpack_u8(st, self._in[k], hi=1, lo=2, div=float(input.get('depth_div', 700.0)))
         self.input_H1, self.input_P1, self.input_D1 = self._in['H1'], self._in['P1'], self._in['D1']
         self.input_H2, self.input_P2, self.input_D2 = self._in['H2'], self._in['P2'], self._in['D2']
         if 'H1_path' in input:
@@ -190,19 +195,7 @@ class MMHandModel(BaseModel):
 
     def _g_engine(self):
         B, _, H, W = self.input_H1.shape
-        eng = self.netG.engine(B, H, W, self.world)
-        ev = getattr(self, '_in_ev', None)
-        # stem -> events of the input tensors it reads (set_input's copy stream)
-        eng.input_events = {0: (ev['H1'],), 1: (ev['P1'], ev['P2']), 2: (ev['D1'], ev['D2'])} if ev else {}
-        return eng
-
-    def _wait_input(self, *names):
-        """The current stream waits for set_input's copies of the named tensors (recorded on tapes like a launch)."""
-        ev = getattr(self, '_in_ev', None)
-        if ev:
-            ops = runtime.get_ops(self.device)
-            for k in names:
-                ops.wait_event(ev[k])
+        return self.netG.engine(B, H, W, self.world)
 
     def forward(self):
         eng = self._g_engine()
@@ -233,13 +226,18 @@ class MMHandModel(BaseModel):
         scale = 1.0
         if self.world is not None and self.world.size > 1:
             stream = ops.in_side                     # NCCL follows torch's current stream
+            # bucketed engines summed their convolution weight gradients over the ranks during backward: what is left is
+            # the small leading region of the flat gradient (BatchNorm scales / shifts, biases)
+            grad = eng.store.grad[:eng.store.n_small] if eng.bucketed() else eng.store.grad
+            self.grad_sync_mode = "bucketed (%d buckets during G backward) + per-network" % len(eng.buckets) \
+                if eng.bucketed() else getattr(self, "grad_sync_mode", "per-network after backward")
 
             def all_reduce():
                 if stream is None:
-                    self.world.all_reduce(eng.store.grad)
+                    self.world.all_reduce(grad)
                 else:
                     with torch.cuda.stream(stream):
-                        self.world.all_reduce(eng.store.grad)
+                        self.world.all_reduce(grad)
             ops.host(all_reduce)
             scale = 1.0 / self.world.size
         eng.store.adam(lambda: self._lr(optimizer), self.opt.beta1, 0.999, 1e-8, grad_scale=scale)
@@ -261,7 +259,6 @@ class MMHandModel(BaseModel):
             ops.input_grad_nchw(src, None, dfake, B, C3, H, W, True)
         n = fake.numel()
         crit = self.criterionL1
-        self._wait_input('H2')
         ops.l1(fake, self.input_H2, opt.lambda_A / n, opt.lambda_A / n, acc[2:3], dfake)
         crit.vgg_engine(B, H, W).loss_and_backward(fake, self.input_H2, opt.lambda_B, opt.percep_is_l1 != 1, acc[3:4],
                                                    dfake)
@@ -427,7 +424,6 @@ class MMHandModel(BaseModel):
 
     def get_current_visuals(self):
         import util.util as util
-        self._wait_input('H1', 'P1', 'D1', 'H2', 'P2', 'D2')
         height, width = self.input_H1.size(2), self.input_H1.size(3)
         panels = [util.tensor2im(self.input_H1.data), util.draw_pose_from_map(self.input_P1.data),
                   util.tensor2im(self.input_D1.data), util.tensor2im(self.input_H2.data),

@@ -41,3 +41,23 @@ def get_heatmaps_batch(uv, shape=(256, 256), sigma=6.0, thresh=0.0099):
     m[m > 1] = 1
     m[m < thresh] = 0
     return m.astype(np.float32)
+
+
+def normalize_image_u8(img_u8, bgr=False):
+    """uint8 frames [..., H, W, 3] -> float32 [..., 3, H, W] in [-1, 1]: cv2.cvtColor(BGR2RGB) (a channel flip),
+    ``normalize`` in float64 and ``make_tensor``'s ``.float()`` of data/generic_dataset.py:140-143,182-189."""
+    img = np.asarray(img_u8)
+    if bgr:
+        img = img[..., ::-1]
+    out = ((img / 255.0) - 0.5) / 0.5                                     # float64
+    return np.ascontiguousarray(np.moveaxis(out, -1, -3)).astype(np.float32)
+
+
+def decode_depth_u8(depth_u8, div=700.0):
+    """uint8 depth frames [..., H, W, 3] as cv2.imread returns them (BGR) -> float32 [..., 3, H, W]:
+    ``256.0 * px[1] + px[2]``, stacked x3, ``((d / 700.0) - 0.5) / 0.5`` in float64 (data/generic_dataset.py:148-159),
+    then the fp32 copy set_input makes."""
+    d = np.asarray(depth_u8)
+    depth = 256.0 * d[..., 1] + d[..., 2]                                 # float64
+    out = ((np.stack([depth, depth, depth], axis=-3) / div) - 0.5) / 0.5
+    return out.astype(np.float32)

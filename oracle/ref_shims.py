@@ -73,6 +73,21 @@ def load_reference_dataset_module():
     return gd
 
 
+def load_reference_dataset_classes():
+    """(RHDdataset, STBdataset, MMHandDatasetDataLoader) of the reference (data/rhd_dataset.py, data/stb_dataset.py,
+    data/mmhand_dataset_data_loader.py), importable here with the shims of load_reference_dataset_module plus
+    ``np.bool`` (removed in numpy 1.24; generic_dataset.py:111 uses it)."""
+    import numpy as np
+    load_reference_dataset_module()
+    if not hasattr(np, "bool"):
+        np.bool = bool
+    with _RefImport():
+        rhd = importlib.import_module("data.rhd_dataset")
+        stb = importlib.import_module("data.stb_dataset")
+        ldr = importlib.import_module("data.mmhand_dataset_data_loader")
+    return rhd.RHDdataset, stb.STBdataset, ldr.MMHandDatasetDataLoader
+
+
 def load_reference_model_class():
     """models.MMHandModel.MMHandModel of the reference, importable on CPU."""
     import torch

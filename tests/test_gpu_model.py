@@ -207,13 +207,17 @@ def test_train_losses_match_oracle(steps, B, S):
         m.optimize_parameters()
         mine.append({k: float(v) for k, v in m.get_current_errors().items()})
     random.seed(7)
-    worst, per_step = 0.0, {}
+    worst, per_step, per_key = 0.0, {}, {}
     for i, b in enumerate(batches):
         ref = tr.step(b["H1"], b["P1"], b["D1"], b["H2"], b["P2"], b["D2"])
         for k in ref:
             rel = abs(mine[i][k] - ref[k]) / max(abs(ref[k]), 1e-6)
             worst = max(worst, rel)
             per_step[i] = max(per_step.get(i, 0.0), rel)
+            per_key[k] = max(per_key.get(k, 0.0), rel)
+        if i < 3:
+            print("step %d mine/oracle:" % i, {k: "%.4f/%.4f" % (mine[i][k], ref[k]) for k in ref})
+    print("worst relative deviation per loss:", {k: "%.4f" % v for k, v in per_key.items()})
     print("per-step worst relative loss deviation:", ["%.4f" % per_step[i] for i in range(steps)])
     print("worst relative loss deviation over %d steps: %.3g" % (steps, worst))
     _note(**{"loss_rel_dev_B%d_%dsteps" % (B, steps): worst,
@@ -226,44 +230,50 @@ def test_train_losses_match_oracle(steps, B, S):
     print("last step:", mine[-1])
 
 
-def test_set_input_keypoints_and_async_copies():
-    """SURVEY N2 on the GPU: (1) 'P1_uv' / 'P2_uv' keypoints rasterised on the device give bit-identical pose maps to
-    feeding the maps (mmh_heatmap_rasterize == the oracle's get_heatmaps); (2) the copy-stream input path (per-tensor
-    events, pose stem last) takes the same steps as the plain one."""
+def test_set_input_compact_forms():
+    """SURVEY N2 on the GPU: 'P*_uv' keypoints, 'H*_u8' colour frames and 'D*_u8' depth frames are turned into the
+    reference's input tensors on the device, bit-identically to the oracle's restatement of the dataset arithmetic
+    (oracle/raster_ref.py), and the training steps are those of the fp32-fed model."""
     from models.MMHandModel import MMHandModel
-    from oracle.raster_ref import get_heatmaps_batch
+    from oracle.raster_ref import decode_depth_u8, get_heatmaps_batch, normalize_image_u8
     from oracle.ref_shims import make_opt
     rng = np.random.RandomState(3)
     B, S = 2, 256
     steps = []
     for it in range(3):
         uv1, uv2 = rng.uniform(8, S - 8, size=(B, 21, 2)), rng.uniform(8, S - 8, size=(B, 21, 2))
-        g = torch.Generator().manual_seed(90 + it)
-        r = lambda *s: torch.rand(*s, generator=g)
-        base = dict(H1=r(B, 3, S, S) * 2 - 1, D1=r(B, 3, S, S) * 2 - 1, H2=r(B, 3, S, S) * 2 - 1, D2=r(B, 3, S, S) * 2 - 1)
-        maps = dict(base, P1=torch.from_numpy(get_heatmaps_batch(uv1, (S, S))),
+        u8 = {k: rng.randint(0, 256, size=(B, S, S, 3)).astype(np.uint8) for k in ("H1", "H2", "D1", "D2")}
+        for k in ("D1", "D2"):
+            u8[k][..., 1] = rng.randint(0, 3, size=(B, S, S))             # depth = 256 * G + R in [0, 768)
+        maps = dict(H1=torch.from_numpy(normalize_image_u8(u8["H1"], bgr=True)),
+                    H2=torch.from_numpy(normalize_image_u8(u8["H2"], bgr=True)),
+                    D1=torch.from_numpy(decode_depth_u8(u8["D1"])), D2=torch.from_numpy(decode_depth_u8(u8["D2"])),
+                    P1=torch.from_numpy(get_heatmaps_batch(uv1, (S, S))),
                     P2=torch.from_numpy(get_heatmaps_batch(uv2, (S, S))))
-        keys = dict(base, P1_uv=torch.from_numpy(uv1), P2_uv=torch.from_numpy(uv2))
+        keys = dict(H1_u8=torch.from_numpy(u8["H1"]), H2_u8=torch.from_numpy(u8["H2"]), D1_u8=torch.from_numpy(u8["D1"]),
+                    D2_u8=torch.from_numpy(u8["D2"]), P1_uv=torch.from_numpy(uv1), P2_uv=torch.from_numpy(uv2),
+                    u8_bgr=True)
         steps.append((maps, keys))
     runs = {}
-    for name, feed, async_in in (("maps", 0, False), ("uv", 1, False), ("uv_async", 1, True), ("maps_async", 0, True)):
+    for name, feed in (("maps", 0), ("compact", 1), ("compact_pinned", 1)):
         torch.manual_seed(4)
         random.seed(4)
         m = MMHandModel(make_opt(batchSize=B, fineSize=S, pool_size=0, local_rank=0, gpu=0, seed=3))
         m.master = False
-        m.async_input = async_in
         errs = []
         for st in steps:
-            src = {k: (v.pin_memory() if async_in else v) for k, v in st[feed].items()}
+            src = {k: (v.pin_memory() if (name.endswith("pinned") and isinstance(v, torch.Tensor)) else v)
+                   for k, v in st[feed].items()}
             m.set_input(src)
             torch.cuda.synchronize()
-            assert torch.equal(m.input_P1.cpu(), st[0]["P1"]) and torch.equal(m.input_P2.cpu(), st[0]["P2"]), name
+            for k in ("H1", "H2", "D1", "D2", "P1", "P2"):
+                assert torch.equal(getattr(m, "input_" + k).cpu(), st[0][k].float()), (name, k)
             m.optimize_parameters()
             errs.append({k: float(v) for k, v in m.get_current_errors().items()})
         runs[name] = errs
         del m
         torch.cuda.empty_cache()
-    for name in ("uv", "uv_async", "maps_async"):
+    for name in ("compact", "compact_pinned"):
         for a, b in zip(runs["maps"], runs[name]):
             for k in a:
                 # identical inputs and launch sequence; fp32 atomics order inside the reduction kernels is the only

@@ -344,34 +344,6 @@ def test_checkpoint_files_and_continue_train(emu_f32, tmp_path, monkeypatch):
     assert torch.equal(m.fake_p2, m2.fake_p2)
 
 
-def test_stem_order_with_input_events_is_equivalent(emu_f32):
-    """MMH_ASYNC_INPUT path (host logic): with per-tensor copy events the generator waits on them and runs the pose
-    stem last; image, gradients and running statistics are those of the default order."""
-    import ctypes
-    torch.manual_seed(12)
-    g1, g2 = _gen(), _gen()
-    g2.load_state_dict(g1.state_dict())
-    x = _x(seed=13)
-    gy = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(14))
-    outs = []
-    for g, with_events in ((g1, False), (g2, True)):
-        g.train()
-        if with_events:
-            eng = g.engine(2, 32, 32)
-            ev = ctypes.c_void_p()
-            assert eng.ops.lib.mmh_event_create(ctypes.byref(ev)) == 0
-            eng.input_events = {0: (ev,), 1: (ev, ev), 2: (ev, ev)}
-        y = g(x)
-        y.backward(gy)
-        outs.append((y.detach().clone(), {k: p.grad.clone() for k, p in g.named_parameters()},
-                     {k: v.clone() for k, v in g.state_dict().items() if "running" in k}))
-    assert torch.equal(outs[0][0], outs[1][0])
-    for k in outs[0][1]:
-        assert torch.equal(outs[0][1][k], outs[1][1][k]), k
-    for k in outs[0][2]:
-        assert torch.equal(outs[0][2][k], outs[1][2][k]), k
-
-
 def test_batch_size_change_keeps_the_optimiser_state(emu_f32):
     """the reference's DataLoader has no drop_last, so the last batch of an epoch is smaller. The
     engines are rebuilt for the new shape, but Adam's moments and step count must survive (they live on the module's
