@@ -121,9 +121,10 @@ class DeviceInputLoader():
         if getattr(opt, 'distributed', False):
             self.distributed_sampler = torch.utils.data.distributed.DistributedSampler(self.dataset)
             init_fn = lambda w_id: np.random.seed(seed)
+        collate = self._collate if isinstance(self.dataset, CompactHandDataset) else None
         self.dataloader = DataLoader(self.dataset, batch_size=opt.batchSize, shuffle=False, pin_memory=True,
                                      sampler=self.distributed_sampler, worker_init_fn=init_fn,
-                                     num_workers=int(getattr(opt, 'nThreads', 0)), collate_fn=self._collate)
+                                     num_workers=int(getattr(opt, 'nThreads', 0)), collate_fn=collate)
 
     @staticmethod
     def _collate(items):
