@@ -202,12 +202,12 @@ __device__ __forceinline__ void bs_load_x(const __nv_bfloat16* xrow_n0, bool in_
 
 // xa / xa2: chunks 0-1 / 2-3 of the row, loaded by the caller BEFORE it waited for the accumulators
 __device__ __forceinline__ void epilogue_row_bwd(const Conv2Params& p, uint32_t t_addr, int nchunks, int n0,
-                                                 int64_t orow, bool in_range, const __nv_bfloat16* xrow,
+                                                 int64_t orow, bool in_range, bool ld_x, const __nv_bfloat16* xrow,
                                                  uint32_t hash_word0, float* s_stats, const float4* s_par,
                                                  uint4 (&xa)[4], uint4 (&xa2)[4]) {
   const int lane = threadIdx.x & 31;
   uint4 xb[4], xb2[4];
-  auto load_x = [&](int j, uint4 (&x)[4]) { bs_load_x(xrow + n0, in_range, j, nchunks, x); };
+  auto load_x = [&](int j, uint4 (&x)[4]) { bs_load_x(xrow + n0, ld_x, j, nchunks, x); };
   auto emit = [&](const uint32_t (&v)[16], const uint4& xa, const uint4& xb, int j) {
     const int nc = n0 + j * 16;
     const uint32_t xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
@@ -523,7 +523,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (tile >= n_tiles) return;
       int64_t xrow, orow; uint32_t w0; bool in_range;
       bs_row(tile, xrow, w0, in_range, orow);
-      if (!in_range) return;
+      if (!in_range || (p.dbg & 16)) return;
       const int tn = tile % p.tiles_n;
       const char* base = reinterpret_cast<const char*>(p.bs_x) + (xrow * p.bs_x_ld + tn * p.BN) * 2;
       for (int b = 0; b < p.BN * 2; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + b));
@@ -538,12 +538,13 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         bs_prefetch(tile + tile_step);                  // the next tile's rows travel to L2 under this tile's work
         const __nv_bfloat16* xr = static_cast<const __nv_bfloat16*>(p.bs_x) + xrow * p.bs_x_ld;
         uint4 xa[4], xa2[4];                            // first 64 channels: in flight while the main loop finishes
-        bs_load_x(xr + n0, in_range, 0, nchunks, xa);
-        bs_load_x(xr + n0, in_range, 2, nchunks, xa2);
+        const bool ld_x = in_range && !(p.dbg & 16);    // MMH_C2_DEBUG=16: no loads of x (timing experiments only)
+        bs_load_x(xr + n0, ld_x, 0, nchunks, xa);
+        bs_load_x(xr + n0, ld_x, 2, nchunks, xa2);
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + acc * kC2AccStride + (static_cast<uint32_t>(quad * 32) << 16);
-        epilogue_row_bwd(p, t_addr, nchunks, n0, orow, in_range, xr, w0, s_stats, s_par + n0, xa, xa2);
+        epilogue_row_bwd(p, t_addr, nchunks, n0, orow, in_range, ld_x, xr, w0, s_stats, s_par + n0, xa, xa2);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {

@@ -198,6 +198,11 @@ class Ops:
     # caching allocator when the last buffer carved from it dies (views keep their storage alive).
     ARENA_CHUNK = 256 << 20
     ARENA_ALIGN = 1024               # TMA base addresses need 128 B; 1 KB keeps swizzle atoms aligned too
+    # debugging aids: MMH_ARENA=0 gives every buffer its own torch allocation; MMH_ARENA_GUARD=<bytes> leaves a zero
+    # gap behind every carved buffer, and Ops.check_guards() reports the buffers whose gap was written to
+    import os as _os
+    ARENA_ON = _os.environ.get("MMH_ARENA", "1") != "0"
+    ARENA_GUARD = int(_os.environ.get("MMH_ARENA_GUARD", "0"))
 
     def zeros(self, *shape, dtype=None):
         dtype = dtype or self.act_dtype
@@ -207,16 +212,33 @@ class Ops:
         for d in shape:
             n *= int(d)
         nbytes = n * torch.empty((), dtype=dtype).element_size()
-        if nbytes == 0 or nbytes > self.ARENA_CHUNK // 2:
+        if nbytes == 0 or nbytes > self.ARENA_CHUNK // 2 or not self.ARENA_ON:
             return torch.zeros(*shape, dtype=dtype, device=self.device)
-        need = (nbytes + self.ARENA_ALIGN - 1) // self.ARENA_ALIGN * self.ARENA_ALIGN
+        need = (nbytes + self.ARENA_GUARD + self.ARENA_ALIGN - 1) // self.ARENA_ALIGN * self.ARENA_ALIGN
         chunk = getattr(self, "_arena", None)
         if chunk is None or self._arena_off + need > chunk.numel():
             chunk = self._arena = torch.zeros(self.ARENA_CHUNK, dtype=torch.uint8, device=self.device)
             self._arena_off = (-chunk.data_ptr()) % self.ARENA_ALIGN
         off = self._arena_off
         self._arena_off = off + need
+        if self.ARENA_GUARD:
+            import traceback
+            who = [f for f in traceback.extract_stack(limit=6) if "kernels.py" not in f.filename]
+            self.__dict__.setdefault("_guards", []).append(
+                (chunk, off + nbytes, off + need, tuple(shape), str(dtype),
+                 " <- ".join("%s:%d" % (f.filename.split("/")[-1], f.lineno) for f in reversed(who[-3:]))))
         return chunk[off:off + nbytes].view(dtype).view(*shape)
+
+    def check_guards(self):
+        """MMH_ARENA_GUARD debugging: the buffers whose trailing gap is no longer zero (out-of-bounds writes)."""
+        bad = []
+        for chunk, lo, hi, shape, dtype, who in getattr(self, "_guards", []):
+            g = chunk[lo:hi]
+            if bool(g.any()):
+                nz = g.nonzero().flatten()
+                bad.append("buffer %s %s (%s): %d dirty guard bytes, first at +%d, last at +%d" % (
+                    shape, dtype, who, nz.numel(), int(nz[0]), int(nz[-1])))
+        return bad
 
     def empty(self, *shape, dtype=None):
         dtype = dtype or self.act_dtype

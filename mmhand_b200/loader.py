@@ -35,6 +35,31 @@ def compact_from_reference(batch):
     return out
 
 
+class CompactBatch(dict):
+    """A compact batch that still answers the reference's keys: ``batch['P1']``, ``['H1']``, ``['D1']`` ... are computed
+    on first access -- on the GPU, by the kernels ``MMHandModel.set_input`` uses -- so that callers written against the
+    reference's loader (``aug.py:43-47`` indexes the six tensors directly) run unchanged. ``'P1' in batch`` stays False:
+    ``set_input`` sees the compact form and never materialises the fp32 tensors on the host side."""
+
+    def __missing__(self, key):
+        from . import runtime
+        from .rasterize import get_heatmaps
+        if key in ('P1', 'P2') and (key + '_uv') in self:
+            ref = self['H1_u8'] if 'H1_u8' in self else self['H1']
+            hw = tuple(ref.shape[1:3]) if ref.dtype == torch.uint8 else tuple(ref.shape[2:])
+            return get_heatmaps(self[key + '_uv'], hw, sigma=float(self.get('sigma', 6.0)))
+        if key in ('H1', 'H2', 'D1', 'D2') and (key + '_u8') in self:
+            ops = runtime.get_ops(None)
+            src = self[key + '_u8'].to(ops.device, non_blocking=True)
+            out = torch.empty(src.shape[0], 3, src.shape[1], src.shape[2], dtype=torch.float32, device=ops.device)
+            if key[0] == 'H':
+                ops.image_unpack_u8(src, out, swap_rb=bool(self.get('u8_bgr', False)))
+            else:
+                ops.depth_unpack_u8(src, out, hi=1, lo=2, div=float(self.get('depth_div', 700.0)))
+            return out
+        raise KeyError(key)
+
+
 class CompactHandDataset(Dataset):
     """opt: dataroot, dataset ('rhd' | 'stb'), augmentation_ratio, isTrain -- the options the reference's datasets read."""
 
@@ -128,7 +153,7 @@ class DeviceInputLoader():
 
     @staticmethod
     def _collate(items):
-        out = {}
+        out = CompactBatch()
         for k in items[0]:
             v = [it[k] for it in items]
             if isinstance(v[0], torch.Tensor):

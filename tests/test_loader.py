@@ -77,6 +77,15 @@ def test_compact_batches_equal_the_reference_loader(data_dir, emu):
             assert torch.equal(a, getattr(m_mine, k)), k
             assert torch.equal(a, getattr(m_c, k)), k
         assert torch.equal(rb['C1'], cb['C1']) and torch.equal(rb['C2'], cb['C2'])
+        # callers that index the reference's keys (aug.py:43-47) get them computed on demand, bit-identically
+        assert 'P1' not in cb and 'H1' not in cb
+        for k in ('H1', 'H2', 'D1', 'D2', 'P1', 'P2'):
+            assert torch.equal(cb[k].cpu(), rb[k].float()), k
+        # and the oracle's restatement of the dataset arithmetic (used by the GPU tests, where the reference tree is
+        # absent) is the reference's
+        from oracle.raster_ref import decode_depth_u8, normalize_image_u8
+        assert torch.equal(torch.from_numpy(normalize_image_u8(cb['H1_u8'].numpy(), bgr=True)), rb['H1'])
+        assert torch.equal(torch.from_numpy(decode_depth_u8(cb['D2_u8'].numpy())), rb['D2'].float())
         n += 1
     assert n == 2
     bytes_ref = sum(v.numel() * v.element_size() for v in rb.values() if isinstance(v, torch.Tensor))
