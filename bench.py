@@ -281,10 +281,11 @@ def run_ours(a):
     model.use_tape = False
     ops.conv_hook = hook
     side, ops.side_stream = ops.side_stream, None      # serial launches: a kernel's events bracket that kernel alone
+    chains, ops.chains = ops.chains, [None]
     model.set_input(dev[0])
     model.optimize_parameters()
     torch.cuda.synchronize()
-    ops.side_stream = side
+    ops.side_stream, ops.chains = side, chains
     ops.conv_hook = None
     model.use_tape = True
     peaks = {}
@@ -328,6 +329,7 @@ def run_ours(a):
                    "pdl": os.environ.get("MMH_PDL", "1") != "0",
                    "grad_allreduce": getattr(model, "grad_sync_mode", "none") if world > 1 else "none",
                    "bn_bwd_in_dgrad_epilogue": os.environ.get("MMH_FUSE_BN_BWD", "1") != "0",
+                   "layer_chain_streams": len(ops.chains),
                    "e2e_feed": "uint8 frames + float64 keypoints from pinned host memory (mmhand_b200/loader.py form); "
                                "heatmaps rasterised and frames normalised on the device inside set_input"},
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 6 * 4,

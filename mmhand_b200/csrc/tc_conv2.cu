@@ -740,7 +740,13 @@ int mmh_conv2_create(const MmhConvDesc* d, MmhConv2** out_plan) {
   batch = env_int("MMH_CONV_BBATCH", batch);
   k.b_batch = batch;
   k.b_slot_bytes = k.b_batch * k.b_tile_stride;
-  const uint32_t budget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/ - stat_bytes;
+  // MMH_CONV_SMEM_KB (default 227 = everything): a smaller cap leaves shared memory for the reduction kernels of another
+  // layer chain to be co-resident with a convolution CTA (engine.py: chains on their own CUDA streams)
+  static const uint32_t cap_kb = [] {
+    const int v = env_int("MMH_CONV_SMEM_KB", 227);
+    return static_cast<uint32_t>(v < 96 ? 96 : (v > 227 ? 227 : v));
+  }();
+  const uint32_t budget = cap_kb * 1024 - 1024 /*align*/ - 512 /*barriers*/ - stat_bytes;
   k.nA = env_int("MMH_CONV_NA", k.a_slot_bytes <= 8192 ? 8 : (k.a_slot_bytes <= 20480 ? 4 : 2));
   if (k.nA > kC2MaxA) k.nA = kC2MaxA;
   if (k.nA * k.a_slot_bytes + 2 * k.b_slot_bytes > budget) { set_error("conv tile does not fit in shared memory"); return fail(); }

@@ -83,15 +83,19 @@ class ParamStore:
             p.grad = grad[off:off + n].view(p.shape)
             off += n
         self.flat, self.grad = flat, grad
+        # Adam moments: allocated (and zero-filled, on the stream current NOW) together with the parameters. They used to
+        # be created lazily inside the first adam() call -- which for the generator runs on the update side stream,
+        # while torch's zero-fill went to the main stream: the first update could read the moments before they were
+        # zeroed (harmless on fresh device memory, NaN / a wrong first step on recycled blocks).
+        if self.m is None or self.m.numel() != total or self.m.device != flat.device:
+            self.m = torch.zeros_like(flat)
+            self.v = torch.zeros_like(flat)
         return True
 
     def zero_grad(self):
         self.ops.memset0(self.grad)
 
     def adam(self, lr, beta1, beta2=0.999, eps=1e-8, grad_scale=1.0):
-        if self.m is None:
-            self.m = torch.zeros_like(self.flat)
-            self.v = torch.zeros_like(self.flat)
         lr_fn = lr if callable(lr) else (lambda: lr)
 
         def bump():
@@ -264,9 +268,10 @@ class ConvL:
 class BNL:
     """BatchNorm2d over a raw conv output (train: batch statistics; eval: running statistics)."""
 
-    def __init__(self, eng, mod, Cc):
+    def __init__(self, eng, mod, Cc, chain=0):
         ops = eng.ops
         self.eng, self.mod, self.C = eng, mod, Cc
+        self.ticket = eng.tickets[chain]         # "last block" counter of the stream this layer's kernels run on
         f = lambda n: ops.zeros(n, dtype=torch.float32)
         self.sums, self.coef, self.save, self.bsums, self.bsums_g, self.k = f(2 * Cc), f(2 * Cc), f(2 * Cc), f(2 * Cc), f(2 * Cc), f(2 * Cc)
 
@@ -282,7 +287,7 @@ class BNL:
             elif eng.fused_stats():
                 # one launch: sums -> (peer exchange) -> coefficients; self.sums returns to zero
                 w = eng.peer_world()
-                ops.bn_stats_finalize(w, raw, rows, ld, self.C, self.sums, eng.ticket, count * (w.size if w else 1),
+                ops.bn_stats_finalize(w, raw, rows, ld, self.C, self.sums, self.ticket, count * (w.size if w else 1),
                                       m.weight, m.bias, m.running_mean, m.running_var, BN_MOM, BN_EPS, self.coef,
                                       self.save)
             else:               # NCCL / gloo groups: statistics, all-reduce, finalise
@@ -303,7 +308,7 @@ class BNL:
         if eng.fused_stats():
             w = eng.peer_world()
             ops.bn_bwd_reduce_finalize(w, dz, dz_f32, relu, dropout, key, x, xl, self.coef, self.save, self.bsums,
-                                       self.k, eng.ticket, count * (w.size if w else 1), dg, db)
+                                       self.k, self.ticket, count * (w.size if w else 1), dg, db)
         else:
             ops.memset0(self.bsums)
             ops.bn_bwd_reduce(dz, dz_f32, relu, dropout, key, x, xl, self.coef, self.save, self.bsums)
@@ -335,7 +340,9 @@ class EngineBase:
         self._scratch = {}
         self.world = world         # None or an object with all_reduce(tensor) and size
         self.store = param_store(ops, module)
-        self.ticket = ops.zeros(1, dtype=torch.int32)    # "last block" ticket of the one-launch statistics kernels
+        # "last block" tickets of the one-launch statistics kernels: one per concurrently running layer chain
+        self.tickets = [ops.zeros(1, dtype=torch.int32) for _ in range(3)]
+        self.ticket = self.tickets[0]
         self.packed_version = None
         self.seed = 0
 
@@ -345,6 +352,22 @@ class EngineBase:
             t = self.ops.zeros(rows, ld, dtype=dtype)
             self._scratch[key] = t
         return t
+
+    def chain(self, s):
+        """Context: the launches of layer chain ``s`` (stream s of a PAT block / stem). Chain 0 stays on the launch
+        stream; chains 1, 2 go to their own CUDA streams when the Ops has them (Ops.chains), so that the bandwidth-bound
+        kernels of one chain run under the tensor-core kernels of another. fork_chains() / join_chains() bracket a
+        group of concurrently running chains."""
+        ch = self.ops.chains
+        return self.ops.side(ch[s] if s < len(ch) else None)
+
+    def fork_chains(self, n=3):
+        for s in range(1, min(n, len(self.ops.chains))):
+            self.ops.fork(self.ops.chains[s])
+
+    def join_chains(self, n=3):
+        for s in range(1, min(n, len(self.ops.chains))):
+            self.ops.join(self.ops.chains[s])
 
     def drop_key(self, layer_id, lay):
         """Dropout key of a layer whose output has layout ``lay``; data parallel: masks are those of the joint batch
@@ -484,7 +507,7 @@ class EngineBase:
             if dz_out_f32 is not None:
                 dz, f32 = dz_out_f32, True
             else:
-                dz, f32 = self.scratch(("dz", B * H * W, Cc), B * H * W, Cc), False
+                dz, f32 = self.scratch(("dz", conv.name, B * H * W, Cc), B * H * W, Cc), False
             ops.grad_gather(srcs, B, H, W, Cc, dz, plain_lay(B, H, W, Cc), f32, trunk=trunk)
         bn.backward(dz, f32, relu, dropout, key, conv.raw, ol, conv.dy, ol, B * H * W, want_wgrad)
         conv.run_bwd(want_wgrad, want_dx)
@@ -514,8 +537,8 @@ class GeneratorEngine(EngineBase):
                        need_dx=False)
             d1 = ConvL(E, "s%d.d1" % s, geom_s2(B, H, W, ngf, 2 * ngf), ngf, 2 * ngf, seq[4].weight)
             d2 = ConvL(E, "s%d.d2" % s, geom_s2(B, H // 2, W // 2, 2 * ngf, dim), 2 * ngf, dim, seq[7].weight)
-            self.stem.append(dict(c7=c7, d1=d1, d2=d2, bn7=BNL(E, seq[2], ngf), bn1=BNL(E, seq[5], 2 * ngf),
-                                  bn2=BNL(E, seq[8], dim)))
+            self.stem.append(dict(c7=c7, d1=d1, d2=d2, bn7=BNL(E, seq[2], ngf, s), bn1=BNL(E, seq[5], 2 * ngf, s),
+                                  bn2=BNL(E, seq[8], dim, s)))
         # --- PAT blocks
         j = 6 if self.use_dropout else 5
         self.blocks = []
@@ -530,7 +553,7 @@ class GeneratorEngine(EngineBase):
                 c2 = ConvL(E, "b%d.s%d.c2" % (i, s), geom_s1(B, h4, w4, 3, 'reflect', cin, dim), cin, dim, seq[j].weight)
                 b["c1"].append(c1)
                 b["c2"].append(c2)
-                b["bn1"].append(BNL(E, seq[2], cin))
+                b["bn1"].append(BNL(E, seq[2], cin, s))
                 if s == 0:
                     b["bn2"] = BNL(E, seq[j + 1], dim)
             self.blocks.append(b)
@@ -559,13 +582,13 @@ class GeneratorEngine(EngineBase):
         if self.bwd_ready:
             return
         for s, st in enumerate(self.stem):
-            st["c7"].prepare_backward("stem7", None)
-            st["d1"].prepare_backward("stemd1", "stemd1")
-            st["d2"].prepare_backward("stemd2", "stemd2")
+            st["c7"].prepare_backward("stem7.s%d" % s, None)          # per stem: the three run concurrently
+            st["d1"].prepare_backward("stemd1.s%d" % s, "stemd1.s%d" % s)
+            st["d2"].prepare_backward("stemd2.s%d" % s, "stemd2.s%d" % s)
         for i, b in enumerate(self.blocks):
             for s in range(3):
-                b["c1"][s].prepare_backward("c1", "c1.s%d" % s)     # dx kept until the previous block's gate backward
-                b["c2"][s].prepare_backward("c2.s%d" % s, "c2")
+                b["c1"][s].prepare_backward("c1.s%d" % s, "c1.s%d" % s)   # dx kept until the previous block's gate backward
+                b["c2"][s].prepare_backward("c2.s%d" % s, "c2.s%d" % s)
         self.up1.prepare_backward("up1", "up1")
         self.up2.prepare_backward("up2", "up2")
         self.cout.prepare_backward("out", "out")
@@ -601,30 +624,38 @@ class GeneratorEngine(EngineBase):
         self.training, self.step, self.net_id = training, step, net_id
         self.ops.step = step
         b0 = self.blocks[0]
+        # the three stems, and the three streams of every PAT block, are independent layer chains: each runs on its own
+        # CUDA stream (chain()), so that the bandwidth-bound kernels of one chain execute under the convolutions of another
+        self.fork_chains()
         for s, (a, b_) in ((0, (x1, None)), (1, (x2a, x2b)), (2, (x3a, x3b))):
-            st = self.stem[s]
-            c7, d1, d2 = st["c7"], st["d1"], st["d2"]
-            ops.assemble(a, b_, c7.x, c7.g.in_lay, 3, 3, True)
-            self._stage_fwd(c7, st["bn7"], training)
-            ops.norm_act(c7.raw, c7.g.out_lay, st["bn7"].coef, True, False, 0, d1.x, d1.g.in_lay, 1, 1, False)
-            self._stage_fwd(d1, st["bn1"], training)
-            ops.norm_act(d1.raw, d1.g.out_lay, st["bn1"].coef, True, False, 0, d2.x, d2.g.in_lay, 1, 1, False)
-            self._stage_fwd(d2, st["bn2"], training)
-            nxt = b0["c1"][s]
-            ops.norm_act(d2.raw, d2.g.out_lay, st["bn2"].coef, True, False, 0, nxt.x, nxt.g.in_lay, 1, 1, True,
-                         dst_f32=self.trunk[0] if s == 0 else None)
+            with self.chain(s):
+                st = self.stem[s]
+                c7, d1, d2 = st["c7"], st["d1"], st["d2"]
+                ops.assemble(a, b_, c7.x, c7.g.in_lay, 3, 3, True)
+                self._stage_fwd(c7, st["bn7"], training)
+                ops.norm_act(c7.raw, c7.g.out_lay, st["bn7"].coef, True, False, 0, d1.x, d1.g.in_lay, 1, 1, False)
+                self._stage_fwd(d1, st["bn1"], training)
+                ops.norm_act(d1.raw, d1.g.out_lay, st["bn1"].coef, True, False, 0, d2.x, d2.g.in_lay, 1, 1, False)
+                self._stage_fwd(d2, st["bn2"], training)
+                nxt = b0["c1"][s]
+                ops.norm_act(d2.raw, d2.g.out_lay, st["bn2"].coef, True, False, 0, nxt.x, nxt.g.in_lay, 1, 1, True,
+                             dst_f32=self.trunk[0] if s == 0 else None)
         cur = 0
         for i, b in enumerate(self.blocks):
+            if i > 0:
+                self.fork_chains()          # (block 0 continues the stems' chains)
             for s in range(3):
-                c1, c2, bn1 = b["c1"][s], b["c2"][s], b["bn1"][s]
-                self._stage_fwd(c1, bn1, training)
-                drop = training and self.use_dropout
-                key = self.drop_key(net_id * 1000 + 3 * i + s, c1.g.out_lay) if drop else 0
-                ops.norm_act(c1.raw, c1.g.out_lay, bn1.coef, True, drop, key, c2.x, c2.g.in_lay, 1, 1, True)
-                fused2 = s == 0 and self.epilogue_stats(c2, b["bn2"], training)
-                c2.run_fwd(stats=fused2)
-                if s == 0:
-                    bn2_fused = fused2
+                with self.chain(s):
+                    c1, c2, bn1 = b["c1"][s], b["c2"][s], b["bn1"][s]
+                    self._stage_fwd(c1, bn1, training)
+                    drop = training and self.use_dropout
+                    key = self.drop_key(net_id * 1000 + 3 * i + s, c1.g.out_lay) if drop else 0
+                    ops.norm_act(c1.raw, c1.g.out_lay, bn1.coef, True, drop, key, c2.x, c2.g.in_lay, 1, 1, True)
+                    fused2 = s == 0 and self.epilogue_stats(c2, b["bn2"], training)
+                    c2.run_fwd(stats=fused2)
+                    if s == 0:
+                        bn2_fused = fused2
+            self.join_chains()
             c2s = b["c2"]
             ol = c2s[0].g.out_lay
             b["bn2"].forward(c2s[0].raw, ol.rows, ol.ld, B * ol.H * ol.W, training, in_epilogue=bn2_fused)
@@ -689,22 +720,28 @@ class GeneratorEngine(EngineBase):
                                   dim)
             ops.gate_bwd_apply(self.dtrunk, c2s[0].raw, c2s[1].raw, c2s[2].raw, ol, bn2.coef, bn2.save, bn2.k, ex2, ex3,
                                c2s[0].dy, c2s[1].dy, c2s[2].dy, ol)
+            self.fork_chains()
             for s in range(3):
-                c1, c2, bn1 = b["c1"][s], b["c2"][s], b["bn1"][s]
-                drop = self.use_dropout
-                key = self.drop_key(net_id * 1000 + 3 * i + s, c1.g.out_lay) if drop else 0
-                fused = c2.fuse_bn_bwd(c1, bn1, True, drop)
-                c2.run_bwd(fused_key=key if fused else None)
-                self._stage_bwd(c1, bn1, [c2.dx_source()], True, drop, key, fused=fused)
+                with self.chain(s):
+                    c1, c2, bn1 = b["c1"][s], b["c2"][s], b["bn1"][s]
+                    drop = self.use_dropout
+                    key = self.drop_key(net_id * 1000 + 3 * i + s, c1.g.out_lay) if drop else 0
+                    fused = c2.fuse_bn_bwd(c1, bn1, True, drop)
+                    c2.run_bwd(fused_key=key if fused else None)
+                    self._stage_bwd(c1, bn1, [c2.dx_source()], True, drop, key, fused=fused)
+            if i >= 1:
+                self.join_chains()          # (block 0's chains run on into the stems)
             if i >= 1 and self.nb >= 2:
                 self.reduce_bucket("tail" if i == self.nb - 1 else "b%d" % i)
         b0 = self.blocks[0]["c1"]
         for s in range(3):
-            st = self.stem[s]
-            self._stage_bwd(st["d2"], st["bn2"], [b0[s].dx_source()], True, False, 0,
-                            trunk=self.dtrunk if s == 0 else None)
-            self._stage_bwd(st["d1"], st["bn1"], [st["d2"].dx_source()], True, False, 0)
-            self._stage_bwd(st["c7"], st["bn7"], [st["d1"].dx_source()], True, False, 0, want_dx=False)
+            with self.chain(s):
+                st = self.stem[s]
+                self._stage_bwd(st["d2"], st["bn2"], [b0[s].dx_source()], True, False, 0,
+                                trunk=self.dtrunk if s == 0 else None)
+                self._stage_bwd(st["d1"], st["bn1"], [st["d2"].dx_source()], True, False, 0)
+                self._stage_bwd(st["c7"], st["bn7"], [st["d1"].dx_source()], True, False, 0, want_dx=False)
+        self.join_chains()
         self.reduce_bucket("head")
         self.end_wgrad()
 

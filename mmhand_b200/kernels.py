@@ -103,6 +103,7 @@ class Ops:
         self.main_stream = None  # optional high-priority stream of the critical path (see Ops.cuda)
         self.in_side = None      # the torch stream launches currently go to, when it is a side stream
         self.side_stream = None  # torch.cuda.Stream of the weight-gradient kernels (None: everything on one stream)
+        self.chains = [None]     # side-stream index per layer chain (one entry: no chain concurrency)
         self._ev = None
         self.conv_hook = None    # optional callable(kind, plan, launch) wrapping conv launches (bench instrumentation)
 
@@ -115,20 +116,25 @@ class Ops:
         ops = Ops(lib, dev, lambda: torch.cuda.current_stream(dev).cuda_stream)
         import os
         if os.environ.get("MMH_WGRAD_STREAM", "1") != "0":
-            ops.enable_side_stream(torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+            chains = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)] \
+                if os.environ.get("MMH_PAT_STREAMS", "1") != "0" else []
+            ops.enable_side_stream(torch.cuda.Stream(dev), torch.cuda.Stream(dev), chains)
             if os.environ.get("MMH_MAIN_PRIORITY", "0") != "0":
                 # critical-path launches on a high-priority stream: its CTAs are placed before pending side-stream ones
                 ops.main_stream = torch.cuda.Stream(dev, priority=-1)
         return ops
 
     # ------------------------------------------------------------------ side stream (weight gradients)
-    def enable_side_stream(self, stream, update_stream=None):
+    def enable_side_stream(self, stream, update_stream=None, chain_streams=()):
         """stream: weight-gradient kernels (index 0); update_stream: optimiser update of one network under the
-        compute of another (index 1, defaults to the same stream)."""
+        compute of another (index 1, defaults to the same stream); chain_streams: indices 2, 3 -- the second and third
+        stream of a PAT block / stem run their layer chains there, next to the first one's on the main stream
+        (``chains``: the side-stream index of chain s, None = the launch stream)."""
         self.side_stream = stream
-        self._sides = [stream, update_stream if update_stream is not None else stream]
+        self._sides = [stream, update_stream if update_stream is not None else stream] + list(chain_streams)
+        self.chains = [None] + [2 + i for i in range(len(chain_streams))]
         self._ev = []
-        for _ in range(4):
+        for _ in range(2 * len(self._sides)):
             e = C.c_void_p()
             if self.lib.mmh_event_create(C.byref(e)) != 0:
                 raise L.MmhError(self.lib.mmh_last_error().decode("utf-8", "replace"))
@@ -153,15 +159,19 @@ class Ops:
 
     @contextmanager
     def side(self, which=0):
-        old = self._stream
+        """Launches inside go to side stream ``which`` (None: no change). Contexts nest: a weight gradient launched
+        from inside a chain forks off the chain's stream."""
+        if which is None:
+            yield
+            return
+        old, old_in = self._stream, self.in_side
         h = self._sides[which].cuda_stream
         self._stream = lambda: h
         self.in_side = self._sides[which]
         try:
             yield
         finally:
-            self._stream = old
-            self.in_side = None
+            self._stream, self.in_side = old, old_in
 
     def st(self):
         return C.c_void_p(self._stream())

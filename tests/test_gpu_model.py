@@ -281,6 +281,38 @@ def test_set_input_compact_forms():
                 assert abs(a[k] - b[k]) <= 2e-3 * max(abs(a[k]), 1e-3), (name, k, a[k], b[k])
 
 
+def test_fresh_models_on_recycled_device_memory():
+    """Six identically seeded models, one after the other, each on device memory the previous one released: every one
+    must take the same two steps. (Regression: Adam's moments used to be allocated lazily inside the first update,
+    whose zero-fill ran on another stream than the update itself -- the fifth model of this loop read recycled,
+    non-zero moments and went NaN at its second step.)"""
+    import math
+    from models.MMHandModel import MMHandModel
+    from oracle.ref_shims import make_opt
+    B, S = 2, 256
+    ref = None
+    for mi in range(6):
+        torch.manual_seed(4)
+        random.seed(4)
+        m = MMHandModel(make_opt(batchSize=B, fineSize=S, pool_size=0, local_rank=0, gpu=0, seed=3))
+        m.master = False
+        g = torch.Generator().manual_seed(90)
+        errs = []
+        for it in range(2):
+            b = _inputs(B, S, 500 + it)
+            m.set_input(b)
+            m.optimize_parameters()
+            errs.append({k: float(v) for k, v in m.get_current_errors().items()})
+        assert all(math.isfinite(v) for e in errs for v in e.values()), (mi, errs)
+        if ref is None:
+            ref = errs
+        for a, b_ in zip(ref, errs):
+            for k in a:
+                assert abs(a[k] - b_[k]) <= 2e-3 * max(abs(a[k]), 1e-3), (mi, k, a[k], b_[k])
+        del m
+        torch.cuda.empty_cache()
+
+
 def test_image_pack_bgr8_matches_cv2_imwrite(tmp_path):
     """aug.py's write-out (aug.py:57-71) on the GPU: mmh_image_pack_bgr8 gives the bytes cv2.imwrite stores."""
     cv2 = pytest.importorskip("cv2")
