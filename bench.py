@@ -328,7 +328,7 @@ def run_ours(a):
                               ("nccl" if world > 1 else "local")),
                    "pdl": os.environ.get("MMH_PDL", "1") != "0",
                    "grad_allreduce": getattr(model, "grad_sync_mode", "none") if world > 1 else "none",
-                   "bn_bwd_in_dgrad_epilogue": os.environ.get("MMH_FUSE_BN_BWD", "1") != "0",
+                   "bn_bwd_in_dgrad_epilogue": os.environ.get("MMH_FUSE_BN_BWD", "0") != "0",
                    "layer_chain_streams": len(ops.chains),
                    "e2e_feed": "uint8 frames + float64 keypoints from pinned host memory (mmhand_b200/loader.py form); "
                                "heatmaps rasterised and frames normalised on the device inside set_input"},

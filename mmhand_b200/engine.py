@@ -28,8 +28,12 @@ FUSE_GATHER = os.environ.get("MMH_FUSE_GATHER", "1") != "0"
 CONV_STATS = int(os.environ.get("MMH_CONV_STATS", "2"))
 # BatchNorm-backward sums (and the ReLU / dropout masks) inside the data-gradient epilogue of the consumer convolution
 # (conv_p -> BN -> ReLU -> dropout -> reflect pad -> conv_c: conv_c's dgrad stores the masked gradient and accumulates
-# sum dze, sum dze * xhat of conv_p's BatchNorm): the reduction pass over dz and x disappears. 0 = off (A/B measurements).
-FUSE_BN_BWD = os.environ.get("MMH_FUSE_BN_BWD", "1") != "0"
+# sum dze, sum dze * xhat of conv_p's BatchNorm): the reduction pass over dz and x disappears. Measured on B200
+# (profiles/r02_bn_bwd_epilogue.txt): the fused launch takes 187 us against 105 us (plain data gradient) + 62 us
+# (reduction kernel) at 512 channels -- with one epilogue warp per scheduler the ~520 instructions per 16-column chunk
+# are latency-bound and the epilogue (25 us per tile) outlasts the main loop (14 us) -- so it is OFF by default
+# (MMH_FUSE_BN_BWD=1 enables it; parity-tested either way).
+FUSE_BN_BWD = os.environ.get("MMH_FUSE_BN_BWD", "0") != "0"
 # data parallel: all-reduce the generator's weight gradients bucket by bucket during its backward pass (0: one all-reduce
 # of the whole gradient after the pass)
 GRAD_BUCKETS = os.environ.get("MMH_GRAD_BUCKETS", "1") != "0"
