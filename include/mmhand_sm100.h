@@ -183,7 +183,10 @@ typedef struct MmhNormAct {
 int mmh_norm_act(const MmhNormAct* p, void* stream);
 
 /* PATBlock tail (models/Generator.py:120-130): out = x1 + BN(c1)*sigmoid(x2o)*sigmoid(x3o); writes the three
- * next-block inputs x1' = out, x2' = [x3o | out], x3' = [x2o | out] (the reference's swapped unpacking). */
+ * next-block inputs x1' = out, x2' = [x3o | out], x3' = [x2o | out] (the reference's swapped unpacking).
+ * x3o == NULL: the two-stream block of the pose-transfer baseline
+ * (baselines/quantitative_on_benchmarks/networks/model_variants.py:58-68): out = x1 + BN(c1)*sigmoid(x2o), the one
+ * next-block stream input [x2o | out] goes to d3 (d2 = NULL). The backward entry points take x3o / dy3 == NULL alike. */
 typedef struct MmhGateFwd {
   const void* c1;
   const void* x2o;
@@ -402,6 +405,14 @@ int mmh_image_unpack_u8(const uint8_t* src_nhwc, int64_t n_img, int32_t H, int32
                         void* stream);
 int mmh_depth_unpack_u8(const uint8_t* src_nhwc, int64_t n_img, int32_t H, int32_t W, int32_t hi_ch, int32_t lo_ch,
                         double div, float* dst_nchw3, void* stream);
+
+/* ---- evaluator hook of the benchmark harness ----------------------------------------------
+ * pytorch_ssim.ssim (baselines/quantitative_on_benchmarks/pytorch_ssim/__init__.py:17-39,65-73) in one kernel:
+ * img1, img2 fp32 NCHW [B][C][H][W]; zero-padded depthwise Gaussian window (window x window, sigma), C1 = 0.01^2,
+ * C2 = 0.03^2. *mean_acc += sum of the SSIM map (divide by B*C*H*W for ssim(size_average=True)); per_image[b] += mean
+ * of image b's map (size_average=False). Either output may be NULL. */
+int mmh_ssim(const float* img1, const float* img2, int64_t B, int32_t C, int32_t H, int32_t W, int32_t window,
+             float sigma, float* mean_acc, float* per_image, void* stream);
 
 /* ---- stream ordering (cudaEvent wrappers, so that recorded launch sequences can fork / join streams) ----
  * The weight-gradient kernels of a layer run on a side stream next to the bandwidth-bound BatchNorm-backward

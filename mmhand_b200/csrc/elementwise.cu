@@ -151,7 +151,7 @@ struct GateFwdF {
       const int64_t so = lay_off(sl, b, hs, ws) + g * 8;
       ld_raw(c1 + so, in.c1);
       ld_raw(x2o + so, in.x2);
-      ld_raw(x3o + so, in.x3);
+      if (x3o != nullptr) ld_raw(x3o + so, in.x3);
       ld_raw(trunk_in + static_cast<int64_t>((b * sl.H + hs) * sl.W + ws) * sl.C + g * 8, in.t);
     }
   }
@@ -164,12 +164,17 @@ struct GateFwdF {
       float v1[8], t[8];
       cvt8(in.c1, v1);
       cvt8(in.x2, a2);
-      cvt8(in.x3, a3);
       cvt8(in.t, t);
+      if (x3o != nullptr) {
+        cvt8(in.x3, a3);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float bn = c.a[j] * v1[j] + c.b[j];
-        out[j] = t[j] + bn * sigmoidf_(a2[j]) * sigmoidf_(a3[j]);
+        for (int j = 0; j < 8; ++j) {
+          const float bn = c.a[j] * v1[j] + c.b[j];
+          out[j] = t[j] + bn * sigmoidf_(a2[j]) * sigmoidf_(a3[j]);
+        }
+      } else {              // two-stream PATBlock (model_variants.py:58-68): one attention map
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out[j] = t[j] + (c.a[j] * v1[j] + c.b[j]) * sigmoidf_(a2[j]);
       }
     }
     st8_bf16(d1 + lay_off(d1l, b, h, w) + g * 8, out);
@@ -392,7 +397,7 @@ struct GateBwdBase {
     const int64_t so = lay_off(sl, b, h, w) + g * 8;
     ld_raw(c1 + so, in.c1);
     ld_raw(x2o + so, in.x2);
-    ld_raw(x3o + so, in.x3);
+    if (x3o != nullptr) ld_raw(x3o + so, in.x3);
   }
   MMH_HD void eff(const GateBwdIn& in, const float (&a)[8], const float (&bb)[8], float (&d1)[8], float (&v1)[8],
                   float (&d2)[8], float (&d3)[8]) const {
@@ -400,10 +405,10 @@ struct GateBwdBase {
     cvt8(in.dv, dv);
     cvt8(in.c1, v1);
     cvt8(in.x2, v2);
-    cvt8(in.x3, v3);
+    if (x3o != nullptr) cvt8(in.x3, v3); else zero8(v3);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float s2 = sigmoidf_(v2[j]), s3 = sigmoidf_(v3[j]);
+      const float s2 = sigmoidf_(v2[j]), s3 = x3o != nullptr ? sigmoidf_(v3[j]) : 1.f;      // (s3 = 1: d3 = 0)
       const float bn = a[j] * v1[j] + bb[j];
       d1[j] = dv[j] * s2 * s3;
       d2[j] = dv[j] * bn * s3 * s2 * (1.f - s2);
@@ -477,7 +482,7 @@ struct GateBwdApplyF {
     const int64_t off = lay_off(yl, b, h, w) + g * 8;
     st8_bf16(dy1 + off, o);
     st8_bf16(dy2 + off, d2);
-    st8_bf16(dy3 + off, d3);
+    if (dy3 != nullptr) st8_bf16(dy3 + off, d3);
   }
 };
 
@@ -587,7 +592,7 @@ extern "C" int mmh_norm_act(const MmhNormAct* p, void* stream) {
 }
 
 extern "C" int mmh_gate_fwd(const MmhGateFwd* p, void* stream) {
-  MMH_CHECK(p && p->c1 && p->x2o && p->x3o && p->coef && p->trunk_in && p->trunk_out && p->d1, "null argument");
+  MMH_CHECK(p && p->c1 && p->x2o && p->coef && p->trunk_in && p->trunk_out && p->d1, "null argument");
   MMH_REQ_VEC(p->sl.C);
   GateFwdF f;
   f.c1 = static_cast<const act_t*>(p->c1); f.x2o = static_cast<const act_t*>(p->x2o);
@@ -718,7 +723,7 @@ static GateBwdBase gate_common(const MmhGateBwd* p) {
   return c;
 }
 extern "C" int mmh_gate_bwd_reduce(const MmhGateBwd* p, void* stream) {
-  MMH_CHECK(p && p->dout && p->c1 && p->x2o && p->x3o && p->coef && p->save && p->sums, "null argument");
+  MMH_CHECK(p && p->dout && p->c1 && p->x2o && p->coef && p->save && p->sums, "null argument");
   MMH_REQ_VEC(p->sl.C);
   GateBwdReduceF f;
   f.cm = gate_common(p);
@@ -726,8 +731,7 @@ extern "C" int mmh_gate_bwd_reduce(const MmhGateBwd* p, void* stream) {
 }
 extern "C" int mmh_gate_bwd_reduce_finalize(MmhPeer* peer, uint32_t seq, const MmhGateBwd* p, uint32_t* counter,
                                             float count_global, float* dgamma, float* dbeta, void* stream) {
-  MMH_CHECK(p && p->dout && p->c1 && p->x2o && p->x3o && p->coef && p->save && p->sums && p->k && counter,
-            "null argument");
+  MMH_CHECK(p && p->dout && p->c1 && p->x2o && p->coef && p->save && p->sums && p->k && counter, "null argument");
   MMH_REQ_VEC(p->sl.C);
   GateBwdReduceF f;
   f.cm = gate_common(p);
@@ -737,8 +741,8 @@ extern "C" int mmh_gate_bwd_reduce_finalize(MmhPeer* peer, uint32_t seq, const M
                                  counter, stream);
 }
 extern "C" int mmh_gate_bwd_apply(const MmhGateBwd* p, void* stream) {
-  MMH_CHECK(p && p->dout && p->c1 && p->x2o && p->x3o && p->coef && p->save && p->k && p->dy1 && p->dy2 && p->dy3,
-            "null argument");
+  MMH_CHECK(p && p->dout && p->c1 && p->x2o && p->coef && p->save && p->k && p->dy1 && p->dy2, "null argument");
+  MMH_CHECK((p->x3o != nullptr) == (p->dy3 != nullptr), "x3o and dy3 come together (three-stream) or not at all");
   MMH_REQ_VEC(p->sl.C);
   GateBwdApplyF f;
   f.cm = gate_common(p); f.k = p->k;

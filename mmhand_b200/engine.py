@@ -526,7 +526,10 @@ class GeneratorEngine(EngineBase):
         assert H % 4 == 0 and W % 4 == 0
         ngf, self.nb, self.use_dropout = m.ngf, m.n_blocks, m.use_dropout
         assert ngf % 16 == 0, "ngf must be a multiple of 16"
-        self.in_nc = [m.input_nc_s1, m.input_nc_s2, m.input_nc_s3]
+        # 3 streams: MM-HAND's generator (image, pose, depth; models/Generator.py); 2 streams: the pose-transfer baseline
+        # of the benchmark harness (image, pose; baselines/quantitative_on_benchmarks/networks/model_variants.py)
+        self.ns = ns = getattr(m, "n_streams", 3)
+        self.in_nc = [m.input_nc_s1, m.input_nc_s2] + ([m.input_nc_s3] if ns == 3 else [])
         self.out_nc = m.output_nc
         dim = ngf * 4
         self.dim = dim
@@ -534,7 +537,7 @@ class GeneratorEngine(EngineBase):
         E = self
         # --- stems: conv7 -> BN ReLU -> conv3 s2 -> BN ReLU -> conv3 s2 -> BN ReLU
         self.stem = []
-        for s in range(3):
+        for s in range(ns):
             seq = getattr(m, "stream%d_down" % (s + 1))
             cin = self.in_nc[s]
             c7 = ConvL(E, "s%d.c7" % s, geom_s1(B, H, W, 7, 'reflect', chan_pad(cin), ngf), cin, ngf, seq[1].weight,
@@ -550,7 +553,7 @@ class GeneratorEngine(EngineBase):
             blk = m.att[i]
             cs = dim if i == 0 else 2 * dim
             b = dict(c1=[], c2=[], bn1=[], bn2=None)
-            for s in range(3):
+            for s in range(ns):
                 seq = getattr(blk, "conv_block_stream%d" % (s + 1))
                 cin = dim if s == 0 else cs
                 c1 = ConvL(E, "b%d.s%d.c1" % (i, s), geom_s1(B, h4, w4, 3, 'reflect', cin, cin), cin, cin, seq[1].weight)
@@ -590,7 +593,7 @@ class GeneratorEngine(EngineBase):
             st["d1"].prepare_backward("stemd1.s%d" % s, "stemd1.s%d" % s)
             st["d2"].prepare_backward("stemd2.s%d" % s, "stemd2.s%d" % s)
         for i, b in enumerate(self.blocks):
-            for s in range(3):
+            for s in range(self.ns):
                 b["c1"][s].prepare_backward("c1.s%d" % s, "c1.s%d" % s)   # dx kept until the previous block's gate backward
                 b["c2"][s].prepare_backward("c2.s%d" % s, "c2.s%d" % s)
         self.up1.prepare_backward("up1", "up1")
@@ -630,8 +633,9 @@ class GeneratorEngine(EngineBase):
         b0 = self.blocks[0]
         # the three stems, and the three streams of every PAT block, are independent layer chains: each runs on its own
         # CUDA stream (chain()), so that the bandwidth-bound kernels of one chain execute under the convolutions of another
-        self.fork_chains()
-        for s, (a, b_) in ((0, (x1, None)), (1, (x2a, x2b)), (2, (x3a, x3b))):
+        ns = self.ns
+        self.fork_chains(ns)
+        for s, (a, b_) in ((0, (x1, None)), (1, (x2a, x2b)), (2, (x3a, x3b)))[:ns]:
             with self.chain(s):
                 st = self.stem[s]
                 c7, d1, d2 = st["c7"], st["d1"], st["d2"]
@@ -647,34 +651,37 @@ class GeneratorEngine(EngineBase):
         cur = 0
         for i, b in enumerate(self.blocks):
             if i > 0:
-                self.fork_chains()          # (block 0 continues the stems' chains)
-            for s in range(3):
+                self.fork_chains(ns)        # (block 0 continues the stems' chains)
+            for s in range(ns):
                 with self.chain(s):
                     c1, c2, bn1 = b["c1"][s], b["c2"][s], b["bn1"][s]
                     self._stage_fwd(c1, bn1, training)
                     drop = training and self.use_dropout
-                    key = self.drop_key(net_id * 1000 + 3 * i + s, c1.g.out_lay) if drop else 0
+                    key = self.drop_key(net_id * 1000 + ns * i + s, c1.g.out_lay) if drop else 0
                     ops.norm_act(c1.raw, c1.g.out_lay, bn1.coef, True, drop, key, c2.x, c2.g.in_lay, 1, 1, True)
                     fused2 = s == 0 and self.epilogue_stats(c2, b["bn2"], training)
                     c2.run_fwd(stats=fused2)
                     if s == 0:
                         bn2_fused = fused2
-            self.join_chains()
+            self.join_chains(ns)
             c2s = b["c2"]
             ol = c2s[0].g.out_lay
             b["bn2"].forward(c2s[0].raw, ol.rows, ol.ld, B * ol.H * ol.W, training, in_epilogue=bn2_fused)
+            d2b = d3b = d2l = d3l = None
             if i + 1 < self.nb:
                 n = self.blocks[i + 1]["c1"]
                 d1b, d1l = n[0].x, n[0].g.in_lay
-                d2b, d2l = n[1].x, n[1].g.in_lay
-                d3b, d3l = n[2].x, n[2].g.in_lay
+                if ns == 3:     # swapped wiring (Generator.py:130 vs :278): [x3o | out] feeds stream 2, [x2o | out] stream 3
+                    d2b, d2l = n[1].x, n[1].g.in_lay
+                    d3b, d3l = n[2].x, n[2].g.in_lay
+                else:           # two streams: [x2o | out] feeds stream 2 (model_variants.py:66-68)
+                    d3b, d3l = n[1].x, n[1].g.in_lay
                 lo, hi, refl = 1, 1, True
             else:
                 d1b, d1l = self.up1.x, self.up1.g.in_lay
-                d2b = d3b = d2l = d3l = None
                 lo, hi, refl = 0, 1, False
-            ops.gate_fwd(c2s[0].raw, c2s[1].raw, c2s[2].raw, ol, b["bn2"].coef, self.trunk[cur], self.trunk[1 - cur],
-                         d1b, d1l, d2b, d2l, d3b, d3l, lo, hi, refl)
+            ops.gate_fwd(c2s[0].raw, c2s[1].raw, c2s[2].raw if ns == 3 else None, ol, b["bn2"].coef, self.trunk[cur],
+                         self.trunk[1 - cur], d1b, d1l, d2b, d2l, d3b, d3l, lo, hi, refl)
             cur = 1 - cur
         self._stage_fwd(self.up1, self.bnu1, training)
         ops.norm_act(self.up1.raw, self.up1.g.out_lay, self.bnu1.coef, True, False, 0, self.up2.x, self.up2.g.in_lay,
@@ -703,49 +710,53 @@ class GeneratorEngine(EngineBase):
         for i in range(self.nb - 1, -1, -1):
             b = self.blocks[i]
             ex2 = ex3 = None
+            ns = self.ns
             if i + 1 < self.nb:
                 n = self.blocks[i + 1]["c1"]
-                s1, s2, s3 = n[0].dx_source(), n[1].dx_source(), n[2].dx_source()
-                ops.grad_gather([s1, s2.view(dim, dim), s3.view(dim, dim)], B, h4, w4, dim, self.dtrunk,
+                srcs = [n[s].dx_source() for s in range(ns)]
+                ops.grad_gather([srcs[0]] + [t.view(dim, dim) for t in srcs[1:]], B, h4, w4, dim, self.dtrunk,
                                 plain_lay(B, h4, w4, dim), True, trunk=self.dtrunk)
-                # swapped wiring: x2o of this block fed stream3 of the next one, x3o fed stream2
-                ex2, ex3 = s3.view(0, dim), s2.view(0, dim)
+                if ns == 3:     # swapped wiring: x2o of this block fed stream3 of the next one, x3o fed stream2
+                    ex2, ex3 = srcs[2].view(0, dim), srcs[1].view(0, dim)
+                else:
+                    ex2 = srcs[1].view(0, dim)
             c2s, bn2 = b["c2"], b["bn2"]
+            x3o, dy3 = (c2s[2].raw, c2s[2].dy) if ns == 3 else (None, None)
             ol = c2s[0].g.out_lay
             if self.fused_stats():
                 w = self.peer_world()
-                ops.gate_bwd_reduce_finalize(w, self.dtrunk, c2s[0].raw, c2s[1].raw, c2s[2].raw, ol, bn2.coef, bn2.save,
+                ops.gate_bwd_reduce_finalize(w, self.dtrunk, c2s[0].raw, c2s[1].raw, x3o, ol, bn2.coef, bn2.save,
                                              bn2.bsums, bn2.k, self.ticket, B * h4 * w4 * (w.size if w else 1),
                                              bn2.mod.weight.grad, bn2.mod.bias.grad)
             else:
                 ops.memset0(bn2.bsums)
-                ops.gate_bwd_reduce(self.dtrunk, c2s[0].raw, c2s[1].raw, c2s[2].raw, ol, bn2.coef, bn2.save, bn2.bsums)
+                ops.gate_bwd_reduce(self.dtrunk, c2s[0].raw, c2s[1].raw, x3o, ol, bn2.coef, bn2.save, bn2.bsums)
                 self.bwd_finalize(bn2.bsums, bn2.bsums_g, B * h4 * w4, bn2.k, bn2.mod.weight.grad, bn2.mod.bias.grad,
                                   dim)
-            ops.gate_bwd_apply(self.dtrunk, c2s[0].raw, c2s[1].raw, c2s[2].raw, ol, bn2.coef, bn2.save, bn2.k, ex2, ex3,
-                               c2s[0].dy, c2s[1].dy, c2s[2].dy, ol)
-            self.fork_chains()
-            for s in range(3):
+            ops.gate_bwd_apply(self.dtrunk, c2s[0].raw, c2s[1].raw, x3o, ol, bn2.coef, bn2.save, bn2.k, ex2, ex3,
+                               c2s[0].dy, c2s[1].dy, dy3, ol)
+            self.fork_chains(ns)
+            for s in range(ns):
                 with self.chain(s):
                     c1, c2, bn1 = b["c1"][s], b["c2"][s], b["bn1"][s]
                     drop = self.use_dropout
-                    key = self.drop_key(net_id * 1000 + 3 * i + s, c1.g.out_lay) if drop else 0
+                    key = self.drop_key(net_id * 1000 + ns * i + s, c1.g.out_lay) if drop else 0
                     fused = c2.fuse_bn_bwd(c1, bn1, True, drop)
                     c2.run_bwd(fused_key=key if fused else None)
                     self._stage_bwd(c1, bn1, [c2.dx_source()], True, drop, key, fused=fused)
             if i >= 1:
-                self.join_chains()          # (block 0's chains run on into the stems)
+                self.join_chains(ns)        # (block 0's chains run on into the stems)
             if i >= 1 and self.nb >= 2:
                 self.reduce_bucket("tail" if i == self.nb - 1 else "b%d" % i)
         b0 = self.blocks[0]["c1"]
-        for s in range(3):
+        for s in range(self.ns):
             with self.chain(s):
                 st = self.stem[s]
                 self._stage_bwd(st["d2"], st["bn2"], [b0[s].dx_source()], True, False, 0,
                                 trunk=self.dtrunk if s == 0 else None)
                 self._stage_bwd(st["d1"], st["bn1"], [st["d2"].dx_source()], True, False, 0)
                 self._stage_bwd(st["c7"], st["bn7"], [st["d1"].dx_source()], True, False, 0, want_dx=False)
-        self.join_chains()
+        self.join_chains(self.ns)
         self.reduce_bucket("head")
         self.end_wgrad()
 

@@ -528,6 +528,11 @@ class Ops:
         n, _, H, W = src.shape
         self._run(self.lib.mmh_image_pack_bgr8, (_p(src), n, H, W, _p(dst), self.st()), keep=(src, dst))
 
+    def ssim(self, a, b, window, sigma, mean_acc, per_image):
+        B, Cc, H, W = a.shape
+        self._run(self.lib.mmh_ssim, (_p(a), _p(b), B, Cc, H, W, window, float(sigma), _p(mean_acc), _p(per_image),
+                                      self.st()), keep=(a, b, mean_acc, per_image))
+
     def image_unpack_u8(self, src, dst, swap_rb=False):
         n, H, W, _ = src.shape
         self._run(self.lib.mmh_image_unpack_u8, (_p(src), n, H, W, 1 if swap_rb else 0, _p(dst), self.st()),

@@ -184,6 +184,7 @@ _SIMPLE_SIGS = {
     "mmh_heatmap_rasterize": [_vp, _i64, _i32, _i32, _f64, _f64, _vp, _vp],
     "mmh_jointsmap_rasterize": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp],
     "mmh_image_pack_bgr8": [_vp, _i64, _i32, _i32, _vp, _vp],
+    "mmh_ssim": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp],
     "mmh_image_unpack_u8": [_vp, _i64, _i32, _i32, _i32, _vp, _vp],
     "mmh_depth_unpack_u8": [_vp, _i64, _i32, _i32, _i32, _i32, _f64, _vp, _vp],
     "mmh_peer_create": [_i32, _i32, C.POINTER(_vp)],

@@ -7,6 +7,8 @@ the CUDA path:
   generator_forward      models/Generator.py:115-130 (PATBlock.forward, incl. the swapped return order that the
                          caller unpacks as x1, x2, x3 -> pose/depth streams alternate, Generator.py:130 vs :278),
                          :269-283 (PATNModel.forward), layer stacks :158-259
+  generator2_forward     baselines/quantitative_on_benchmarks/networks/model_variants.py:8-173 (two-stream PATNetwork)
+  ssim                   baselines/quantitative_on_benchmarks/pytorch_ssim/__init__.py:7-73
   discriminator_forward  models/Discriminator.py:53-55 (ResnetBlock.forward), :79-154
   gan_loss               models/network_utils.py:129-163 (always BCEWithLogitsLoss, :141)
   l1_plus_perceptual     losses/L1_plus_perceptualLoss.py:32-75
@@ -158,6 +160,50 @@ def generator_forward(sd, inputs, train=False, use_dropout=True, n_blocks=9, dro
     h = F.relu(_bn(sd, u + ".4", h, train))
     h = _conv(_rpad(h, 3), sd[u + ".7.weight"], sd[u + ".7.bias"], q_out=False)
     return torch.tanh(h)
+
+
+def generator2_forward(sd, inputs, train=False, use_dropout=True, n_blocks=9, drop=None):
+    """Two-stream pose-transfer generator of the benchmark harness
+    (baselines/quantitative_on_benchmarks/networks/model_variants.py:58-68 PATBlock.forward, :139-153 PATNModel.forward):
+    ``out = x1 + stream1(x1) * sigmoid(stream2(x2))``, next pose input ``cat(x2_out, out)`` -- no depth stream, no swap."""
+    drop = drop or DropCtx("off")
+    x1, x2 = inputs
+    x1 = _down_stream(sd, "model.stream1_down", x1, train)
+    x2 = _down_stream(sd, "model.stream2_down", x2, train)
+    for i in range(n_blocks):
+        p = "model.att.%d" % i
+        c1 = _conv_block(sd, p + ".conv_block_stream1", x1, train, use_dropout, drop, True)
+        o2 = _conv_block(sd, p + ".conv_block_stream2", x2, train, use_dropout, drop, False)
+        out = x1 + c1 * torch.sigmoid(o2)
+        x1, x2 = out, torch.cat((o2, out), 1)
+    u = "model.stream1_up"
+    h = _convT(x1, sd[u + ".0.weight"])
+    h = F.relu(_bn(sd, u + ".1", h, train))
+    h = _convT(h, sd[u + ".3.weight"])
+    h = F.relu(_bn(sd, u + ".4", h, train))
+    h = _conv(_rpad(h, 3), sd[u + ".7.weight"], sd[u + ".7.bias"], q_out=False)
+    return torch.tanh(h)
+
+
+def ssim(img1, img2, window_size=11, size_average=True):
+    """baselines/quantitative_on_benchmarks/pytorch_ssim/__init__.py:7-39,65-73: Gaussian window (sigma 1.5) built as
+    the fp32 outer product of the normalised 1-D window, five zero-padded depthwise convolutions, C1 = 0.01^2,
+    C2 = 0.03^2, mean over everything (or per image)."""
+    from math import exp
+    ch = img1.shape[1]
+    g = torch.Tensor([exp(-(x - window_size // 2) ** 2 / float(2 * 1.5 ** 2)) for x in range(window_size)])
+    g = (g / g.sum()).unsqueeze(1)
+    w = g.mm(g.t()).float().unsqueeze(0).unsqueeze(0).expand(ch, 1, window_size, window_size).contiguous().to(img1)
+    pad = window_size // 2
+    mu1 = F.conv2d(img1, w, padding=pad, groups=ch)
+    mu2 = F.conv2d(img2, w, padding=pad, groups=ch)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    s1 = F.conv2d(img1 * img1, w, padding=pad, groups=ch) - mu1_sq
+    s2 = F.conv2d(img2 * img2, w, padding=pad, groups=ch) - mu2_sq
+    s12 = F.conv2d(img1 * img2, w, padding=pad, groups=ch) - mu1_mu2
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    m = ((2 * mu1_mu2 + C1) * (2 * s12 + C2)) / ((mu1_sq + mu2_sq + C1) * (s1 + s2 + C2))
+    return m.mean() if size_average else m.mean(1).mean(1).mean(1)
 
 
 def discriminator_forward(sd, x, train=True, use_dropout=True, n_blocks=3, drop=None):

@@ -16,7 +16,7 @@ OUT = os.path.join(ROOT, "tests", "_hostemu", "libmmhand_hostemu.so")
 OUT_F32 = os.path.join(ROOT, "tests", "_hostemu", "libmmhand_hostemu_f32.so")
 
 # sources compiled in host mode: the dual-mode .cu files (as C++) and the emulation-only .cpp files
-DUAL = ["api.cu", "elementwise.cu", "loss.cu", "optim.cu", "raster.cu", "peer.cu", "jointsmap.cu", "aug.cu", "input.cu"]
+DUAL = ["api.cu", "elementwise.cu", "loss.cu", "optim.cu", "raster.cu", "peer.cu", "jointsmap.cu", "aug.cu", "input.cu", "ssim.cu"]
 EMU_ONLY = ["emu_conv.cpp"]
 
 

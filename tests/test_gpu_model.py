@@ -387,3 +387,41 @@ def test_jointsmap_rasteriser():
                              dtype=torch.uint8).cpu().numpy()
     assert np.array_equal(big[:96].astype(np.float64), full[..., 0]) and np.array_equal(big[:96], big[-96:])
     assert generate_jointsmap(torch.zeros(0, 21, 2), torch.zeros(0, 21), 256, 256, dtype=torch.uint8).shape == (0, 256, 256)
+
+
+def test_two_stream_network_and_ssim():
+    """SURVEY N4 on the GPU: the pose-transfer baseline generator (networks/model_variants.py) at its evaluation size
+    against the oracle (train-mode forward + backward, eval-mode forward), and the evaluator's SSIM kernel."""
+    from mmhand_b200.metrics import ssim
+    from models.network_utils import get_norm_layer, init_weights
+    from networks.model_variants import PATNetwork
+    from oracle import patn_ref as O
+    torch.manual_seed(21)
+    net = PATNetwork([3, 3], 3, 64, get_norm_layer('batch'), True, 9)
+    init_weights(net, 'normal')
+    net = net.to(DEV)
+    sd = _sd(net)
+    gen = torch.Generator().manual_seed(22)
+    x = [(torch.rand(2, 3, 256, 256, generator=gen) * 2 - 1).to(DEV), torch.rand(2, 3, 256, 256, generator=gen).to(DEV)]
+    net.train()
+    net._step = 0
+    y = net(x)
+    gy = torch.randn(y.shape, generator=gen).to(DEV)
+    y.backward(gy)
+    sdo = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+           for k, v in sd.items()}
+    want = O.generator2_forward(sdo, x, train=True, use_dropout=True, drop=O.DropCtx("hash", 0, 0, 0))
+    want.backward(gy)
+    err = (y.detach() - want.detach()).abs()
+    print("two-stream G train max-abs", err.max().item(), "mean-abs", err.mean().item())
+    _note(g2_train_max_abs=err.max().item(), g2_train_mean_abs=err.mean().item())
+    assert err.mean().item() <= 7e-3 and err.max().item() <= 6.5e-2
+    mine = torch.cat([p.grad.flatten() for _, p in net.named_parameters()])
+    ref = torch.cat([sdo[k].grad.flatten() for k, _ in net.named_parameters()])
+    assert torch.nn.functional.cosine_similarity(mine, ref, dim=0).item() > 0.97
+    a = torch.rand(4, 3, 256, 256, generator=gen).to(DEV)
+    b = (a + 0.1 * torch.randn(4, 3, 256, 256, generator=gen).to(DEV)).clamp(0, 1)
+    assert abs(float(ssim(a, b)) - float(O.ssim(a, b))) < 1e-5
+    assert torch.allclose(ssim(a, b, size_average=False), O.ssim(a, b, size_average=False), atol=1e-5)
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "patn2_ngf4.pt"))
+    assert abs(float(ssim(g["ssim_a"].to(DEV), g["ssim_b"].to(DEV))) - float(g["ssim_mean"])) < 2e-6
