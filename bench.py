@@ -329,7 +329,7 @@ def run_ours(a):
                    "pdl": os.environ.get("MMH_PDL", "1") != "0",
                    "grad_allreduce": getattr(model, "grad_sync_mode", "none") if world > 1 else "none",
                    "bn_bwd_in_dgrad_epilogue": os.environ.get("MMH_FUSE_BN_BWD", "0") != "0",
-                   "layer_chain_streams": len(ops.chains),
+                   "layer_chain_streams": len(model.netG.engine(B, S, S, model.world)._chains()),
                    "e2e_feed": "uint8 frames + float64 keypoints from pinned host memory (mmhand_b200/loader.py form); "
                                "heatmaps rasterised and frames normalised on the device inside set_input"},
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 6 * 4,
@@ -670,6 +670,11 @@ def _watchdog(seconds):
     def fire():
         rank = int(os.environ.get("RANK", "0"))
         sys.stderr.write("bench.py watchdog: rank %d still running after %d s -- giving up\n" % (rank, seconds))
+        try:                                   # where every thread of this rank is stuck
+            import faulthandler
+            faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+        except Exception:
+            pass
         sys.stderr.flush()
         if rank == 0:
             print(json.dumps({"error": "watchdog: multi-GPU run exceeded %d s" % seconds,

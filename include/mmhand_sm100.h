@@ -325,6 +325,11 @@ int mmh_memset(void* p, int32_t byte, int64_t bytes, void* stream);
  * >1 -> 1, < thresh -> 0, all in fp64, cast last. */
 int mmh_heatmap_rasterize(const double* uv, int64_t n_maps, int32_t H, int32_t W, double sigma, double thresh,
                           float* out, void* stream);
+/* Offline pose maps of the dataset tool (tool/generate_pose_map_RHD.py:22-29, cords_to_map): yx [n_pose][J][2] = (y, x)
+ * float64 -> out [n_pose][H][W][J] fp32 = exp(-((gy - y)^2 + (gx - x)^2) / (2 sigma^2)) evaluated in float64, no clamp,
+ * no threshold; a joint with y == missing or x == missing (MISSING_VALUE = -1) keeps a zero plane. */
+int mmh_pose_map_rasterize(const double* yx, int64_t n_pose, int32_t J, int32_t H, int32_t W, double sigma,
+                           double missing, float* out_hwc, void* stream);
 
 /* ---- joints -> depth-ordered part map (generate_jointsmap, data/generic_dataset.py:30-78) ------------
  * uv: float64 [n_pose][21][2] (x, y); depth: float64 [n_pose][21]. Per bone (:33-54): ellipse polygon

@@ -67,9 +67,45 @@ __global__ void __launch_bounds__(256) raster_kernel(const RasterF f, const int6
 }
 #endif
 
+// Offline pose maps of the reference's dataset tool (tool/generate_pose_map_RHD.py:22-29, ``cords_to_map``):
+// result[y][x][j] = exp(-((y - cy)^2 + (x - cx)^2) / (2 sigma^2)) in float64, cast to fp32, HWC layout, no clamp and no
+// threshold; a joint whose y or x equals MISSING_VALUE (-1) leaves its plane zero. One item = one pixel of one pose: J
+// consecutive floats. Values below the smallest fp32 denormal (exponent < -105) are written as the 0 they round to.
+struct PoseMapF {
+  const double* yx; float* out; int J, H, W; double two_sigma2, missing;
+  MMH_HD void operator()(int64_t i) const {
+    const int64_t hw = static_cast<int64_t>(H) * W;
+    const int64_t pose = i / hw;
+    const int p = static_cast<int>(i - pose * hw);
+    const int y = p / W, x = p - y * W;
+    const double* c = yx + pose * J * 2;
+    float* o = out + i * J;
+    for (int j = 0; j < J; ++j) {
+      const double cy = c[2 * j], cx = c[2 * j + 1];
+      float v = 0.f;
+      if (!(cy == missing || cx == missing)) {
+        const double dy = static_cast<double>(y) - cy, dx = static_cast<double>(x) - cx;
+        const double e = -(dy * dy + dx * dx) / two_sigma2;
+        v = e < -105.0 ? 0.f : static_cast<float>(exp(e));
+      }
+      o[j] = v;
+    }
+  }
+};
+
 }  // namespace mmh
 
 using namespace mmh;
+
+extern "C" int mmh_pose_map_rasterize(const double* yx, int64_t n_pose, int32_t J, int32_t H, int32_t W, double sigma,
+                                      double missing, float* out_hwc, void* stream) {
+  if (n_pose <= 0) return 0;
+  MMH_CHECK(yx && out_hwc && J > 0 && H > 0 && W > 0 && sigma > 0.0, "bad argument");
+  PoseMapF f;
+  f.yx = yx; f.out = out_hwc; f.J = J; f.H = H; f.W = W; f.missing = missing;
+  f.two_sigma2 = 2.0 * (sigma * sigma);          // the tool divides by the single number (2 * sigma ** 2)
+  return launch_map(f, n_pose * static_cast<int64_t>(H) * W, stream);
+}
 
 extern "C" int mmh_heatmap_rasterize(const double* uv, int64_t n_maps, int32_t H, int32_t W, double sigma,
                                      double thresh, float* out, void* stream) {

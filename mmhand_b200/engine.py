@@ -362,16 +362,27 @@ class EngineBase:
         stream; chains 1, 2 go to their own CUDA streams when the Ops has them (Ops.chains), so that the bandwidth-bound
         kernels of one chain run under the tensor-core kernels of another. fork_chains() / join_chains() bracket a
         group of concurrently running chains."""
-        ch = self.ops.chains
+        ch = self._chains()
         return self.ops.side(ch[s] if s < len(ch) else None)
 
+    def _chains(self):
+        """Side-stream index per chain. Data-parallel groups keep everything on the launch stream (MMH_PAT_STREAMS_DP=1
+        overrides): the SyncBN exchanges -- sequence-numbered peer mailboxes, or torch.distributed collectives that follow
+        torch's current stream -- assume one stream-ordered sequence of exchanges per rank."""
+        w = self.world
+        if w is not None and w.size > 1 and os.environ.get("MMH_PAT_STREAMS_DP", "0") != "1":
+            return [None]
+        return self.ops.chains
+
     def fork_chains(self, n=3):
-        for s in range(1, min(n, len(self.ops.chains))):
-            self.ops.fork(self.ops.chains[s])
+        ch = self._chains()
+        for s in range(1, min(n, len(ch))):
+            self.ops.fork(ch[s])
 
     def join_chains(self, n=3):
-        for s in range(1, min(n, len(self.ops.chains))):
-            self.ops.join(self.ops.chains[s])
+        ch = self._chains()
+        for s in range(1, min(n, len(ch))):
+            self.ops.join(ch[s])
 
     def drop_key(self, layer_id, lay):
         """Dropout key of a layer whose output has layout ``lay``; data parallel: masks are those of the joint batch

@@ -548,6 +548,11 @@ class Ops:
         self._run(self.lib.mmh_jointsmap_rasterize, (_p(uv), _p(depth), n, H, W, _p(out_f64), _p(out_u8), self.st()),
                   keep=(uv, depth, out_f64, out_u8))
 
+    def pose_maps(self, yx, H, W, sigma, missing, out):
+        n, J = yx.shape[0], yx.shape[1]
+        self._run(self.lib.mmh_pose_map_rasterize, (_p(yx), n, J, H, W, float(sigma), float(missing), _p(out), self.st()),
+                  keep=(yx, out))
+
     def heatmaps(self, uv, H, W, sigma, thresh, out):
         n = uv.numel() // 2
         self._run(self.lib.mmh_heatmap_rasterize, (_p(uv), n, H, W, float(sigma), float(thresh), _p(out), self.st()))

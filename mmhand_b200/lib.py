@@ -182,6 +182,7 @@ _SIMPLE_SIGS = {
     "mmh_adam": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _f32, _vp],
     "mmh_memset": [_vp, _i32, _i64, _vp],
     "mmh_heatmap_rasterize": [_vp, _i64, _i32, _i32, _f64, _f64, _vp, _vp],
+    "mmh_pose_map_rasterize": [_vp, _i64, _i32, _i32, _i32, _f64, _f64, _vp, _vp],
     "mmh_jointsmap_rasterize": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp],
     "mmh_image_pack_bgr8": [_vp, _i64, _i32, _i32, _vp, _vp],
     "mmh_ssim": [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp],

@@ -27,6 +27,23 @@ def get_heatmaps(uv_coords, shape=(256, 256), sigma=SIGMA, thresh=THRESH, out=No
     return out
 
 
+MISSING_VALUE = -1
+
+
+def cords_to_map(cords, img_size, sigma=6, device=None):
+    """``cords_to_map`` of the reference's dataset tool (tool/generate_pose_map_RHD.py:22-29) on the GPU: ``cords``
+    [..., J, 2] as (y, x) -> float32 [..., H, W, J] un-thresholded Gaussian maps (HWC), a joint with a MISSING_VALUE
+    coordinate keeps a zero plane. Batched: any leading dimensions."""
+    H, W = int(img_size[0]), int(img_size[1])
+    yx = torch.as_tensor(cords)
+    ops = runtime.get_ops(device if device is not None else (yx.device if yx.is_cuda else None))
+    yx = yx.to(ops.device, torch.float64).contiguous()
+    lead, J = tuple(yx.shape[:-2]), yx.shape[-2]
+    out = torch.empty(lead + (H, W, J), dtype=torch.float32, device=ops.device)
+    ops.pose_maps(yx.reshape(-1, J, 2), H, W, sigma, MISSING_VALUE, out)
+    return out
+
+
 def generate_jointsmap(uv_coord, depth, width, height, channel=3, dtype=torch.float64, device=None):
     """``generate_jointsmap`` of the reference (data/generic_dataset.py:30-78) on the GPU (mmh_jointsmap_rasterize).
 

@@ -61,3 +61,17 @@ def decode_depth_u8(depth_u8, div=700.0):
     depth = 256.0 * d[..., 1] + d[..., 2]                                 # float64
     out = ((np.stack([depth, depth, depth], axis=-3) / div) - 0.5) / 0.5
     return out.astype(np.float32)
+
+
+MISSING_VALUE = -1
+
+
+def cords_to_map(cords, img_size, sigma=6):
+    """tool/generate_pose_map_RHD.py:22-29, restated line by line (cords = (y, x) per joint, HWC float32 result)."""
+    result = np.zeros(tuple(img_size) + cords.shape[0:1], dtype='float32')
+    for i, point in enumerate(cords):
+        if point[0] == MISSING_VALUE or point[1] == MISSING_VALUE:
+            continue
+        xx, yy = np.meshgrid(np.arange(img_size[1]), np.arange(img_size[0]))
+        result[..., i] = np.exp(-((yy - point[0]) ** 2 + (xx - point[1]) ** 2) / (2 * sigma ** 2))
+    return result

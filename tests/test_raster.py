@@ -64,3 +64,30 @@ def test_kernel_body_matches_oracle_bit_exactly():
         assert gpu_heatmaps(torch.zeros(0, 21, 2, dtype=torch.float64), (256, 256)).shape == (0, 21, 256, 256)
     finally:
         runtime._TEST_OPS = None
+
+
+def test_cords_to_map_variant():
+    """Offline pose maps of the dataset tool (tool/generate_pose_map_RHD.py:22-29): un-thresholded, HWC, MISSING_VALUE
+    joints skipped -- bit-exact against the line-by-line restatement, on the host emulation of the kernel."""
+    import hostemu
+    from mmhand_b200 import runtime
+    from mmhand_b200.rasterize import cords_to_map
+    from oracle.raster_ref import cords_to_map as ref
+    runtime._TEST_OPS = hostemu.ops()
+    try:
+        rng = np.random.RandomState(5)
+        cords = rng.uniform(-10, 70, size=(3, 18, 2))
+        cords[0, 3] = (-1, 20.5)                 # missing y
+        cords[1, 7] = (12.25, -1)                # missing x
+        cords[2, 0] = (30, 30)                   # integer joint: exactly 1.0 at its pixel
+        cords[2, 1] = (500.0, -300.0)            # far outside: underflows to 0 / denormals
+        got = cords_to_map(torch.from_numpy(cords), (48, 64)).numpy()
+        assert got.shape == (3, 48, 64, 18) and got.dtype == np.float32
+        for i in range(3):
+            want = ref(cords[i], (48, 64))
+            assert np.array_equal(got[i], want), (i, np.abs(got[i] - want).max())
+        assert got[0, :, :, 3].max() == 0 and got[1, :, :, 7].max() == 0 and got[2, 30, 30, 0] == 1.0
+        ints = np.array([[10, 20], [-1, 5], [40, 63]])       # integer annotations, as json.loads returns them
+        assert np.array_equal(cords_to_map(torch.from_numpy(ints), (48, 64)).numpy(), ref(ints, (48, 64)))
+    finally:
+        runtime._TEST_OPS = None
