@@ -314,6 +314,10 @@ def run_ours(a):
     roofline["step_tensor_util"] = GFLOP_PER_IMG * 1e9 * value / world / (peak * 1e12)
     roofline_wgrad = roof("wgrad", "wgrad2_kernel (tcgen05 weight gradient, csrc/tc_wgrad2.cu)", None,
                           "algorithmic 2*MACs over all grid rows with un-padded channel counts")
+    chains_used = len(model.netG.engine(B, S, S, model.world)._chains())
+    if world > 1:
+        dist.barrier()                       # every rank is done measuring before the group goes away
+        dist.destroy_process_group()
     if rank != 0:
         return
     line = {
@@ -329,7 +333,7 @@ def run_ours(a):
                    "pdl": os.environ.get("MMH_PDL", "1") != "0",
                    "grad_allreduce": getattr(model, "grad_sync_mode", "none") if world > 1 else "none",
                    "bn_bwd_in_dgrad_epilogue": os.environ.get("MMH_FUSE_BN_BWD", "0") != "0",
-                   "layer_chain_streams": len(model.netG.engine(B, S, S, model.world)._chains()),
+                   "layer_chain_streams": chains_used,
                    "e2e_feed": "uint8 frames + float64 keypoints from pinned host memory (mmhand_b200/loader.py form); "
                                "heatmaps rasterised and frames normalised on the device inside set_input"},
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 6 * 4,
@@ -341,9 +345,6 @@ def run_ours(a):
         rate, n, cores = cpu_reference_rate(S, a.cpu_seconds)
         line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
                                 "sample": "%d step(s) of batch 1, oracle port of the reference step, torch fp32 CPU" % n}
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     return line
 
 

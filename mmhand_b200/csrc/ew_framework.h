@@ -329,8 +329,13 @@ inline int pg_threads(int groups) {
 }
 
 
+// resident blocks per SM the compiler must allow for the pixel kernels (register cap = 65536 / (256 * MMH_EW_MINBLOCKS))
+#ifndef MMH_EW_MINBLOCKS
+#define MMH_EW_MINBLOCKS 2
+#endif
+
 template <class F>
-__global__ void __launch_bounds__(256, 2) pg_kernel(const F f, const RowGeom rg, const int groups, const int chunks) {
+__global__ void __launch_bounds__(256, MMH_EW_MINBLOCKS) pg_kernel(const F f, const RowGeom rg, const int groups, const int chunks) {
   pdl_sync();
   constexpr int U = F::kUnroll;
   const int ppb = blockDim.x / groups;                       // pixels per block and sweep
@@ -417,7 +422,7 @@ __device__ __forceinline__ void reduce_ch_body(const F& f, const RowGeom& rg, co
   }
 }
 template <int NV, class F>
-__global__ void __launch_bounds__(256, 2) reduce_ch_kernel(const F f, const RowGeom rg, const int groups, const int chunks,
+__global__ void __launch_bounds__(256, MMH_EW_MINBLOCKS) reduce_ch_kernel(const F f, const RowGeom rg, const int groups, const int chunks,
                                                            const int C, float* __restrict__ out) {
   extern __shared__ float red[];   // [ppb][groups][NV*8]
   pdl_sync();
@@ -428,7 +433,7 @@ __global__ void __launch_bounds__(256, 2) reduce_ch_kernel(const F f, const RowG
 // cross-GPU exchange when there is one -- and the accumulators and the counter go back to zero for the next launch.
 // One launch instead of memset + reduction + finalise.
 template <int NV, class F, class Fin>
-__global__ void __launch_bounds__(256, 2) reduce_ch_fin_kernel(const F f, const RowGeom rg, const int groups,
+__global__ void __launch_bounds__(256, MMH_EW_MINBLOCKS) reduce_ch_fin_kernel(const F f, const RowGeom rg, const int groups,
                                                                const int chunks, const int C, float* out,
                                                                const Fin fin, uint32_t* counter) {
   extern __shared__ float red[];

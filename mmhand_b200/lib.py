@@ -118,7 +118,7 @@ def load(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("MMH_LIB_PATH") or LIB_PATH      # MMH_LIB_PATH: A/B builds of the same library
     if not os.path.exists(p):
         raise MmhError(
             "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -9,7 +9,7 @@ grep -E "passed|failed|skipped|joint-batch" gpurun_out/pytest_ddp_n$N.log | tail
 grep -E "^E  " gpurun_out/pytest_ddp_n$N.log | head -10
 run() { # name, env...
   name=$1; shift
-  env MMH_BENCH_WATCHDOG_S=120 "$@" timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29400 + RANDOM % 200)) \
+  env MMH_BENCH_WATCHDOG_S=100 "$@" timeout 160 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29400 + RANDOM % 200)) \
     bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n${N}_$name.json 2> gpurun_out/bench_n${N}_$name.err; rc=$?
   python -c "
 import json
