@@ -35,7 +35,18 @@
 
 namespace mmh {
 
-constexpr int kC2Threads = 192;
+// Epilogue warp groups. 1: warps 2..5 drain every tile (192 threads). 2: two groups of four warps (warps 4..7 and 8..11,
+// 384 threads) take alternate tiles -- group g owns accumulator stage g -- so that an epilogue may last two main loops:
+// with ONE warp per scheduler the epilogue arithmetic is latency-bound (~6 cycles per instruction, profiles/
+// r02_bn_bwd_epilogue.txt), which makes the short-contraction layers (7x7 stems, stride-2 and transposed layers) and
+// every fused-statistics epilogue epilogue-bound. Registers move with setmaxnreg: the warp group of the TMA / MMA warps
+// gives up what the epilogue groups need (56 + 2 x 224 registers per thread of the three groups = 64.5 K).
+#ifndef MMH_C2_EPI_GROUPS
+#define MMH_C2_EPI_GROUPS 2
+#endif
+constexpr int kC2EpiGroups = MMH_C2_EPI_GROUPS;
+constexpr int kC2EpiWarp0 = kC2EpiGroups == 2 ? 4 : 2;          // first epilogue warp
+constexpr int kC2Threads = 32 * (kC2EpiWarp0 + 4 * kC2EpiGroups);
 constexpr int kC2MaxGroups = 16;
 constexpr int kC2MaxA = 8;
 constexpr int kC2MaxB = 8;
@@ -425,6 +436,8 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     __syncthreads();
   }
 
+  if (warp < kC2EpiWarp0) {
+  if (kC2EpiGroups == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");      // (all four warps of the group)
   if (warp == 0) {
     if (elect_one()) {
       // ===== TMA producer: windows into the A ring, weight tiles into the B ring, in consumption order
@@ -496,14 +509,17 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
 #undef MMH_ISSUE
     }
+  }
   } else {
-    // ===== epilogue warps: TMEM lane quadrant = warp id % 4
+    // ===== epilogue warps: TMEM lane quadrant = warp id % 4; group = accumulator stage it drains
+    if (kC2EpiGroups == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int quad = warp & 3;
+    const int grp = (warp - kC2EpiWarp0) >> 2;
     const int row = quad * 32 + lane;
     const int hw = p.Hg * p.Wg;
     const int nchunks = p.BN / 16;
     const uint32_t empty_remote = NCTA == 2 ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : 0u;
-    uint32_t acc = 0, acc_phase = 0;
+    const int my_step = tile_step * kC2EpiGroups;        // distance between two tiles of this group
     // fused BN-backward statistics (MB == 1): row -> mirrored logical pixel -> row of the producer's raw output
     auto bs_row = [&](int tile, int64_t& xrow, uint32_t& word0, bool& in_range, int64_t& orow) {
       const int tm = tile / p.tiles_n;
@@ -528,14 +544,17 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const char* base = reinterpret_cast<const char*>(p.bs_x) + (xrow * p.bs_x_ld + tn * p.BN) * 2;
       for (int b = 0; b < p.BN * 2; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + b));
     };
-    if (BS) bs_prefetch(first_tile);
-    for (int tile = first_tile; tile < n_tiles; tile += tile_step) {
+    if (BS) bs_prefetch(first_tile + grp * tile_step);
+    int kt = 0;                                          // k-th tile of this CTA: stage kt & 1, phase (kt >> 1) & 1
+    for (int tile = first_tile; tile < n_tiles; tile += tile_step, ++kt) {
+      if (kC2EpiGroups == 2 && (kt & 1) != grp) continue;
+      const uint32_t acc = kt & 1, acc_phase = (kt >> 1) & 1;
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
       const int n0 = tn * p.BN;
       if (BS) {
         int64_t xrow, orow; uint32_t w0; bool in_range;
         bs_row(tile, xrow, w0, in_range, orow);
-        bs_prefetch(tile + tile_step);                  // the next tile's rows travel to L2 under this tile's work
+        bs_prefetch(tile + my_step);                    // the group's next tile: its rows travel to L2 under this one
         const __nv_bfloat16* xr = static_cast<const __nv_bfloat16*>(p.bs_x) + xrow * p.bs_x_ld;
         uint4 xa[4], xa2[4];                            // first 64 channels: in flight while the main loop finishes
         const bool ld_x = in_range && !(p.dbg & 16);    // MMH_C2_DEBUG=16: no loads of x (timing experiments only)
@@ -551,7 +570,6 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (NCTA == 2) mbar_arrive_cluster(empty_remote + acc * 8);
           else mbar_arrive(&tmem_empty[acc]);
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
       }
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -583,12 +601,11 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (NCTA == 2) mbar_arrive_cluster(empty_remote + acc * 8);
         else mbar_arrive(&tmem_empty[acc]);
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (p.bn_sums != nullptr) {
-      // the four epilogue warps are done with their tiles: CTA partial sums -> global accumulators
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = threadIdx.x - 64; i < 2 * p.N; i += 128) {
+      // the epilogue warps are done with their tiles: CTA partial sums -> global accumulators
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * kC2EpiGroups) : "memory");
+      for (int i = threadIdx.x - 32 * kC2EpiWarp0; i < 2 * p.N; i += 128 * kC2EpiGroups) {
         const int st = i >= p.N ? 1 : 0, c = i - st * p.N;
         const float v = s_stats[i];
         if (c < p.bn_C && v != 0.f) atomicAdd(p.bn_sums + st * p.bn_C + c, v);

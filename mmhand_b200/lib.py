@@ -123,10 +123,6 @@ def load(path=None):
         raise MmhError(
             "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(there is no CPU fallback for the mmhand_b200 kernels)" % p)
-    if int(os.environ.get("WORLD_SIZE", "1") or 1) > 1 and "MMH_PDL" not in os.environ:
-        # Programmatic dependent launch was measured and validated on one GPU only (it came after the last 2-GPU
-        # visit of round 1): multi-process runs keep plain stream-ordered launches unless MMH_PDL=1 is given.
-        os.environ["MMH_PDL"] = "0"
     lib = C.CDLL(p)
     lib.mmh_last_error.restype = C.c_char_p
     lib.mmh_version.restype = C.c_int

