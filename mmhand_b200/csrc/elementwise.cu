@@ -131,6 +131,97 @@ struct NormActF {
   }
 };
 
+// element offsets of the even- / odd-column pixels of one (image, row) of a grid (parity-plane grids keep the two
+// in different planes; plain grids: e == o); 32-bit: the launchers check rows * pitch < 2^31
+struct RowOff { int32_t e, o; };
+MMH_HD void rowoff(const LayD& l, int b, int h, RowOff& r) {
+  const int hp = h + l.h0;
+  if (!l.phase) {
+    r.e = ((b * l.Hg + hp) * l.Wg + l.w0) * l.ld + l.c0;
+    r.o = r.e;
+  } else {
+    r.e = (((hp & 1) * 2) * l.plane_rows + (b * l.Hg + (hp >> 1)) * l.Wg) * l.ld + l.c0;
+    r.o = r.e + l.plane_rows * l.ld;
+  }
+}
+MMH_HD int32_t rowat(const LayD& l, const RowOff& r, int w) {
+  if (!l.phase) return r.e + w * l.ld;
+  const int wp = w + l.w0;
+  return ((wp & 1) ? r.o : r.e) + (wp >> 1) * l.ld;
+}
+inline bool lay_fits32(const MmhLay& l) {
+  return static_cast<int64_t>(l.B) * l.Hg * l.Wg * (l.phase ? 4 : 1) * l.ld + l.c0 < (int64_t(1) << 31);
+}
+
+// ------------------------------------------------------------------------------------------------ norm + act, lean
+// NormActF as a row kernel: the source row (mirrored for halo rows), the destination row and the dropout counter are
+// set up once per (image, row); dropout and the fp32 residual are compile-time.
+struct NormLeanRow { RowOff s, d; int32_t plain; uint32_t dword; int h, live; };
+template <bool RESID> struct NormLeanIn { ActX8 x; };
+template <> struct NormLeanIn<true> { ActX8 x; F32x8 r; };
+template <bool DROP, bool RESID, int U>
+struct NormLeanF {
+  static constexpr int kUnroll = U;
+  struct Ctx { float a[8], b[8]; };
+  typedef NormLeanIn<RESID> In;
+  typedef NormLeanRow Row;
+  const act_t* src; LayD sl; const float* coef; int relu; uint32_t key;
+  const float* resid; act_t* dst; LayD dl; int reflect; float* dst_f32;
+  MMH_HD void prep(int g, Ctx& c) const {
+    if (coef != nullptr) { ld8_f32(coef + g * 8, c.a); ld8_f32(coef + sl.C + g * 8, c.b); }
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c.a[j] = 1.f; c.b[j] = 0.f; }
+    }
+  }
+  MMH_HD void row(int b, int h, Row& r) const {
+    const int H = sl.H, W = sl.W;
+    r.h = h;
+    r.live = (reflect || (h >= 0 && h < H)) ? 1 : 0;
+    const int hs = r.live ? reflect_idx(h, H) : 0;
+    rowoff(sl, b, hs, r.s);
+    if (dst != nullptr) rowoff(dl, b, h, r.d); else r.d = r.s;
+    r.plain = (b * H + hs) * W * sl.C;
+    r.dword = (static_cast<uint32_t>(b) * H + hs) * W * static_cast<uint32_t>((sl.C + 7) / 8);
+  }
+  MMH_HD bool live(const Row& r, int w) const { return r.live && (reflect || (w >= 0 && w < sl.W)); }
+  MMH_HD void load(const Row& r, int w, int g, const Ctx&, In& in) const {
+    if (live(r, w)) {
+      const int ws = reflect_idx(w, sl.W);
+      ld_raw(src + (rowat(sl, r.s, ws) + g * 8), in.x);
+      if constexpr (RESID) ld_raw(resid + (r.plain + ws * sl.C + g * 8), in.r);
+    }
+  }
+  MMH_HD void finish(const In& in, const Row& r, int w, int g, const Ctx& c) const {
+    const int H = sl.H, W = sl.W, C = sl.C;
+    float y[8];
+    zero8(y);
+    if (live(r, w)) {
+      const int ws = reflect_idx(w, W);
+      cvt8(in.x, y);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = c.a[j] * y[j] + c.b[j];
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = y[j] > 0.f ? y[j] : 0.f;
+      }
+      if (DROP) {
+        const uint32_t word = r.dword + static_cast<uint32_t>(ws) * static_cast<uint32_t>((C + 7) / 8) + g;
+        const uint32_t bits = mix32(word * 0x9E3779B1u + key);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = ((bits >> j) & 1u) ? 2.0f * y[j] : 0.f;
+      }
+      if constexpr (RESID) {
+        float rr[8];
+        cvt8(in.r, rr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] += rr[j];
+      }
+    }
+    if (dst != nullptr) st8_bf16(dst + (rowat(dl, r.d, w) + g * 8), y);
+    if (dst_f32 != nullptr && r.h >= 0 && r.h < H && w >= 0 && w < W) st8_f32(dst_f32 + (r.plain + w * C + g * 8), y);
+  }
+};
 // ------------------------------------------------------------------------------------------------ PAT gate
 struct GateFwdF {
   static constexpr int kUnroll = 2;
@@ -387,6 +478,112 @@ struct BnBwdApplyF {
     st8_bf16(dy + lay_off(yl, b, h, w) + g * 8, o);
   }
 };
+// ------------------------------------------------------------------------------------------------ BN backward, lean
+// The hot instance of the two kernels above -- ONE gathered source, no fp32 trunk term: every BatchNorm of the
+// generator and the discriminators except the two that join the residual trunk -- as row kernels (ew_framework.h):
+// base offsets per (image, row), ~3x fewer instructions per 16-byte vector than the general functors (whose per-item
+// layout arithmetic, source loops and 4-byte parameter loads made them issue-bound at 1.7-2.9 TB/s), ReLU and dropout
+// resolved at compile time. The reduction accumulates sum dz*(x - mean) and scales by rstd once per thread.
+struct BnLeanRow { RowOff x, s, y; uint32_t dword; int b, h, hb; };
+struct BnLeanIn { ActX8 x, s; };
+
+template <bool RELU, bool DROP>
+struct BnLeanBase {
+  const act_t* x; LayD xl; GradSrcD src; const float* coef; const float* save; uint32_t key;
+  MMH_HD void row(int b, int h, BnLeanRow& r) const {
+    r.b = b; r.h = h;
+    rowoff(xl, b, h, r.x);
+    rowoff(src.l, b, h, r.s);
+    r.y = r.x;
+    r.hb = (src.reflect && on_fold_border(h, xl.H, src.lo, src.hi)) ? 1 : 0;
+    r.dword = (static_cast<uint32_t>(b) * xl.H + h) * xl.W * static_cast<uint32_t>((xl.C + 7) / 8);
+  }
+  MMH_HD void load(const BnLeanRow& r, int w, int g, BnLeanIn& in) const {
+    ld_raw(x + (rowat(xl, r.x, w) + g * 8), in.x);
+    ld_raw(src.p + (rowat(src.l, r.s, w) + g * 8), in.s);
+  }
+  // effective upstream gradient (gathered, masked) and raw activation of one vector
+  MMH_HD void eff(const BnLeanIn& in, const BnLeanRow& r, int w, int g, const float (&a)[8], const float (&bb)[8],
+                  float (&dze)[8], float (&xv)[8]) const {
+    cvt8(in.s, dze);
+    if (src.reflect && (r.hb || on_fold_border(w, xl.W, src.lo, src.hi))) fold_extra8(src, r.b, r.h, w, g * 8, dze);
+    cvt8(in.x, xv);
+    if (RELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (!(a[j] * xv[j] + bb[j] > 0.f)) dze[j] = 0.f;
+    }
+    if (DROP) {
+      const uint32_t word = r.dword + static_cast<uint32_t>(w) * static_cast<uint32_t>((xl.C + 7) / 8) + g;
+      const uint32_t bits = mix32(word * 0x9E3779B1u + key);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dze[j] = ((bits >> j) & 1u) ? 2.0f * dze[j] : 0.f;
+    }
+  }
+};
+template <bool RELU, bool DROP, int U>
+struct BnLeanReduceF {
+  static constexpr int kUnroll = U;
+  struct Ctx { float a[8], b[8], mean[8]; };
+  typedef BnLeanIn In;
+  typedef BnLeanRow Row;
+  BnLeanBase<RELU, DROP> cm;
+  MMH_HD void prep(int g, Ctx& c) const {
+    const int C = cm.xl.C;
+    if (RELU) { ld8_f32(cm.coef + g * 8, c.a); ld8_f32(cm.coef + C + g * 8, c.b); }
+    else { zero8(c.a); zero8(c.b); }
+    ld8_f32(cm.save + g * 8, c.mean);
+  }
+  MMH_HD void row(int b, int h, Row& r) const { cm.row(b, h, r); }
+  MMH_HD void load(const Row& r, int w, int g, const Ctx&, In& in) const { cm.load(r, w, g, in); }
+  MMH_HD void accum(const In& in, const Row& r, int w, int g, const Ctx& c, float (&acc)[2][8]) const {
+    float dze[8], xv[8];
+    cm.eff(in, r, w, g, c.a, c.b, dze, xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[0][j] += dze[j];
+      acc[1][j] += dze[j] * (xv[j] - c.mean[j]);
+    }
+  }
+  MMH_HD void post(int g, const Ctx&, float (&acc)[2][8]) const {
+    float rstd[8];
+    ld8_f32(cm.save + cm.xl.C + g * 8, rstd);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[1][j] *= rstd[j];
+  }
+};
+template <bool RELU, bool DROP, int U>
+struct BnLeanApplyF {
+  static constexpr int kUnroll = U;
+  struct Ctx { float a[8], b[8], bx[8], cc[8]; };
+  typedef BnLeanIn In;
+  typedef BnLeanRow Row;
+  BnLeanBase<RELU, DROP> cm; const float* k; act_t* dy; LayD yl;
+  MMH_HD void prep(int g, Ctx& c) const {
+    const int C = cm.xl.C;
+    float mean[8], rstd[8], k0[8], k1[8];
+    ld8_f32(cm.coef + g * 8, c.a); ld8_f32(cm.coef + C + g * 8, c.b);
+    ld8_f32(cm.save + g * 8, mean); ld8_f32(cm.save + C + g * 8, rstd);
+    ld8_f32(k + g * 8, k0); ld8_f32(k + C + g * 8, k1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      c.bx[j] = -c.a[j] * k1[j] * rstd[j];
+      c.cc[j] = -c.a[j] * k0[j] + c.a[j] * k1[j] * rstd[j] * mean[j];
+    }
+  }
+  MMH_HD void row(int b, int h, Row& r) const {
+    cm.row(b, h, r);
+    rowoff(yl, b, h, r.y);
+  }
+  MMH_HD void load(const Row& r, int w, int g, const Ctx&, In& in) const { cm.load(r, w, g, in); }
+  MMH_HD void finish(const In& in, const Row& r, int w, int g, const Ctx& c) const {
+    float dze[8], xv[8], o[8];
+    cm.eff(in, r, w, g, c.a, c.b, dze, xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = c.a[j] * dze[j] + c.bx[j] * xv[j] + c.cc[j];
+    st8_bf16(dy + (rowat(yl, r.y, w) + g * 8), o);
+  }
+};
 // ------------------------------------------------------------------------------------------------ gate backward
 struct GateBwdIn { F32x8 dv; ActX8 c1, x2, x3, e2, e3; };
 struct GateBwdBase {
@@ -577,6 +774,28 @@ extern "C" int mmh_bn_finalize(const float* sums, float count, const float* gamm
   return launch_map(f, C, stream);
 }
 
+static bool ew_lean_enabled() {       // MMH_EW_LEAN=0: the general kernels everywhere (read per call: tests switch)
+  const char* e = getenv("MMH_EW_LEAN");
+  return e == nullptr || atoi(e) != 0;
+}
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static bool norm_lean_ok(const MmhNormAct* p) {
+  if (!ew_lean_enabled() || p->sl.C > 1024) return false;
+  if (!lay_fits32(p->sl) || (p->dst && !lay_fits32(p->dl))) return false;
+  if (static_cast<int64_t>(p->sl.B) * p->sl.H * p->sl.W * p->sl.C >= (int64_t(1) << 31)) return false;
+  return p->coef == nullptr || aligned16(p->coef);
+}
+template <bool DROP, bool RESID, bool PF>
+static int norm_lean_pf(const NormActF& g, const RowGeom& rg, void* stream) {
+  NormLeanF<DROP, RESID, (PF && RESID) ? 2 : 4> f;
+  f.src = g.src; f.sl = g.sl; f.coef = g.coef; f.relu = g.relu; f.key = g.key; f.resid = g.resid;
+  f.dst = g.dst; f.dl = g.dl; f.reflect = g.reflect; f.dst_f32 = g.dst_f32;
+  return launch_rows_pg<PF>(f, rg, g.sl.C / 8, 1, stream);
+}
+template <bool DROP, bool RESID>
+static int norm_lean_t(const NormActF& g, const RowGeom& rg, void* stream) {
+  return rows_prefetch() ? norm_lean_pf<DROP, RESID, true>(g, rg, stream) : norm_lean_pf<DROP, RESID, false>(g, rg, stream);
+}
 extern "C" int mmh_norm_act(const MmhNormAct* p, void* stream) {
   MMH_CHECK(p && p->src && (p->dst || p->dst_f32), "null argument");
   MMH_REQ_VEC(p->sl.C);
@@ -588,7 +807,13 @@ extern "C" int mmh_norm_act(const MmhNormAct* p, void* stream) {
   f.reflect = p->reflect; f.dst_f32 = p->dst_f32;
   MMH_CHECK(!p->dst || (p->dl.H == p->sl.H && p->dl.W == p->sl.W && p->dl.C == p->sl.C), "src/dst shape mismatch");
   MMH_CHECK(!f.reflect || (lo < f.sl.H && hi < f.sl.H && lo < f.sl.W && hi < f.sl.W), "halo too large");
-  return launch_pg(f, make_rowgeom(f.sl.B, f.sl.H, f.sl.W, lo, hi), p->sl.C / 8, stream);
+  const RowGeom rg = make_rowgeom(f.sl.B, f.sl.H, f.sl.W, lo, hi);
+  if (norm_lean_ok(p)) {
+    // the convolution that produced `src` wrote its rows in ascending order: start with the last ones (still in L2)
+    if (p->dropout) return p->resid ? norm_lean_t<true, true>(f, rg, stream) : norm_lean_t<true, false>(f, rg, stream);
+    return p->resid ? norm_lean_t<false, true>(f, rg, stream) : norm_lean_t<false, false>(f, rg, stream);
+  }
+  return launch_pg(f, rg, p->sl.C / 8, stream);
 }
 
 extern "C" int mmh_gate_fwd(const MmhGateFwd* p, void* stream) {
@@ -665,6 +890,61 @@ static int bn_bwd_apply_t(const MmhBnBwd* p, void* stream) {
   f.cm = bn_common<NS, TR>(p); f.k = p->k; f.dy = static_cast<act_t*>(p->dy); f.yl = to_layd(p->yl);
   return launch_pg(f, make_rowgeom(p->xl.B, p->xl.H, p->xl.W, 0, 0), p->xl.C / 8, stream);
 }
+// ---- lean path selection (MMH_BN_LEAN=0: always the general kernels)
+static bool bn_lean_enabled() {       // read per call: tests switch between the two paths inside one process
+  const char* e = getenv("MMH_BN_LEAN");
+  return e == nullptr || atoi(e) != 0;
+}
+static bool bn_lean_ok(const MmhBnBwd* p, bool apply) {
+  if (!bn_lean_enabled() || !ew_lean_enabled() || p->nsrc != 1 || p->trunk != nullptr) return false;
+  if (!lay_fits32(p->xl) || !lay_fits32(p->src[0].l) || (apply && !lay_fits32(p->yl))) return false;
+  if (p->xl.C > 1024 || !aligned16(p->coef) || !aligned16(p->save) || (apply && !aligned16(p->k))) return false;
+  if (static_cast<int64_t>(p->xl.B) * p->xl.H * p->xl.W >= (int64_t(1) << 30)) return false;
+  return true;
+}
+template <bool RELU, bool DROP>
+static BnLeanBase<RELU, DROP> bn_lean_common(const MmhBnBwd* p) {
+  BnLeanBase<RELU, DROP> c;
+  c.x = static_cast<const act_t*>(p->x); c.xl = to_layd(p->xl); c.src = to_gsd(p->src[0]);
+  c.coef = p->coef; c.save = p->save; c.key = p->drop_key;
+  return c;
+}
+// reduce sweeps the rows from the last to the first (the data gradient that produced the source has just written
+// them in ascending order), apply from the first to the last (= the rows the reduction touched last)
+template <bool RELU, bool DROP, bool PF>
+static int bn_lean_reduce_pf(const MmhBnBwd* p, const BnBwdFin* fin, uint32_t* counter, void* stream) {
+  BnLeanReduceF<RELU, DROP, PF ? 2 : 4> f;       // software pipelining: two register sets of two vectors
+  f.cm = bn_lean_common<RELU, DROP>(p);
+  const RowGeom rg = make_rowgeom(p->xl.B, p->xl.H, p->xl.W, 0, 0);
+  if (fin != nullptr)
+    return launch_rows_reduce_fin<2, PF>(f, rg, p->xl.C / 8, p->xl.C, p->sums, *fin, counter, 1, stream);
+  return launch_rows_reduce<2, PF>(f, rg, p->xl.C / 8, p->xl.C, p->sums, 1, stream);
+}
+template <bool RELU, bool DROP>
+static int bn_lean_reduce_t(const MmhBnBwd* p, const BnBwdFin* fin, uint32_t* counter, void* stream) {
+  return rows_prefetch() ? bn_lean_reduce_pf<RELU, DROP, true>(p, fin, counter, stream)
+                         : bn_lean_reduce_pf<RELU, DROP, false>(p, fin, counter, stream);
+}
+template <bool RELU, bool DROP, bool PF>
+static int bn_lean_apply_pf(const MmhBnBwd* p, void* stream) {
+  BnLeanApplyF<RELU, DROP, PF ? 2 : 4> f;
+  f.cm = bn_lean_common<RELU, DROP>(p); f.k = p->k; f.dy = static_cast<act_t*>(p->dy); f.yl = to_layd(p->yl);
+  return launch_rows_pg<PF>(f, make_rowgeom(p->xl.B, p->xl.H, p->xl.W, 0, 0), p->xl.C / 8, 0, stream);
+}
+template <bool RELU, bool DROP>
+static int bn_lean_apply_t(const MmhBnBwd* p, void* stream) {
+  return rows_prefetch() ? bn_lean_apply_pf<RELU, DROP, true>(p, stream) : bn_lean_apply_pf<RELU, DROP, false>(p, stream);
+}
+static int bn_lean_reduce(const MmhBnBwd* p, const BnBwdFin* fin, uint32_t* counter, void* stream) {
+  if (p->relu) return p->dropout ? bn_lean_reduce_t<true, true>(p, fin, counter, stream)
+                                 : bn_lean_reduce_t<true, false>(p, fin, counter, stream);
+  return p->dropout ? bn_lean_reduce_t<false, true>(p, fin, counter, stream)
+                    : bn_lean_reduce_t<false, false>(p, fin, counter, stream);
+}
+static int bn_lean_apply(const MmhBnBwd* p, void* stream) {
+  if (p->relu) return p->dropout ? bn_lean_apply_t<true, true>(p, stream) : bn_lean_apply_t<true, false>(p, stream);
+  return p->dropout ? bn_lean_apply_t<false, true>(p, stream) : bn_lean_apply_t<false, false>(p, stream);
+}
 #define MMH_BN_BWD_DISPATCH(fn)                                                            \
   do {                                                                                     \
     const bool tr = p->trunk != nullptr;                                                   \
@@ -675,6 +955,7 @@ static int bn_bwd_apply_t(const MmhBnBwd* p, void* stream) {
 extern "C" int mmh_bn_bwd_reduce(const MmhBnBwd* p, void* stream) {
   if (bn_bwd_check(p)) return 1;
   MMH_CHECK(p->sums, "null argument");
+  if (bn_lean_ok(p, false)) return bn_lean_reduce(p, nullptr, nullptr, stream);
   MMH_BN_BWD_DISPATCH(bn_bwd_reduce_t);
 }
 extern "C" int mmh_bn_bwd_reduce_finalize(MmhPeer* peer, uint32_t seq, const MmhBnBwd* p, uint32_t* counter,
@@ -683,6 +964,7 @@ extern "C" int mmh_bn_bwd_reduce_finalize(MmhPeer* peer, uint32_t seq, const Mmh
   MMH_CHECK(p->sums && p->k && counter, "null argument");
   BnBwdFin fin = bwd_fin(p->sums, count_global, const_cast<float*>(p->k), dgamma, dbeta, p->xl.C);
   if (peer_dev(peer, seq, 2 * p->xl.C, &fin.px)) return 1;
+  if (bn_lean_ok(p, false)) return bn_lean_reduce(p, &fin, counter, stream);
   const bool tr = p->trunk != nullptr;
   if (p->nsrc == 0) return bn_bwd_reduce_fin_t<0, false>(p, fin, counter, stream);
   if (p->nsrc == 1) return tr ? bn_bwd_reduce_fin_t<1, true>(p, fin, counter, stream)
@@ -706,6 +988,7 @@ extern "C" int mmh_bn_bwd_finalize_reset(MmhPeer* peer, uint32_t seq, float* sum
 extern "C" int mmh_bn_bwd_apply(const MmhBnBwd* p, void* stream) {
   if (bn_bwd_check(p)) return 1;
   MMH_CHECK(p->k && p->dy, "null argument");
+  if (bn_lean_ok(p, true)) return bn_lean_apply(p, stream);
   MMH_BN_BWD_DISPATCH(bn_bwd_apply_t);
 }
 extern "C" int mmh_bn_bwd_finalize(const float* sums_global, const float* sums_local, float count, float* k,

@@ -175,6 +175,12 @@ MMH_HD void zero8(float (&f)[8]) {
   for (int i = 0; i < 8; ++i) f[i] = 0.f;
 }
 
+// MMH_ROWS_PF=0: row kernels without software pipelining (read per call: A/B inside one process)
+inline bool rows_prefetch() {
+  const char* e = getenv("MMH_ROWS_PF");
+  return e == nullptr || atoi(e) != 0;
+}
+
 // ------------------------------------------------------------------ launchers
 #ifdef MMH_HOST_EMU
 
@@ -228,6 +234,65 @@ template <int NV, class F, class Fin>
 int launch_reduce_ch_fin(const F& f, const RowGeom& rg, int groups, int C, float* out, const Fin& fin, uint32_t*,
                          void* stream) {
   launch_reduce_ch<NV>(f, rg, groups, C, out, stream);
+  for (int c = 0; c < C; ++c) {
+    fin(c);
+    for (int v = 0; v < NV; ++v) out[v * C + c] = 0.f;
+  }
+  return 0;
+}
+// ---- row launchers (lean kernels): the functor computes the base offsets of an (image, row) once (F::Row); items
+// are addressed as base + column * pitch
+template <bool PF, class F>
+int launch_rows_pg(const F& f, const RowGeom& rg, int groups, int /*reverse*/, void*) {
+  for (int g = 0; g < groups; ++g) {
+    typename F::Ctx c;
+    f.prep(g, c);
+    for (int row = 0; row < rg.n_rows; ++row) {
+      const int b = row / rg.h_ext, h = row % rg.h_ext - rg.lo;
+      typename F::Row r;
+      f.row(b, h, r);
+      for (int col = 0; col < rg.n_cols; ++col) {
+        typename F::In in;
+        f.load(r, col - rg.lo, g, c, in);
+        f.finish(in, r, col - rg.lo, g, c);
+      }
+    }
+  }
+  return 0;
+}
+template <int NV, bool PF, class F>
+int launch_rows_reduce(const F& f, const RowGeom& rg, int groups, int C, float* out, int /*reverse*/, void*) {
+  for (int g = 0; g < groups; ++g) {
+    typename F::Ctx c;
+    f.prep(g, c);
+    // per-row partial sums in fp32 (as a GPU block does), rows combined in double
+    double acc[NV][8];
+    for (int v = 0; v < NV; ++v)
+      for (int j = 0; j < 8; ++j) acc[v][j] = 0.0;
+    for (int row = 0; row < rg.n_rows; ++row) {
+      const int b = row / rg.h_ext, h = row % rg.h_ext - rg.lo;
+      typename F::Row r;
+      f.row(b, h, r);
+      float a[NV][8];
+      for (int v = 0; v < NV; ++v) zero8(a[v]);
+      for (int col = 0; col < rg.n_cols; ++col) {
+        typename F::In in;
+        f.load(r, col - rg.lo, g, c, in);
+        f.accum(in, r, col - rg.lo, g, c, a);
+      }
+      f.post(g, c, a);
+      for (int v = 0; v < NV; ++v)
+        for (int j = 0; j < 8; ++j) acc[v][j] += a[v][j];
+    }
+    for (int v = 0; v < NV; ++v)
+      for (int j = 0; j < 8; ++j) out[v * C + g * 8 + j] += static_cast<float>(acc[v][j]);
+  }
+  return 0;
+}
+template <int NV, bool PF, class F, class Fin>
+int launch_rows_reduce_fin(const F& f, const RowGeom& rg, int groups, int C, float* out, const Fin& fin, uint32_t*,
+                           int reverse, void* stream) {
+  launch_rows_reduce<NV, PF>(f, rg, groups, C, out, reverse, stream);
   for (int c = 0; c < C; ++c) {
     fin(c);
     for (int v = 0; v < NV; ++v) out[v * C + c] = 0.f;
@@ -373,6 +438,43 @@ int launch_pg(const F& f, const RowGeom& rg, int groups, void* stream) {
   return 0;
 }
 
+// block-level end of a per-channel reduction: registers -> shared memory -> one atomic per (block, channel)
+template <int NV>
+__device__ __forceinline__ void reduce_ch_tail(const float (&acc)[NV][8], const int groups, const int ppb, const int g,
+                                               const int lr, const int C, float* __restrict__ out, float* red) {
+  float* mine = red + (static_cast<size_t>(lr) * groups + g) * (NV * 8);
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mine[v * 8 + j] = acc[v][j];
+  __syncthreads();
+  // column sums over the ppb pixel lanes: thread t handles (g, v, j) combos round-robin
+  const int total = groups * NV * 8;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int gg = idx / (NV * 8), vj = idx % (NV * 8);
+    float s = 0.f;
+    for (int l = 0; l < ppb; ++l) s += red[(static_cast<size_t>(l) * groups + gg) * (NV * 8) + vj];
+    atomicAdd(out + (vj / 8) * C + gg * 8 + (vj % 8), s);
+  }
+}
+// the block that takes the last ticket finalises the channels and resets accumulators and counter
+template <int NV, class Fin>
+__device__ __forceinline__ void reduce_ch_last_block(const Fin& fin, const int C, float* out, uint32_t* counter) {
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    fin(c);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) out[v * C + c] = 0.f;
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+
 // Persistent: the grid is one resident wave (2 blocks per SM) and a block walks over (row, column chunk) units, so
 // that a launch ends with 2 * SMs * NV * C atomics on the NV * C result words (one block per row used to mean
 // B * H blocks hammering the same few cache lines: measured 41 % of HBM speed on the 512-channel layers).
@@ -406,20 +508,7 @@ __device__ __forceinline__ void reduce_ch_body(const F& f, const RowGeom& rg, co
       if (col < rg.n_cols) f.accum(in[u], b, h, col - rg.lo, g, c, acc);
     }
   }
-  float* mine = red + (static_cast<size_t>(lr) * groups + g) * (NV * 8);
-#pragma unroll
-  for (int v = 0; v < NV; ++v)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) mine[v * 8 + j] = acc[v][j];
-  __syncthreads();
-  // column sums over the ppb pixel lanes: thread t handles (g, v, j) combos round-robin
-  const int total = groups * NV * 8;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int gg = idx / (NV * 8), vj = idx % (NV * 8);
-    float s = 0.f;
-    for (int l = 0; l < ppb; ++l) s += red[(static_cast<size_t>(l) * groups + gg) * (NV * 8) + vj];
-    atomicAdd(out + (vj / 8) * C + gg * 8 + (vj % 8), s);
-  }
+  reduce_ch_tail<NV>(acc, groups, ppb, g, lr, C, out, red);
 }
 template <int NV, class F>
 __global__ void __launch_bounds__(256, MMH_EW_MINBLOCKS) reduce_ch_kernel(const F f, const RowGeom rg, const int groups, const int chunks,
@@ -439,19 +528,7 @@ __global__ void __launch_bounds__(256, MMH_EW_MINBLOCKS) reduce_ch_fin_kernel(co
   extern __shared__ float red[];
   pdl_sync();
   reduce_ch_body<NV>(f, rg, groups, chunks, C, out, red);
-  __shared__ int is_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    fin(c);
-#pragma unroll
-    for (int v = 0; v < NV; ++v) out[v * C + c] = 0.f;
-  }
-  if (threadIdx.x == 0) *counter = 0u;
+  reduce_ch_last_block<NV>(fin, C, out, counter);
 }
 template <int NV, class F>
 int launch_reduce_ch(const F& f, const RowGeom& rg, int groups, int C, float* out, void* stream) {
@@ -485,6 +562,217 @@ int launch_reduce_ch_fin(const F& f, const RowGeom& rg, int groups, int C, float
   const int blocks = static_cast<int>(units < wave ? units : wave);
   MMH_CUDA(launch_k(reduce_ch_fin_kernel<NV, F, Fin>, dim3(blocks), dim3(threads), smem, stream, f, rg, groups, chunks,
                     C, out, fin, counter));
+  return 0;
+}
+
+// ------------------------------------------------------------------ row kernels (lean variants of the hot functors)
+// Persistent blocks walk over units = (image row, chunk of columns). Everything that depends on (image, row) only --
+// base offsets of the row in every tensor, border flags, the dropout counter -- is computed once per unit (F::Row,
+// block-uniform); an item is base + column * pitch. The per-channel-group parameters are 16-byte loads (prep).
+// `reverse` walks the units from the last to the first: the kernel that follows a producer (or an earlier sweep over
+// the same tensors) starts with the rows that were touched last and are still in the 126 MB L2.
+struct RowSched {
+  int units, chunks, reverse;
+  FastDiv d_chunks, d_hext;
+};
+inline RowSched make_rowsched(const RowGeom& rg, int chunks, int reverse) {
+  RowSched s;
+  s.units = rg.n_rows * chunks; s.chunks = chunks; s.reverse = reverse;
+  s.d_chunks = make_fastdiv(static_cast<uint32_t>(chunks));
+  s.d_hext = make_fastdiv(static_cast<uint32_t>(rg.h_ext));
+  return s;
+}
+#ifndef MMH_ROWS_MINBLOCKS
+#define MMH_ROWS_MINBLOCKS 4
+#endif
+// read per call (tests and A/B measurements switch inside one process)
+inline int rows_wave_per_sm() {
+  const char* e = getenv("MMH_ROWS_WAVE");
+  const int v = e != nullptr ? atoi(e) : 0;
+  return v > 0 && v <= 16 ? v : MMH_ROWS_MINBLOCKS;
+}
+inline int rows_reverse_enabled() {
+  const char* e = getenv("MMH_EW_REVERSE");
+  return e == nullptr || atoi(e) != 0;
+}
+
+// One unit of a row kernel: decode (block-uniform), row setup, loads of U items
+template <class F>
+struct RowUnit {
+  typename F::Row r;
+  typename F::In in[F::kUnroll];
+  int col0;
+  __device__ __forceinline__ void issue(const F& f, const typename F::Ctx& c, const RowGeom& rg, const RowSched& sc,
+                                        const int u0, const int ppb, const int lr, const int g) {
+    constexpr int U = F::kUnroll;
+    const int unit = sc.reverse ? sc.units - 1 - u0 : u0;
+    const int row = static_cast<int>(fdiv(static_cast<uint32_t>(unit), sc.d_chunks)), chunk = unit - row * sc.chunks;
+    const int b = static_cast<int>(fdiv(static_cast<uint32_t>(row), sc.d_hext)), h = row - b * rg.h_ext - rg.lo;
+    f.row(b, h, r);
+    col0 = chunk * (ppb * U) + lr;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int col = col0 + u * ppb;
+      if (col < rg.n_cols) f.load(r, col - rg.lo, g, c, in[u]);
+    }
+  }
+};
+// PF: software pipelining -- the loads of the block's next unit are issued before the arithmetic of the current one
+// (two register sets, ping-pong), so that a warp always has U vectors in flight instead of alternating between
+// "all loads outstanding" and "all arithmetic"
+template <class F, bool PF>
+__global__ void __launch_bounds__(128, MMH_ROWS_MINBLOCKS) rows_pg_kernel(const F f, const RowGeom rg, const int groups,
+                                                                           const RowSched sc) {
+  pdl_sync();
+  constexpr int U = F::kUnroll;
+  const int ppb = blockDim.x / groups;
+  const int g = threadIdx.x % groups;
+  const int lr = threadIdx.x / groups;
+  typename F::Ctx c;
+  f.prep(g, c);
+  const int stride = gridDim.x;
+  if (!PF) {
+    for (int u0 = blockIdx.x; u0 < sc.units; u0 += stride) {
+      RowUnit<F> a;
+      a.issue(f, c, rg, sc, u0, ppb, lr, g);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int col = a.col0 + u * ppb;
+        if (col < rg.n_cols) f.finish(a.in[u], a.r, col - rg.lo, g, c);
+      }
+    }
+  } else {
+    RowUnit<F> a, b;
+    int ua = blockIdx.x;
+    if (ua < sc.units) a.issue(f, c, rg, sc, ua, ppb, lr, g);
+    while (ua < sc.units) {
+      const int ub = ua + stride;
+      if (ub < sc.units) b.issue(f, c, rg, sc, ub, ppb, lr, g);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int col = a.col0 + u * ppb;
+        if (col < rg.n_cols) f.finish(a.in[u], a.r, col - rg.lo, g, c);
+      }
+      if (ub >= sc.units) break;
+      ua = ub + stride;
+      if (ua < sc.units) a.issue(f, c, rg, sc, ua, ppb, lr, g);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int col = b.col0 + u * ppb;
+        if (col < rg.n_cols) f.finish(b.in[u], b.r, col - rg.lo, g, c);
+      }
+    }
+  }
+}
+template <int NV, class F, bool PF>
+__device__ __forceinline__ void rows_reduce_body(const F& f, const RowGeom& rg, const int groups, const RowSched& sc,
+                                                 const int C, float* __restrict__ out, float* red) {
+  constexpr int U = F::kUnroll;
+  const int ppb = blockDim.x / groups;
+  const int g = threadIdx.x % groups;
+  const int lr = threadIdx.x / groups;
+  float acc[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) zero8(acc[v]);
+  typename F::Ctx c;
+  f.prep(g, c);
+  const int stride = gridDim.x;
+  if (!PF) {
+    for (int u0 = blockIdx.x; u0 < sc.units; u0 += stride) {
+      RowUnit<F> a;
+      a.issue(f, c, rg, sc, u0, ppb, lr, g);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int col = a.col0 + u * ppb;
+        if (col < rg.n_cols) f.accum(a.in[u], a.r, col - rg.lo, g, c, acc);
+      }
+    }
+  } else {
+    RowUnit<F> a, b;
+    int ua = blockIdx.x;
+    if (ua < sc.units) a.issue(f, c, rg, sc, ua, ppb, lr, g);
+    while (ua < sc.units) {
+      const int ub = ua + stride;
+      if (ub < sc.units) b.issue(f, c, rg, sc, ub, ppb, lr, g);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int col = a.col0 + u * ppb;
+        if (col < rg.n_cols) f.accum(a.in[u], a.r, col - rg.lo, g, c, acc);
+      }
+      if (ub >= sc.units) break;
+      ua = ub + stride;
+      if (ua < sc.units) a.issue(f, c, rg, sc, ua, ppb, lr, g);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int col = b.col0 + u * ppb;
+        if (col < rg.n_cols) f.accum(b.in[u], b.r, col - rg.lo, g, c, acc);
+      }
+    }
+  }
+  f.post(g, c, acc);
+  reduce_ch_tail<NV>(acc, groups, ppb, g, lr, C, out, red);
+}
+template <int NV, class F, bool PF>
+__global__ void __launch_bounds__(128, MMH_ROWS_MINBLOCKS) rows_reduce_kernel(const F f, const RowGeom rg, const int groups,
+                                                                               const RowSched sc, const int C,
+                                                                               float* __restrict__ out) {
+  extern __shared__ float red[];   // [ppb][groups][NV*8]
+  pdl_sync();
+  rows_reduce_body<NV, F, PF>(f, rg, groups, sc, C, out, red);
+}
+template <int NV, class F, class Fin, bool PF>
+__global__ void __launch_bounds__(128, MMH_ROWS_MINBLOCKS) rows_reduce_fin_kernel(const F f, const RowGeom rg,
+                                                                                   const int groups, const RowSched sc,
+                                                                                   const int C, float* out, const Fin fin,
+                                                                                   uint32_t* counter) {
+  extern __shared__ float red[];
+  pdl_sync();
+  rows_reduce_body<NV, F, PF>(f, rg, groups, sc, C, out, red);
+  reduce_ch_last_block<NV>(fin, C, out, counter);
+}
+// threads: the largest multiple of `groups` <= 128; chunks of ppb * U columns
+struct RowsLaunch { int threads, ppb, chunks, blocks; RowSched sc; };
+template <class F>
+inline RowsLaunch rows_launch(const RowGeom& rg, int groups, int reverse) {
+  RowsLaunch l;
+  l.threads = (128 / groups) * groups;
+  l.ppb = l.threads / groups;
+  l.chunks = (rg.n_cols + l.ppb * F::kUnroll - 1) / (l.ppb * F::kUnroll);
+  l.sc = make_rowsched(rg, l.chunks, reverse && rows_reverse_enabled());
+  const int64_t wave = static_cast<int64_t>(num_sms()) * rows_wave_per_sm();
+  l.blocks = static_cast<int>(l.sc.units < wave ? l.sc.units : wave);
+  return l;
+}
+template <bool PF, class F>
+int launch_rows_pg(const F& f, const RowGeom& rg, int groups, int reverse, void* stream) {
+  if (rg.n_rows <= 0 || rg.n_cols <= 0) return 0;
+  MMH_CHECK(groups >= 1 && groups <= 128, "channel groups=%d unsupported by the row kernels", groups);
+  MMH_CHECK(static_cast<int64_t>(rg.n_rows) * rg.n_cols < (int64_t(1) << 30), "too many work units");
+  const RowsLaunch l = rows_launch<F>(rg, groups, reverse);
+  MMH_CUDA(launch_k(rows_pg_kernel<F, PF>, dim3(l.blocks), dim3(l.threads), 0, stream, f, rg, groups, l.sc));
+  return 0;
+}
+template <int NV, bool PF, class F>
+int launch_rows_reduce(const F& f, const RowGeom& rg, int groups, int C, float* out, int reverse, void* stream) {
+  if (rg.n_rows <= 0 || rg.n_cols <= 0) return 0;
+  MMH_CHECK(groups >= 1 && groups <= 128, "channel groups=%d unsupported by the row kernels", groups);
+  MMH_CHECK(static_cast<int64_t>(rg.n_rows) * rg.n_cols < (int64_t(1) << 30), "too many work units");
+  const RowsLaunch l = rows_launch<F>(rg, groups, reverse);
+  const size_t smem = static_cast<size_t>(l.threads) * NV * 8 * sizeof(float);
+  MMH_CUDA(launch_k(rows_reduce_kernel<NV, F, PF>, dim3(l.blocks), dim3(l.threads), smem, stream, f, rg, groups, l.sc, C, out));
+  return 0;
+}
+template <int NV, bool PF, class F, class Fin>
+int launch_rows_reduce_fin(const F& f, const RowGeom& rg, int groups, int C, float* out, const Fin& fin,
+                           uint32_t* counter, int reverse, void* stream) {
+  if (rg.n_rows <= 0 || rg.n_cols <= 0) return 0;
+  MMH_CHECK(groups >= 1 && groups <= 128, "channel groups=%d unsupported by the row kernels", groups);
+  MMH_CHECK(static_cast<int64_t>(rg.n_rows) * rg.n_cols < (int64_t(1) << 30), "too many work units");
+  MMH_CHECK(counter != nullptr, "null ticket counter");
+  const RowsLaunch l = rows_launch<F>(rg, groups, reverse);
+  const size_t smem = static_cast<size_t>(l.threads) * NV * 8 * sizeof(float);
+  MMH_CUDA(launch_k(rows_reduce_fin_kernel<NV, F, Fin, PF>, dim3(l.blocks), dim3(l.threads), smem, stream, f, rg, groups,
+                    l.sc, C, out, fin, counter));
   return 0;
 }
 
