@@ -153,75 +153,6 @@ inline bool lay_fits32(const MmhLay& l) {
   return static_cast<int64_t>(l.B) * l.Hg * l.Wg * (l.phase ? 4 : 1) * l.ld + l.c0 < (int64_t(1) << 31);
 }
 
-// ------------------------------------------------------------------------------------------------ norm + act, lean
-// NormActF as a row kernel: the source row (mirrored for halo rows), the destination row and the dropout counter are
-// set up once per (image, row); dropout and the fp32 residual are compile-time.
-struct NormLeanRow { RowOff s, d; int32_t plain; uint32_t dword; int h, live; };
-template <bool RESID> struct NormLeanIn { ActX8 x; };
-template <> struct NormLeanIn<true> { ActX8 x; F32x8 r; };
-template <bool DROP, bool RESID, int U>
-struct NormLeanF {
-  static constexpr int kUnroll = U;
-  struct Ctx { float a[8], b[8]; };
-  typedef NormLeanIn<RESID> In;
-  typedef NormLeanRow Row;
-  const act_t* src; LayD sl; const float* coef; int relu; uint32_t key;
-  const float* resid; act_t* dst; LayD dl; int reflect; float* dst_f32;
-  MMH_HD void prep(int g, Ctx& c) const {
-    if (coef != nullptr) { ld8_f32(coef + g * 8, c.a); ld8_f32(coef + sl.C + g * 8, c.b); }
-    else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { c.a[j] = 1.f; c.b[j] = 0.f; }
-    }
-  }
-  MMH_HD void row(int b, int h, Row& r) const {
-    const int H = sl.H, W = sl.W;
-    r.h = h;
-    r.live = (reflect || (h >= 0 && h < H)) ? 1 : 0;
-    const int hs = r.live ? reflect_idx(h, H) : 0;
-    rowoff(sl, b, hs, r.s);
-    if (dst != nullptr) rowoff(dl, b, h, r.d); else r.d = r.s;
-    r.plain = (b * H + hs) * W * sl.C;
-    r.dword = (static_cast<uint32_t>(b) * H + hs) * W * static_cast<uint32_t>((sl.C + 7) / 8);
-  }
-  MMH_HD bool live(const Row& r, int w) const { return r.live && (reflect || (w >= 0 && w < sl.W)); }
-  MMH_HD void load(const Row& r, int w, int g, const Ctx&, In& in) const {
-    if (live(r, w)) {
-      const int ws = reflect_idx(w, sl.W);
-      ld_raw(src + (rowat(sl, r.s, ws) + g * 8), in.x);
-      if constexpr (RESID) ld_raw(resid + (r.plain + ws * sl.C + g * 8), in.r);
-    }
-  }
-  MMH_HD void finish(const In& in, const Row& r, int w, int g, const Ctx& c) const {
-    const int H = sl.H, W = sl.W, C = sl.C;
-    float y[8];
-    zero8(y);
-    if (live(r, w)) {
-      const int ws = reflect_idx(w, W);
-      cvt8(in.x, y);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) y[j] = c.a[j] * y[j] + c.b[j];
-      if (relu) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = y[j] > 0.f ? y[j] : 0.f;
-      }
-      if (DROP) {
-        const uint32_t word = r.dword + static_cast<uint32_t>(ws) * static_cast<uint32_t>((C + 7) / 8) + g;
-        const uint32_t bits = mix32(word * 0x9E3779B1u + key);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = ((bits >> j) & 1u) ? 2.0f * y[j] : 0.f;
-      }
-      if constexpr (RESID) {
-        float rr[8];
-        cvt8(in.r, rr);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] += rr[j];
-      }
-    }
-    if (dst != nullptr) st8_bf16(dst + (rowat(dl, r.d, w) + g * 8), y);
-    if (dst_f32 != nullptr && r.h >= 0 && r.h < H && w >= 0 && w < W) st8_f32(dst_f32 + (r.plain + w * C + g * 8), y);
-  }
-};
 // ------------------------------------------------------------------------------------------------ PAT gate
 struct GateFwdF {
   static constexpr int kUnroll = 2;
@@ -521,9 +452,9 @@ struct BnLeanBase {
     }
   }
 };
-template <bool RELU, bool DROP, int U>
+template <bool RELU, bool DROP>
 struct BnLeanReduceF {
-  static constexpr int kUnroll = U;
+  static constexpr int kUnroll = 4;
   struct Ctx { float a[8], b[8], mean[8]; };
   typedef BnLeanIn In;
   typedef BnLeanRow Row;
@@ -552,9 +483,9 @@ struct BnLeanReduceF {
     for (int j = 0; j < 8; ++j) acc[1][j] *= rstd[j];
   }
 };
-template <bool RELU, bool DROP, int U>
+template <bool RELU, bool DROP>
 struct BnLeanApplyF {
-  static constexpr int kUnroll = U;
+  static constexpr int kUnroll = 4;
   struct Ctx { float a[8], b[8], bx[8], cc[8]; };
   typedef BnLeanIn In;
   typedef BnLeanRow Row;
@@ -779,23 +710,6 @@ static bool ew_lean_enabled() {       // MMH_EW_LEAN=0: the general kernels ever
   return e == nullptr || atoi(e) != 0;
 }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-static bool norm_lean_ok(const MmhNormAct* p) {
-  if (!ew_lean_enabled() || p->sl.C > 1024) return false;
-  if (!lay_fits32(p->sl) || (p->dst && !lay_fits32(p->dl))) return false;
-  if (static_cast<int64_t>(p->sl.B) * p->sl.H * p->sl.W * p->sl.C >= (int64_t(1) << 31)) return false;
-  return p->coef == nullptr || aligned16(p->coef);
-}
-template <bool DROP, bool RESID, bool PF>
-static int norm_lean_pf(const NormActF& g, const RowGeom& rg, void* stream) {
-  NormLeanF<DROP, RESID, (PF && RESID) ? 2 : 4> f;
-  f.src = g.src; f.sl = g.sl; f.coef = g.coef; f.relu = g.relu; f.key = g.key; f.resid = g.resid;
-  f.dst = g.dst; f.dl = g.dl; f.reflect = g.reflect; f.dst_f32 = g.dst_f32;
-  return launch_rows_pg<PF>(f, rg, g.sl.C / 8, 1, stream);
-}
-template <bool DROP, bool RESID>
-static int norm_lean_t(const NormActF& g, const RowGeom& rg, void* stream) {
-  return rows_prefetch() ? norm_lean_pf<DROP, RESID, true>(g, rg, stream) : norm_lean_pf<DROP, RESID, false>(g, rg, stream);
-}
 extern "C" int mmh_norm_act(const MmhNormAct* p, void* stream) {
   MMH_CHECK(p && p->src && (p->dst || p->dst_f32), "null argument");
   MMH_REQ_VEC(p->sl.C);
@@ -808,11 +722,6 @@ extern "C" int mmh_norm_act(const MmhNormAct* p, void* stream) {
   MMH_CHECK(!p->dst || (p->dl.H == p->sl.H && p->dl.W == p->sl.W && p->dl.C == p->sl.C), "src/dst shape mismatch");
   MMH_CHECK(!f.reflect || (lo < f.sl.H && hi < f.sl.H && lo < f.sl.W && hi < f.sl.W), "halo too large");
   const RowGeom rg = make_rowgeom(f.sl.B, f.sl.H, f.sl.W, lo, hi);
-  if (norm_lean_ok(p)) {
-    // the convolution that produced `src` wrote its rows in ascending order: start with the last ones (still in L2)
-    if (p->dropout) return p->resid ? norm_lean_t<true, true>(f, rg, stream) : norm_lean_t<true, false>(f, rg, stream);
-    return p->resid ? norm_lean_t<false, true>(f, rg, stream) : norm_lean_t<false, false>(f, rg, stream);
-  }
   return launch_pg(f, rg, p->sl.C / 8, stream);
 }
 
@@ -911,29 +820,19 @@ static BnLeanBase<RELU, DROP> bn_lean_common(const MmhBnBwd* p) {
 }
 // reduce sweeps the rows from the last to the first (the data gradient that produced the source has just written
 // them in ascending order), apply from the first to the last (= the rows the reduction touched last)
-template <bool RELU, bool DROP, bool PF>
-static int bn_lean_reduce_pf(const MmhBnBwd* p, const BnBwdFin* fin, uint32_t* counter, void* stream) {
-  BnLeanReduceF<RELU, DROP, PF ? 2 : 4> f;       // software pipelining: two register sets of two vectors
-  f.cm = bn_lean_common<RELU, DROP>(p);
-  const RowGeom rg = make_rowgeom(p->xl.B, p->xl.H, p->xl.W, 0, 0);
-  if (fin != nullptr)
-    return launch_rows_reduce_fin<2, PF>(f, rg, p->xl.C / 8, p->xl.C, p->sums, *fin, counter, 1, stream);
-  return launch_rows_reduce<2, PF>(f, rg, p->xl.C / 8, p->xl.C, p->sums, 1, stream);
-}
 template <bool RELU, bool DROP>
 static int bn_lean_reduce_t(const MmhBnBwd* p, const BnBwdFin* fin, uint32_t* counter, void* stream) {
-  return rows_prefetch() ? bn_lean_reduce_pf<RELU, DROP, true>(p, fin, counter, stream)
-                         : bn_lean_reduce_pf<RELU, DROP, false>(p, fin, counter, stream);
-}
-template <bool RELU, bool DROP, bool PF>
-static int bn_lean_apply_pf(const MmhBnBwd* p, void* stream) {
-  BnLeanApplyF<RELU, DROP, PF ? 2 : 4> f;
-  f.cm = bn_lean_common<RELU, DROP>(p); f.k = p->k; f.dy = static_cast<act_t*>(p->dy); f.yl = to_layd(p->yl);
-  return launch_rows_pg<PF>(f, make_rowgeom(p->xl.B, p->xl.H, p->xl.W, 0, 0), p->xl.C / 8, 0, stream);
+  BnLeanReduceF<RELU, DROP> f;
+  f.cm = bn_lean_common<RELU, DROP>(p);
+  const RowGeom rg = make_rowgeom(p->xl.B, p->xl.H, p->xl.W, 0, 0);
+  if (fin != nullptr) return launch_rows_reduce_fin<2>(f, rg, p->xl.C / 8, p->xl.C, p->sums, *fin, counter, 1, stream);
+  return launch_rows_reduce<2>(f, rg, p->xl.C / 8, p->xl.C, p->sums, 1, stream);
 }
 template <bool RELU, bool DROP>
 static int bn_lean_apply_t(const MmhBnBwd* p, void* stream) {
-  return rows_prefetch() ? bn_lean_apply_pf<RELU, DROP, true>(p, stream) : bn_lean_apply_pf<RELU, DROP, false>(p, stream);
+  BnLeanApplyF<RELU, DROP> f;
+  f.cm = bn_lean_common<RELU, DROP>(p); f.k = p->k; f.dy = static_cast<act_t*>(p->dy); f.yl = to_layd(p->yl);
+  return launch_rows_pg(f, make_rowgeom(p->xl.B, p->xl.H, p->xl.W, 0, 0), p->xl.C / 8, 0, stream);
 }
 static int bn_lean_reduce(const MmhBnBwd* p, const BnBwdFin* fin, uint32_t* counter, void* stream) {
   if (p->relu) return p->dropout ? bn_lean_reduce_t<true, true>(p, fin, counter, stream)

@@ -175,12 +175,6 @@ MMH_HD void zero8(float (&f)[8]) {
   for (int i = 0; i < 8; ++i) f[i] = 0.f;
 }
 
-// MMH_ROWS_PF=0: row kernels without software pipelining (read per call: A/B inside one process)
-inline bool rows_prefetch() {
-  const char* e = getenv("MMH_ROWS_PF");
-  return e == nullptr || atoi(e) != 0;
-}
-
 // ------------------------------------------------------------------ launchers
 #ifdef MMH_HOST_EMU
 
@@ -242,7 +236,7 @@ int launch_reduce_ch_fin(const F& f, const RowGeom& rg, int groups, int C, float
 }
 // ---- row launchers (lean kernels): the functor computes the base offsets of an (image, row) once (F::Row); items
 // are addressed as base + column * pitch
-template <bool PF, class F>
+template <class F>
 int launch_rows_pg(const F& f, const RowGeom& rg, int groups, int /*reverse*/, void*) {
   for (int g = 0; g < groups; ++g) {
     typename F::Ctx c;
@@ -260,7 +254,7 @@ int launch_rows_pg(const F& f, const RowGeom& rg, int groups, int /*reverse*/, v
   }
   return 0;
 }
-template <int NV, bool PF, class F>
+template <int NV, class F>
 int launch_rows_reduce(const F& f, const RowGeom& rg, int groups, int C, float* out, int /*reverse*/, void*) {
   for (int g = 0; g < groups; ++g) {
     typename F::Ctx c;
@@ -289,10 +283,10 @@ int launch_rows_reduce(const F& f, const RowGeom& rg, int groups, int C, float* 
   }
   return 0;
 }
-template <int NV, bool PF, class F, class Fin>
+template <int NV, class F, class Fin>
 int launch_rows_reduce_fin(const F& f, const RowGeom& rg, int groups, int C, float* out, const Fin& fin, uint32_t*,
                            int reverse, void* stream) {
-  launch_rows_reduce<NV, PF>(f, rg, groups, C, out, reverse, stream);
+  launch_rows_reduce<NV>(f, rg, groups, C, out, reverse, stream);
   for (int c = 0; c < C; ++c) {
     fin(c);
     for (int v = 0; v < NV; ++v) out[v * C + c] = 0.f;
@@ -617,10 +611,7 @@ struct RowUnit {
     }
   }
 };
-// PF: software pipelining -- the loads of the block's next unit are issued before the arithmetic of the current one
-// (two register sets, ping-pong), so that a warp always has U vectors in flight instead of alternating between
-// "all loads outstanding" and "all arithmetic"
-template <class F, bool PF>
+template <class F>
 __global__ void __launch_bounds__(128, MMH_ROWS_MINBLOCKS) rows_pg_kernel(const F f, const RowGeom rg, const int groups,
                                                                            const RowSched sc) {
   pdl_sync();
@@ -630,41 +621,17 @@ __global__ void __launch_bounds__(128, MMH_ROWS_MINBLOCKS) rows_pg_kernel(const 
   const int lr = threadIdx.x / groups;
   typename F::Ctx c;
   f.prep(g, c);
-  const int stride = gridDim.x;
-  if (!PF) {
-    for (int u0 = blockIdx.x; u0 < sc.units; u0 += stride) {
-      RowUnit<F> a;
-      a.issue(f, c, rg, sc, u0, ppb, lr, g);
+  for (int u0 = blockIdx.x; u0 < sc.units; u0 += gridDim.x) {
+    RowUnit<F> a;
+    a.issue(f, c, rg, sc, u0, ppb, lr, g);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int col = a.col0 + u * ppb;
-        if (col < rg.n_cols) f.finish(a.in[u], a.r, col - rg.lo, g, c);
-      }
-    }
-  } else {
-    RowUnit<F> a, b;
-    int ua = blockIdx.x;
-    if (ua < sc.units) a.issue(f, c, rg, sc, ua, ppb, lr, g);
-    while (ua < sc.units) {
-      const int ub = ua + stride;
-      if (ub < sc.units) b.issue(f, c, rg, sc, ub, ppb, lr, g);
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int col = a.col0 + u * ppb;
-        if (col < rg.n_cols) f.finish(a.in[u], a.r, col - rg.lo, g, c);
-      }
-      if (ub >= sc.units) break;
-      ua = ub + stride;
-      if (ua < sc.units) a.issue(f, c, rg, sc, ua, ppb, lr, g);
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int col = b.col0 + u * ppb;
-        if (col < rg.n_cols) f.finish(b.in[u], b.r, col - rg.lo, g, c);
-      }
+    for (int u = 0; u < U; ++u) {
+      const int col = a.col0 + u * ppb;
+      if (col < rg.n_cols) f.finish(a.in[u], a.r, col - rg.lo, g, c);
     }
   }
 }
-template <int NV, class F, bool PF>
+template <int NV, class F>
 __device__ __forceinline__ void rows_reduce_body(const F& f, const RowGeom& rg, const int groups, const RowSched& sc,
                                                  const int C, float* __restrict__ out, float* red) {
   constexpr int U = F::kUnroll;
@@ -676,58 +643,34 @@ __device__ __forceinline__ void rows_reduce_body(const F& f, const RowGeom& rg, 
   for (int v = 0; v < NV; ++v) zero8(acc[v]);
   typename F::Ctx c;
   f.prep(g, c);
-  const int stride = gridDim.x;
-  if (!PF) {
-    for (int u0 = blockIdx.x; u0 < sc.units; u0 += stride) {
-      RowUnit<F> a;
-      a.issue(f, c, rg, sc, u0, ppb, lr, g);
+  for (int u0 = blockIdx.x; u0 < sc.units; u0 += gridDim.x) {
+    RowUnit<F> a;
+    a.issue(f, c, rg, sc, u0, ppb, lr, g);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int col = a.col0 + u * ppb;
-        if (col < rg.n_cols) f.accum(a.in[u], a.r, col - rg.lo, g, c, acc);
-      }
-    }
-  } else {
-    RowUnit<F> a, b;
-    int ua = blockIdx.x;
-    if (ua < sc.units) a.issue(f, c, rg, sc, ua, ppb, lr, g);
-    while (ua < sc.units) {
-      const int ub = ua + stride;
-      if (ub < sc.units) b.issue(f, c, rg, sc, ub, ppb, lr, g);
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int col = a.col0 + u * ppb;
-        if (col < rg.n_cols) f.accum(a.in[u], a.r, col - rg.lo, g, c, acc);
-      }
-      if (ub >= sc.units) break;
-      ua = ub + stride;
-      if (ua < sc.units) a.issue(f, c, rg, sc, ua, ppb, lr, g);
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int col = b.col0 + u * ppb;
-        if (col < rg.n_cols) f.accum(b.in[u], b.r, col - rg.lo, g, c, acc);
-      }
+    for (int u = 0; u < U; ++u) {
+      const int col = a.col0 + u * ppb;
+      if (col < rg.n_cols) f.accum(a.in[u], a.r, col - rg.lo, g, c, acc);
     }
   }
   f.post(g, c, acc);
   reduce_ch_tail<NV>(acc, groups, ppb, g, lr, C, out, red);
 }
-template <int NV, class F, bool PF>
+template <int NV, class F>
 __global__ void __launch_bounds__(128, MMH_ROWS_MINBLOCKS) rows_reduce_kernel(const F f, const RowGeom rg, const int groups,
                                                                                const RowSched sc, const int C,
                                                                                float* __restrict__ out) {
   extern __shared__ float red[];   // [ppb][groups][NV*8]
   pdl_sync();
-  rows_reduce_body<NV, F, PF>(f, rg, groups, sc, C, out, red);
+  rows_reduce_body<NV>(f, rg, groups, sc, C, out, red);
 }
-template <int NV, class F, class Fin, bool PF>
+template <int NV, class F, class Fin>
 __global__ void __launch_bounds__(128, MMH_ROWS_MINBLOCKS) rows_reduce_fin_kernel(const F f, const RowGeom rg,
                                                                                    const int groups, const RowSched sc,
                                                                                    const int C, float* out, const Fin fin,
                                                                                    uint32_t* counter) {
   extern __shared__ float red[];
   pdl_sync();
-  rows_reduce_body<NV, F, PF>(f, rg, groups, sc, C, out, red);
+  rows_reduce_body<NV>(f, rg, groups, sc, C, out, red);
   reduce_ch_last_block<NV>(fin, C, out, counter);
 }
 // threads: the largest multiple of `groups` <= 128; chunks of ppb * U columns
@@ -743,26 +686,26 @@ inline RowsLaunch rows_launch(const RowGeom& rg, int groups, int reverse) {
   l.blocks = static_cast<int>(l.sc.units < wave ? l.sc.units : wave);
   return l;
 }
-template <bool PF, class F>
+template <class F>
 int launch_rows_pg(const F& f, const RowGeom& rg, int groups, int reverse, void* stream) {
   if (rg.n_rows <= 0 || rg.n_cols <= 0) return 0;
   MMH_CHECK(groups >= 1 && groups <= 128, "channel groups=%d unsupported by the row kernels", groups);
   MMH_CHECK(static_cast<int64_t>(rg.n_rows) * rg.n_cols < (int64_t(1) << 30), "too many work units");
   const RowsLaunch l = rows_launch<F>(rg, groups, reverse);
-  MMH_CUDA(launch_k(rows_pg_kernel<F, PF>, dim3(l.blocks), dim3(l.threads), 0, stream, f, rg, groups, l.sc));
+  MMH_CUDA(launch_k(rows_pg_kernel<F>, dim3(l.blocks), dim3(l.threads), 0, stream, f, rg, groups, l.sc));
   return 0;
 }
-template <int NV, bool PF, class F>
+template <int NV, class F>
 int launch_rows_reduce(const F& f, const RowGeom& rg, int groups, int C, float* out, int reverse, void* stream) {
   if (rg.n_rows <= 0 || rg.n_cols <= 0) return 0;
   MMH_CHECK(groups >= 1 && groups <= 128, "channel groups=%d unsupported by the row kernels", groups);
   MMH_CHECK(static_cast<int64_t>(rg.n_rows) * rg.n_cols < (int64_t(1) << 30), "too many work units");
   const RowsLaunch l = rows_launch<F>(rg, groups, reverse);
   const size_t smem = static_cast<size_t>(l.threads) * NV * 8 * sizeof(float);
-  MMH_CUDA(launch_k(rows_reduce_kernel<NV, F, PF>, dim3(l.blocks), dim3(l.threads), smem, stream, f, rg, groups, l.sc, C, out));
+  MMH_CUDA(launch_k(rows_reduce_kernel<NV, F>, dim3(l.blocks), dim3(l.threads), smem, stream, f, rg, groups, l.sc, C, out));
   return 0;
 }
-template <int NV, bool PF, class F, class Fin>
+template <int NV, class F, class Fin>
 int launch_rows_reduce_fin(const F& f, const RowGeom& rg, int groups, int C, float* out, const Fin& fin,
                            uint32_t* counter, int reverse, void* stream) {
   if (rg.n_rows <= 0 || rg.n_cols <= 0) return 0;
@@ -771,7 +714,7 @@ int launch_rows_reduce_fin(const F& f, const RowGeom& rg, int groups, int C, flo
   MMH_CHECK(counter != nullptr, "null ticket counter");
   const RowsLaunch l = rows_launch<F>(rg, groups, reverse);
   const size_t smem = static_cast<size_t>(l.threads) * NV * 8 * sizeof(float);
-  MMH_CUDA(launch_k(rows_reduce_fin_kernel<NV, F, Fin, PF>, dim3(l.blocks), dim3(l.threads), smem, stream, f, rg, groups,
+  MMH_CUDA(launch_k(rows_reduce_fin_kernel<NV, F, Fin>, dim3(l.blocks), dim3(l.threads), smem, stream, f, rg, groups,
                     l.sc, C, out, fin, counter));
   return 0;
 }

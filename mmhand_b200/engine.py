@@ -777,22 +777,29 @@ class DiscriminatorEngine(EngineBase):
     def __init__(self, ops, module, B, H, W, world=None):
         super().__init__(ops, module, B, H, W, world)
         m = module
-        assert m.n_downsampling == 2, "only n_downsampling=2 is built (the shipped configuration)"
+        nd = m.n_downsampling
+        assert 0 <= nd <= 3, "n_downsampling in 0..3 (reference Discriminator.py:86-133)"
         ndf, self.nb, self.use_dropout = m.ngf, m.n_blocks, m.use_dropout
-        assert ndf % 16 == 0
+        assert ndf % 16 == 0 and H % (1 << nd) == 0 and W % (1 << nd) == 0
         self.in_nc = m.input_nc
-        dim = ndf * 4
-        self.dim, self.h4, self.w4 = dim, H // 4, W // 4
+        # channels of the stride-2 stages (reference :86-133): ndf -> 2 ndf -> 4 ndf [-> 4 ndf when n_downsampling = 3]
+        chans = [ndf * (2 ** i) for i in range(min(nd, 2) + 1)] + ([ndf * 4] if nd == 3 else [])
+        dim = chans[-1]
+        self.dim, self.h4, self.w4 = dim, H >> nd, W >> nd      # (h4, w4: resolution of the residual trunk)
         h4, w4 = self.h4, self.w4
         E, seq = self, m.model
         self.c7 = ConvL(E, "c7", geom_s1(B, H, W, 7, 'reflect', chan_pad(self.in_nc), ndf), self.in_nc, ndf, seq[1].weight)
-        self.d1 = ConvL(E, "d1", geom_s2(B, H, W, ndf, 2 * ndf), ndf, 2 * ndf, seq[4].weight)
-        self.d2 = ConvL(E, "d2", geom_s2(B, H // 2, W // 2, 2 * ndf, dim), 2 * ndf, dim, seq[7].weight)
-        self.bn7, self.bn1, self.bn2 = BNL(E, seq[2], ndf), BNL(E, seq[5], 2 * ndf), BNL(E, seq[8], dim)
+        self.bn7 = BNL(E, seq[2], ndf)
+        self.downs, self.bnd = [], []
+        for i in range(nd):
+            self.downs.append(ConvL(E, "d%d" % (i + 1), geom_s2(B, H >> i, W >> i, chans[i], chans[i + 1]), chans[i],
+                                    chans[i + 1], seq[4 + 3 * i].weight))
+            self.bnd.append(BNL(E, seq[5 + 3 * i], chans[i + 1]))
+        first_block = 4 + 3 * nd
         j = 6 if self.use_dropout else 5
         self.blocks = []
         for i in range(self.nb):
-            cb = seq[10 + i].conv_block
+            cb = seq[first_block + i].conv_block
             c1 = ConvL(E, "r%d.c1" % i, geom_s1(B, h4, w4, 3, 'reflect', dim, dim), dim, dim, cb[1].weight)
             c2 = ConvL(E, "r%d.c2" % i, geom_s1(B, h4, w4, 3, 'reflect', dim, dim), dim, dim, cb[j].weight)
             self.blocks.append(dict(c1=c1, c2=c2, bn1=BNL(E, cb[2], dim), bn2=BNL(E, cb[j + 1], dim)))
@@ -800,7 +807,7 @@ class DiscriminatorEngine(EngineBase):
         self.bwd_ready = False
 
     def convs(self):
-        out = [self.c7, self.d1, self.d2]
+        out = [self.c7] + list(self.downs)
         for b in self.blocks:
             out += [b["c1"], b["c2"]]
         return out
@@ -809,8 +816,8 @@ class DiscriminatorEngine(EngineBase):
         if self.bwd_ready:
             return
         self.c7.prepare_backward("c7", "c7")
-        self.d1.prepare_backward("d1", "d1")
-        self.d2.prepare_backward("d2", "d2")
+        for i, d in enumerate(self.downs):
+            d.prepare_backward("d%d" % (i + 1), "d%d" % (i + 1))
         for b in self.blocks:
             b["c1"].prepare_backward("c1", "c1")
             b["c2"].prepare_backward("c2", "c2")
@@ -828,16 +835,19 @@ class DiscriminatorEngine(EngineBase):
         self.repack()
         self.training, self.step, self.net_id = training, step, net_id
         self.ops.step = step
-        c7, d1, d2 = self.c7, self.d1, self.d2
+        c7 = self.c7
         ops.assemble(xa, xb, c7.x, c7.g.in_lay, 3, 3, True)
-        self._stage_fwd(c7, self.bn7, training)
-        ops.norm_act(c7.raw, c7.g.out_lay, self.bn7.coef, True, False, 0, d1.x, d1.g.in_lay, 1, 1, False)
-        self._stage_fwd(d1, self.bn1, training)
-        ops.norm_act(d1.raw, d1.g.out_lay, self.bn1.coef, True, False, 0, d2.x, d2.g.in_lay, 1, 1, False)
-        self._stage_fwd(d2, self.bn2, training)
-        n = self.blocks[0]["c1"]
-        ops.norm_act(d2.raw, d2.g.out_lay, self.bn2.coef, True, False, 0, n.x, n.g.in_lay, 1, 1, True,
-                     dst_f32=self.trunk[0])
+        # c7 -> stride-2 stages -> first residual block: every stage normalises into the next convolution's input grid
+        # (zero halo + parity planes for a stride-2 consumer, reflect halo for a block); the last one also writes the
+        # fp32 trunk
+        stages = [(c7, self.bn7)] + list(zip(self.downs, self.bnd))
+        assert self.nb >= 1, "a discriminator without residual blocks has no consumer for its stem"
+        consumers = list(self.downs) + [self.blocks[0]["c1"]]
+        for k, (cv, bn) in enumerate(stages):
+            self._stage_fwd(cv, bn, training)
+            nxt, last = consumers[k], k == len(stages) - 1
+            ops.norm_act(cv.raw, cv.g.out_lay, bn.coef, True, False, 0, nxt.x, nxt.g.in_lay, 1, 1, last,
+                         dst_f32=self.trunk[0] if last else None)
         cur = 0
         for i, b in enumerate(self.blocks):
             c1, c2 = b["c1"], b["c2"]
@@ -879,10 +889,13 @@ class DiscriminatorEngine(EngineBase):
             # d x_k = d x_{k+1} + fold(d pad(x_k))
             ops.grad_gather([c1.dx_source()], B, h4, w4, dim, self.dtrunk, plain_lay(B, h4, w4, dim), True, trunk=dcur)
             dcur = self.dtrunk
-        self._stage_bwd(self.d2, self.bn2, [], True, False, 0, trunk=dcur, want_wgrad=want_wgrad)
-        self._stage_bwd(self.d1, self.bn1, [self.d2.dx_source()], True, False, 0, want_wgrad=want_wgrad)
-        self._stage_bwd(self.c7, self.bn7, [self.d1.dx_source()], True, False, 0, want_wgrad=want_wgrad,
-                        want_dx=want_input_grad)
+        stages = [(self.c7, self.bn7)] + list(zip(self.downs, self.bnd))
+        for k in range(len(stages) - 1, -1, -1):
+            cv, bn = stages[k]
+            last = k == len(stages) - 1          # its gradient is the fp32 trunk gradient; the others gather their consumer's
+            self._stage_bwd(cv, bn, [] if last else [stages[k + 1][0].dx_source()], True, False, 0,
+                            trunk=dcur if last else None, want_wgrad=want_wgrad,
+                            want_dx=want_input_grad if k == 0 else True)
         if want_wgrad:
             self.end_wgrad()
         return self.c7.dx_source() if want_input_grad else None

@@ -71,13 +71,14 @@ class Discriminator(nn.Module):
         f = norm_layer.func if isinstance(norm_layer, functools.partial) else norm_layer
         use_bias = f == nn.InstanceNorm2d
         seq = [Slot('ReflectionPad2d(3)'), Conv2dParams(input_nc, ngf, 7, use_bias), norm_params(norm_layer, ngf), Slot('ReLU')]
-        if n_downsampling > 2:
-            raise NotImplementedError("n_downsampling=3 is not built (the shipped configuration uses 2)")
+        if n_downsampling > 3:
+            raise NotImplementedError("n_downsampling=%d: the reference builds 0..3 stride-2 stages (:86-133)" % n_downsampling)
+        # reference :86-133: ndf -> 2 ndf -> 4 ndf, and a third stage 4 ndf -> 4 ndf when n_downsampling == 3
+        chans = [ngf * (2 ** i) for i in range(min(n_downsampling, 2) + 1)] + ([ngf * 4] if n_downsampling == 3 else [])
         for i in range(n_downsampling):
-            mult = 2 ** i
-            seq += [Conv2dParams(ngf * mult, ngf * mult * 2, 3, use_bias, stride=2), norm_params(norm_layer, ngf * mult * 2),
+            seq += [Conv2dParams(chans[i], chans[i + 1], 3, use_bias, stride=2), norm_params(norm_layer, chans[i + 1]),
                     Slot('ReLU')]
-        mult = 2 ** n_downsampling
+        mult = chans[-1] // ngf
         for i in range(n_blocks):
             seq.append(ResnetBlock(ngf * mult, padding_type=padding_type, norm_layer=norm_layer,
                                    use_dropout=use_dropout, use_bias=use_bias))

@@ -114,11 +114,13 @@ def _convT(x, w):
     return _q(F.conv_transpose2d(_q(x, "act"), _q(w, "w"), stride=2, padding=1, output_padding=1), "raw")
 
 
-def _down_stream(sd, p, x, train):
-    """pad3-conv7-BN-ReLU, 2 x [conv3 s2 p1 - BN - ReLU]  (Generator.py:158-223, Discriminator.py:79-99)."""
+def _down_stream(sd, p, x, train, n_down=2):
+    """pad3-conv7-BN-ReLU, n_down x [conv3 s2 p1 - BN - ReLU]  (Generator.py:158-223, Discriminator.py:79-133: the
+    channel counts -- incl. the 4 ndf -> 4 ndf third stage of n_downsampling == 3 -- are those of the weights)."""
     x = F.relu(_bn(sd, p + ".2", _conv(_rpad(x, 3), sd[p + ".1.weight"]), train))
-    x = F.relu(_bn(sd, p + ".5", _conv(x, sd[p + ".4.weight"], stride=2, padding=1), train))
-    x = F.relu(_bn(sd, p + ".8", _conv(x, sd[p + ".7.weight"], stride=2, padding=1), train))
+    for i in range(n_down):
+        x = F.relu(_bn(sd, p + ".%d" % (5 + 3 * i), _conv(x, sd[p + ".%d.weight" % (4 + 3 * i)], stride=2, padding=1),
+                       train))
     return x
 
 
@@ -206,11 +208,12 @@ def ssim(img1, img2, window_size=11, size_average=True):
     return m.mean() if size_average else m.mean(1).mean(1).mean(1)
 
 
-def discriminator_forward(sd, x, train=True, use_dropout=True, n_blocks=3, drop=None):
+def discriminator_forward(sd, x, train=True, use_dropout=True, n_blocks=3, drop=None, n_downsampling=2):
+    """Discriminator.py:79-151: stem, n_downsampling stride-2 stages, n_blocks ResnetBlocks (no head)."""
     drop = drop or DropCtx("off")
-    x = _down_stream(sd, "model", x, train)
+    x = _down_stream(sd, "model", x, train, n_downsampling)
     for i in range(n_blocks):
-        p = "model.%d.conv_block" % (10 + i)
+        p = "model.%d.conv_block" % (4 + 3 * n_downsampling + i)
         x = x + _conv_block(sd, p, x, train, use_dropout, drop, True)
     return x
 

@@ -379,3 +379,34 @@ def test_batch_size_change_keeps_the_optimiser_state(emu_f32):
             stores.add((id(net), id(eng.store), eng.store.m.data_ptr()))
             assert eng.store.step == it + 1 and float(eng.store.v.abs().sum()) > 0
     assert len(stores) == 3
+
+
+@pytest.mark.parametrize("nd", [1, 3])
+def test_discriminator_n_downsampling_variants(emu_f32, nd):
+    """n_downsampling != 2 (reference Discriminator.py:86-133; 3 = a third, 4 ndf -> 4 ndf stride-2 stage): forward,
+    input gradient and every parameter gradient against the oracle, whose variants are pinned to the reference class
+    by tests/golden/disc_variants_ngf4.pt (tests/test_oracle_golden.py)."""
+    from models.Discriminator import Discriminator
+    from models.network_utils import GANLoss, get_norm_layer, init_weights
+    torch.manual_seed(11)
+    d = Discriminator(6, 16, get_norm_layer('batch'), True, 2, [], 'reflect', False, nd)
+    init_weights(d, 'normal')
+    sd = _sd(d)
+    x = (torch.rand(2, 6, 32, 32) * 2 - 1).requires_grad_(True)
+    d.train()
+    d.drop_net_id = 2
+    y = d(x)
+    assert y.shape == (2, 16 * min(2 ** nd, 4), 32 >> nd, 32 >> nd)
+    loss = GANLoss(use_lsgan=False)(y, False)
+    loss.backward()
+    sdo = _grad_sd(sd)
+    xo = x.detach().clone().requires_grad_(True)
+    yo = O.discriminator_forward(sdo, xo, True, True, n_blocks=2, drop=O.DropCtx("hash", 0, 0, 2), n_downsampling=nd)
+    lo = O.gan_loss(yo, False)
+    lo.backward()
+    assert torch.allclose(y.detach(), yo.detach(), atol=1e-4)
+    assert abs(loss.item() - lo.item()) < 1e-6
+    assert (x.grad - xo.grad).abs().max() <= 1e-4 * xo.grad.abs().max()
+    for k, p in d.named_parameters():
+        r = sdo[k].grad
+        assert (p.grad - r).abs().max() <= 2e-4 * r.abs().max() + 1e-9, k

@@ -75,3 +75,17 @@ def test_four_training_steps():
         assert abs(float(tr.g[k].double().abs().sum()) - s) <= 1e-4 * max(1.0, s), k
     for k, s in g["final_dpb_sum"].items():
         assert abs(float(tr.dpb[k].double().abs().sum()) - s) <= 1e-4 * max(1.0, s), k
+
+
+def test_discriminator_variants_match_reference_class():
+    """oracle.discriminator_forward(n_downsampling = 1, 3) reproduces the reference Discriminator (eval mode) recorded by
+    oracle/make_golden_dvariants.py."""
+    import os
+    import torch
+    from oracle import patn_ref as O
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "disc_variants_ngf4.pt"))
+    for nd in (1, 3):
+        c = g["nd%d" % nd]
+        y = O.discriminator_forward(c["sd"], c["x"], train=False, use_dropout=True, n_blocks=2, n_downsampling=nd)
+        assert y.shape == c["y"].shape
+        assert torch.allclose(y, c["y"], atol=1e-6), (nd, (y - c["y"]).abs().max())

@@ -1,5 +1,5 @@
 """Isolated timing of the BatchNorm-backward pair (reduce + finalise, apply) and of norm_act on the training step's
-shapes: general functors against the lean row kernels, with / without software pipelining and reversed sweeps.
+shapes: general functors against the lean row kernels (BN backward only), with / without reversed sweeps.
 Buffers rotate over four sets (> the 126 MB L2 in total) so that one iteration does not find the previous one's data.
   python tools/exp/ew_bench.py [--iters 20]"""
 import argparse
@@ -21,10 +21,8 @@ a = ap.parse_args()
 ops = runtime.get_ops(torch.device("cuda", 0))
 B = 16
 CONFIGS = (("general", dict(MMH_EW_LEAN="0")),
-           ("lean", dict(MMH_EW_LEAN="1", MMH_ROWS_PF="0", MMH_EW_REVERSE="0")),
-           ("lean+rev", dict(MMH_EW_LEAN="1", MMH_ROWS_PF="0", MMH_EW_REVERSE="1")),
-           ("lean+pf", dict(MMH_EW_LEAN="1", MMH_ROWS_PF="1", MMH_EW_REVERSE="0")),
-           ("lean+pf+rev", dict(MMH_EW_LEAN="1", MMH_ROWS_PF="1", MMH_EW_REVERSE="1")))
+           ("lean", dict(MMH_EW_LEAN="1", MMH_EW_REVERSE="0")),
+           ("lean+rev", dict(MMH_EW_LEAN="1", MMH_EW_REVERSE="1")))
 
 
 def shapes():
