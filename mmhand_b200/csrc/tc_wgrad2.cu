@@ -14,6 +14,12 @@
 //                        that "next group of channels" means "next pixel" -- N = dy channels, one accumulator per
 //                        (kernel row, block of 128/cw column taps). 7 MMAs of 128 x 64 x 16 replace 49 of
 //                        64 x 16 x 16 per 16 pixel rows.
+// mode 2 (same layers, "kernel rows on M"): M index = (kh, c) -- the leading-dimension stride of the MN-major window
+//                        descriptor is ONE WINDOW (+ one row of skew), so that the eight 16-channel chunks of an MMA
+//                        come from eight different windows and land in different banks; the column taps kw are the
+//                        accumulators (7 x N columns), their descriptors start kw rows into the windows. Mode 1's
+//                        chunks overlap (one row apart): its operand fetch reads 4 KB out of a 736-byte region and
+//                        the MMAs run at a fifth of their rate (profiles/r02_stem_wgrad_ablation.txt).
 // fp32 partial sums are reduced into dw with red.global.add (split-K across CTAs).
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -62,6 +68,10 @@ struct Wg2Params {
   int32_t tap_index[MMH_MAX_TAPS];
   // mode 1: accumulator a -> (group, first column tap); kw_per_mma = 128 / w_cw
   int32_t kw_per_mma;
+  // mode 2: kernel rows per MMA (128 / w_cw), M blocks, window slots per stage, leading-dimension stride of the window
+  // descriptor (window pitch + skew), rows of skew per kernel row
+  int32_t kh_per_mma, n_mblocks, w_slots, skew_rows;
+  uint32_t w_lbo;
   int32_t dbg;   // MMH_W2_DEBUG: 1 skip epilogue reductions, 2 skip MMAs, 4 skip TMA loads (timing experiments only)
 };
 
@@ -145,7 +155,7 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ 
             for (int g = 0; g < p.n_groups; ++g)
               for (int b = 0; b < p.w_boxes; ++b)
                 tma_load_2d_pair(&tmA, bar, sw + g * p.w_bytes + b * p.w_box_bytes, a_c0 + b * p.w_cw,
-                                 q0 + p.g_min[g0 + g]);
+                                 q0 + p.g_min[g0 + g] - g * p.skew_rows);
           } else {
             mbar_expect_tx(&full_bar[stage], bytes);
             for (int b = 0; b < p.dy_boxes; ++b)
@@ -153,7 +163,7 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ 
             for (int g = 0; g < p.n_groups; ++g)
               for (int b = 0; b < p.w_boxes; ++b)
                 tma_load_2d(&tmA, &full_bar[stage], sw + g * p.w_bytes + b * p.w_box_bytes, a_c0 + b * p.w_cw,
-                            q0 + p.g_min[g0 + g]);
+                            q0 + p.g_min[g0 + g] - g * p.skew_rows);
           }
           if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
         }
@@ -198,6 +208,37 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ 
               }
             }
             if (NCTA == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
+          }
+        } else if (p.mode == 2) {
+          // kernel rows on M: A = the windows of the unit's kernel rows (MN-major, leading-dimension stride = one
+          // window + skew), B = dy; accumulator (M block, kw)
+          const uint32_t idesc = make_idesc_bf16(128, p.BNc, 1, 1);
+          const uint64_t w_proto = make_smem_desc(0, p.w_lbo, p.w_sbo, p.w_swz);
+          const uint32_t w_hi = static_cast<uint32_t>(w_proto >> 32), w_lo = static_cast<uint32_t>(w_proto);
+          const uint32_t mb16 = (static_cast<uint32_t>(p.kh_per_mma) * p.w_lbo) >> 4;
+          const int n_mb = p.n_mblocks, ntaps = p.g_first[g0 + 1] - p.g_first[g0];
+          for (int it = 0; it < n_iters; ++it) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sd = smem16 + stage * stage16 + dy_lo;
+            const uint32_t sw = smem16 + stage * stage16 + win16 + w_lo;
+            if (!skip) {
+#pragma unroll
+              for (int k = 0; k < kW2BK / 16; ++k) {
+                const uint64_t bd = (static_cast<uint64_t>(dy_hi) << 32) | (sd + k * dy_k16);
+                const uint32_t accf = (it | k) != 0 ? 1u : 0u;
+                uint32_t d = tmem_base;
+                for (int mb = 0; mb < n_mb; ++mb) {
+                  uint32_t wa = sw + mb * mb16 + k * w_k16;
+                  for (int kw = 0; kw < ntaps; ++kw, wa += row16, d += BNc) {
+                    const uint64_t ad = (static_cast<uint64_t>(w_hi) << 32) | wa;
+                    umma_bf16(d, ad, bd, idesc, accf);
+                  }
+                }
+              }
+            }
+            umma_commit(&empty_bar[stage]);
             if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
         } else {
@@ -262,6 +303,31 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
                   if (c0 + i < p.C_store) red_add_f32(dst_row + c0 + i, __uint_as_float(v[i]));
+              }
+            }
+          }
+        }
+      } else if (p.mode == 2) {
+        // lane = (kh_local, c); accumulator (M block, kw) holds dw[(kh, kw)][n][c] in column n
+        const int khl = row / p.w_cw, c = tc * p.w_cw + row % p.w_cw;
+        const int ntaps = p.g_first[g0 + 1] - p.g_first[g0];
+        int acc = 0;
+        for (int mb = 0; mb < p.n_mblocks; ++mb) {
+          const int kh = mb * p.kh_per_mma + khl;
+          const bool ok = kh < p.n_groups && c < p.C_store;
+          for (int kw = 0; kw < ntaps; ++kw, ++acc) {
+            const int tap = ok ? p.tap_index[p.g_first[g0 + kh] + kw] : 0;
+            float* dst = p.dw + static_cast<int64_t>(tap) * p.N_store * p.C_store + c;
+            for (int n16 = 0; n16 < p.BNc / 16; ++n16) {
+              uint32_t v[16];
+              tmem_ld16(t_addr + acc * p.BNc + n16 * 16, v);
+              tmem_ld_wait();
+              if (ok && !(p.dbg & 1)) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const int n = n16 * 16 + i;
+                  if (n < p.N_store) red_add_f32(dst + static_cast<int64_t>(n) * p.C_store, __uint_as_float(v[i]));
+                }
               }
             }
           }
@@ -348,7 +414,8 @@ int mmh_wgrad2_create(const MmhWgradDesc* d, MmhWgrad2** out_plan) {
   // mode: taps on M for few-channel stems with many taps whose groups are runs of consecutive shifts
   int mode = w2_env("MMH_WGRAD_MODE", -1);
   const bool stem_like = d->T >= 16 && d->N <= 64 && (d->C <= 64);
-  if (mode < 0) mode = stem_like ? 1 : 0;
+  if (mode < 0) mode = stem_like ? 2 : 0;
+  if (mode != 0 && !stem_like) mode = 0;
   k.mode = mode;
 
   int gmax_taps;   // taps per group limit
@@ -363,7 +430,7 @@ int mmh_wgrad2_create(const MmhWgradDesc* d, MmhWgrad2** out_plan) {
   std::vector<int> gf, gm;
   for (int t = 0; t < d->T; ++t) {
     const bool fresh = t == 0 || taps[t].first - taps[t - 1].first >= 64 || (t - gf.back()) >= gmax_taps ||
-                       (mode == 1 && taps[t].first - taps[t - 1].first != 1);
+                       (mode != 0 && taps[t].first - taps[t - 1].first != 1);
     if (fresh) { gf.push_back(t); gm.push_back(taps[t].first); }
     k.rel[t] = taps[t].first - gm.back();
     k.tap_index[t] = taps[t].second;
@@ -379,7 +446,7 @@ int mmh_wgrad2_create(const MmhWgradDesc* d, MmhWgrad2** out_plan) {
     span_max = std::max(span_max, k.rel[end - 1]);
   }
   k.g_first[ng] = d->T;
-  if (mode == 1) {
+  if (mode != 0) {
     for (int g = 0; g < ng; ++g)
       if (k.g_first[g + 1] - k.g_first[g] != gt_max) { set_error("wgrad taps-on-M mode needs equal kernel rows"); return fail(); }
   }
@@ -403,6 +470,30 @@ int mmh_wgrad2_create(const MmhWgradDesc* d, MmhWgrad2** out_plan) {
     k.w_rows = (kW2BK + span_max + 7) / 8 * 8;
     k.n_acc = gt_max;
     k.kw_per_mma = 1;
+  } else if (mode == 2) {
+    // mode 2: one unit = one channel chunk of width cw (16, or 64 when C is a multiple of 64) x ALL kernel rows
+    k.w_cw = (d->C % 64) == 0 ? 64 : 16;
+    k.kh_per_mma = 128 / k.w_cw;
+    k.n_mblocks = (ng + k.kh_per_mma - 1) / k.kh_per_mma;
+    k.w_slots = k.n_mblocks * k.kh_per_mma;
+    // 32-byte chunks of one K row spread over the banks; 128-byte ones fill them (MMH_WGRAD_SKEW: timing experiments)
+    k.skew_rows = w2_env("MMH_WGRAD_SKEW", k.w_cw == 16 ? 1 : 0);
+    k.kw_per_mma = 1;
+    k.BNc = d->N;
+    if ((d->N % 16) != 0 || d->N > 256) { set_error("wgrad mode 2: N=%d unsupported", d->N); return fail(); }
+    if (ng > kW2MaxGroups || k.n_mblocks * gt_max * k.BNc > 512) { set_error("wgrad mode 2: accumulators do not fit"); return fail(); }
+    k.n_groups = ng;
+    k.units_g = 1;
+    k.tiles_n = 1;
+    k.tiles_c = d->C / k.w_cw;
+    k.dy_cols = d->N;
+    k.dy_cw = w2_cw(d->N);
+    k.dy_boxes = d->N / k.dy_cw;
+    k.w_cols = k.w_cw;
+    k.w_boxes = 1;
+    // window rows: 64 pixel rows + column taps + the skew of the last kernel row, rounded up to 8
+    k.w_rows = (kW2BK + (gt_max - 1) + k.skew_rows * (ng - 1) + 7) / 8 * 8;
+    k.n_acc = k.n_mblocks * gt_max;
   } else {
     // mode 1: one unit = one channel chunk of width cw (16, or 64 when C is a multiple of 64) x all groups
     k.w_cw = (d->C % 64) == 0 ? 64 : 16;
@@ -441,7 +532,9 @@ int mmh_wgrad2_create(const MmhWgradDesc* d, MmhWgrad2** out_plan) {
   k.w_swz = w2_swz_code(k.w_cw);
   k.w_sbo = 8 * k.w_row_bytes;
   k.win_off = (k.dy_boxes * k.dy_box_bytes + 1023u) & ~1023u;
-  k.stage_bytes = k.win_off + k.n_groups * k.w_bytes;
+  k.w_lbo = k.w_bytes + static_cast<uint32_t>(k.skew_rows) * k.w_row_bytes;
+  if (mode != 2) k.w_slots = k.n_groups;
+  k.stage_bytes = k.win_off + k.w_slots * k.w_bytes;
   k.stage_bytes = (k.stage_bytes + 1023u) & ~1023u;
   // The weight gradient runs on a side stream next to the bandwidth-bound BN-backward kernels (engine.py::run_bwd):
   // leave room in shared memory for two of their blocks (2 x (16 KB + 1 KB)) so that they can be co-resident.
