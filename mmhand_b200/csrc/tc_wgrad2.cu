@@ -414,7 +414,9 @@ int mmh_wgrad2_create(const MmhWgradDesc* d, MmhWgrad2** out_plan) {
   // mode: taps on M for few-channel stems with many taps whose groups are runs of consecutive shifts
   int mode = w2_env("MMH_WGRAD_MODE", -1);
   const bool stem_like = d->T >= 16 && d->N <= 64 && (d->C <= 64);
-  if (mode < 0) mode = stem_like ? 2 : 0;
+  // measured (profiles/r02_stem_wgrad_modes.txt): 16-channel chunks 389 -> 778 / 403 -> 873 TFLOP/s with the kernel
+  // rows on M; the 64-channel chunk of the output layer (2 kernel rows per MMA, N = 16) stays with the taps on M
+  if (mode < 0) mode = stem_like ? ((d->C % 64) == 0 ? 1 : 2) : 0;
   if (mode != 0 && !stem_like) mode = 0;
   k.mode = mode;
 

@@ -62,8 +62,10 @@ class MMHandModel(BaseModel):
             self.fake_PB_pool = ImagePool(opt.pool_size)
             self.criterionGAN = GANLoss(use_lsgan=not opt.no_lsgan, gpu=self.opt.local_rank)
             if opt.L1_type == 'origin':
+                # accepted exactly as far as the reference accepts it: construction works, the first generator step
+                # fails -- backward_G indexes the loss (`losses[0]`, reference :247-248) and nn.L1Loss returns a 0-dim
+                # tensor, which raises IndexError in every torch release since 0.4
                 self.criterionL1 = torch.nn.L1Loss()
-                raise NotImplementedError("L1_type 'origin' is not built on the B200 path (shipped: l1_plus_perL1)")
             elif opt.L1_type == 'l1_plus_perL1':
                 self.criterionL1 = L1_plus_perceptualLoss(opt.lambda_A, opt.lambda_B, opt.perceptual_layers,
                                                           self.gpu_ids, opt.percep_is_l1).to(self.device)
@@ -259,6 +261,10 @@ class MMHandModel(BaseModel):
             ops.input_grad_nchw(src, None, dfake, B, C3, H, W, True)
         n = fake.numel()
         crit = self.criterionL1
+        if opt.L1_type == 'origin':
+            raise IndexError("invalid index of a 0-dim tensor. Use `tensor.item()` in Python or `tensor.item<T>()` in "
+                             "C++ to convert a 0-dim tensor to a number  [L1_type='origin': the reference's backward_G "
+                             "(models/MMHandModel.py:247-248) indexes the scalar nn.L1Loss returns]")
         ops.l1(fake, self.input_H2, opt.lambda_A / n, opt.lambda_A / n, acc[2:3], dfake)
         crit.vgg_engine(B, H, W).loss_and_backward(fake, self.input_H2, opt.lambda_B, opt.percep_is_l1 != 1, acc[3:4],
                                                    dfake)

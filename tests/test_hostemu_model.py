@@ -410,3 +410,20 @@ def test_discriminator_n_downsampling_variants(emu_f32, nd):
     for k, p in d.named_parameters():
         r = sdo[k].grad
         assert (p.grad - r).abs().max() <= 2e-4 * r.abs().max() + 1e-9, k
+
+
+def test_l1_type_origin_fails_where_the_reference_fails(emu_bf16):
+    """--L1_type origin: the reference constructs nn.L1Loss (MMHandModel.py:81-82) and then indexes its 0-dim result in
+    backward_G (:247-248) -- IndexError at the first generator step. The drop-in accepts and fails at the same place."""
+    from models.MMHandModel import MMHandModel
+    assert_raises = pytest.raises(IndexError, match="0-dim")
+    with assert_raises:
+        torch.nn.L1Loss()(torch.zeros(2, 3), torch.ones(2, 3))[0]          # what the reference's line does
+    opt = make_opt(batchSize=1, fineSize=32, ngf=16, ndf=16, local_rank='cpu', seed=7, L1_type='origin')
+    m = MMHandModel(opt)
+    assert isinstance(m.criterionL1, torch.nn.L1Loss)
+    r = lambda *s: torch.rand(*s)
+    m.set_input(dict(H1=r(1, 3, 32, 32), P1=r(1, 21, 32, 32), D1=r(1, 3, 32, 32), H2=r(1, 3, 32, 32),
+                     P2=r(1, 21, 32, 32), D2=r(1, 3, 32, 32)))
+    with assert_raises:
+        m.optimize_parameters()
