@@ -330,7 +330,8 @@ def run_ours(a):
                    "vgg_weights": "random-init (no network)",
                    "syncbn": ("peer" if (model.world is not None and model.world.peer is not None) else
                               ("nccl" if world > 1 else "local")),
-                   "pdl": os.environ.get("MMH_PDL", "1") != "0",
+                   "pdl": bool(ops.lib.mmh_get_pdl()),
+                   "g_update_stream": os.environ.get("MMH_G_UPDATE_STREAM", "0" if world > 1 else "1") != "0",
                    "grad_allreduce": getattr(model, "grad_sync_mode", "none") if world > 1 else "none",
                    "bn_bwd_in_dgrad_epilogue": os.environ.get("MMH_FUSE_BN_BWD", "0") != "0",
                    "layer_chain_streams": chains_used,
@@ -419,17 +420,22 @@ def run_infer(a):
         h = [b["H1"], torch.cat((b["P1"], b["P2"]), 1).pin_memory(), torch.cat((b["D1"], b["D2"]), 1).pin_memory()]
         hosts.append(h)
         devs.append([t.cuda(non_blocking=True) for t in h])
-    out_host = torch.empty(B, 3, S, S, dtype=torch.float32).pin_memory()
-    h2d = sum(t.numel() * t.element_size() for t in hosts[0])
+    # end to end = the public aug.py path of this repository (mmhand_b200.augment.generate_batch): the loader's compact
+    # batch (uint8 frames + float64 keypoints, pinned) -> six tensors on the device -> generator -> BGR uint8 images
+    # (the bytes cv2.imwrite stores) -> pinned host buffer
+    from mmhand_b200 import augment
+    from mmhand_b200.loader import CompactBatch
+    compact = [CompactBatch(synth_compact_batch(B, S, 2100 + 17 * rank + i, pin=True)) for i in range(2)]
+    out_host = torch.empty(B, S, S, 3, dtype=torch.uint8).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in compact[0].values() if torch.is_tensor(v))
 
     def dev_step(i):
         with torch.no_grad():
             g(devs[i % 2])
 
     def e2e_step(i):
-        with torch.no_grad():
-            y = g([t.cuda(non_blocking=True) for t in hosts[i % 2]])
-        out_host.copy_(y, non_blocking=True)
+        # a fresh CompactBatch per step: the device tensors it materialises are not cached across steps
+        augment.generate_batch(g, CompactBatch(compact[i % 2]), host_out=out_host)
         torch.cuda.current_stream().synchronize()       # aug.py writes each batch of images to disk
 
     warm = max(a.warmup, 3)
@@ -476,7 +482,8 @@ def run_infer(a):
                    "per_gpu_batch": B, "frame": S, "parallelism": "dp%d (independent images, no collective)" % world,
                    "l2": "activations of one batch (> 2 GB) exceed the 126 MB L2"},
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e / a.steps},
+                "d2h_bytes_per_step": out_host.numel(), "ms_per_step": ms_e2e / a.steps,
+                "path": "mmhand_b200.augment.generate_batch on the loader's compact batch; BGR uint8 images back"},
         "gpu_launches": launches, "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "kernel": "conv2_kernel (tcgen05 implicit-GEMM fprop, csrc/tc_conv2.cu)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,

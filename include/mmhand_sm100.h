@@ -31,6 +31,12 @@ int mmh_version(void);
 const char* mmh_last_error(void);
 /* 1 when the library was built as the CUDA product, 0 for the host emulation used by CPU tests. */
 int mmh_is_device_build(void);
+/* Programmatic dependent launch (every kernel starts with griddepcontrol.wait / launch_dependents) on (1) / off (0) for
+ * all later launches; -1 returns to the default (environment MMH_PDL, else on). Data-parallel groups switch it off:
+ * CTAs parked by a dependent launch next to BatchNorm kernels that spin on their peers' mailboxes starved NCCL's
+ * kernels on 8 GPUs (mmhand_b200/runtime.py::World). No counterpart in the reference (launch plumbing). */
+int mmh_set_pdl(int32_t on);
+int mmh_get_pdl(void);
 
 /* ---- convolution as a shifted-row GEMM on tcgen05 ---------------------------------------------- */
 /*

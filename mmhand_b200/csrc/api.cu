@@ -74,7 +74,21 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, int64_t cols, int64_t 
 
 }  // namespace mmh
 
+#include <stdlib.h>
 #include "ew_common.h"
+namespace mmh {
+static int g_pdl = -1;      // -1: not set through the ABI -> MMH_PDL, else on
+bool pdl_enabled() {
+  if (g_pdl >= 0) return g_pdl != 0;
+  static const bool env_on = [] {
+    const char* e = getenv("MMH_PDL");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return env_on;
+}
+}  // namespace mmh
+extern "C" int mmh_set_pdl(int32_t on) { mmh::g_pdl = on < 0 ? -1 : (on != 0 ? 1 : 0); return 0; }
+extern "C" int mmh_get_pdl(void) { return mmh::pdl_enabled() ? 1 : 0; }
 extern "C" int mmh_version(void) { return 100; }
 extern "C" int mmh_act_bytes(void) { return static_cast<int>(sizeof(mmh::act_t)); }
 extern "C" const char* mmh_last_error(void) { return mmh::get_error(); }

@@ -313,13 +313,6 @@ __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
-inline bool pdl_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("MMH_PDL");
-    return e == nullptr || atoi(e) != 0;
-  }();
-  return on;
-}
 template <class... KArgs, class... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, void* stream, Args... args) {
   cudaLaunchConfig_t cfg;

@@ -17,6 +17,9 @@ const char* get_error();
     }                                   \
   } while (0)
 
+// programmatic dependent launch on / off for every launch of the library (mmh_set_pdl; default: MMH_PDL, else on)
+bool pdl_enabled();
+
 #ifndef MMH_HOST_EMU
 #define MMH_CUDA(expr)                                                                      \
   do {                                                                                      \

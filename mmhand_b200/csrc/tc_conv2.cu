@@ -807,7 +807,7 @@ int mmh_conv2_run_key(const MmhConv2* plan, uint32_t drop_key, void* stream) {
   cfg.dynamicSmemBytes = plan->smem;
   cfg.stream = static_cast<cudaStream_t>(stream);
   cudaLaunchAttribute attr[2];
-  static const bool pdl = [] { const char* e = getenv("MMH_PDL"); return e == nullptr || atoi(e) != 0; }();
+  const bool pdl = pdl_enabled();
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
   cfg.attrs = attr;

@@ -593,7 +593,7 @@ int mmh_wgrad2_run(const MmhWgrad2* plan, void* stream) {
   cfg.dynamicSmemBytes = plan->smem;
   cfg.stream = static_cast<cudaStream_t>(stream);
   cudaLaunchAttribute attr[2];
-  static const bool pdl = [] { const char* e = getenv("MMH_PDL"); return e == nullptr || atoi(e) != 0; }();
+  const bool pdl = pdl_enabled();
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
   cfg.attrs = attr;

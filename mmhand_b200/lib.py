@@ -128,6 +128,8 @@ def load(path=None):
     lib.mmh_version.restype = C.c_int
     lib.mmh_is_device_build.restype = C.c_int
     lib.mmh_act_bytes.restype = C.c_int
+    lib.mmh_set_pdl.argtypes, lib.mmh_set_pdl.restype = [C.c_int32], C.c_int
+    lib.mmh_get_pdl.restype = C.c_int
     lib.act_bytes = lib.mmh_act_bytes()      # 2 (bf16) in the product; 4 only in the fp32 host emulation
     _declare(lib)
     if path is None:
@@ -204,7 +206,7 @@ _SIMPLE_SIGS = {
     "mmh_stream_wait_event": [_vp, _vp],
 }
 PEER_HANDLE_BYTES = 64
-EXPORTS = ["mmh_version", "mmh_last_error", "mmh_is_device_build", "mmh_conv_plan_create", "mmh_conv_plan_destroy",
+EXPORTS = ["mmh_version", "mmh_last_error", "mmh_is_device_build", "mmh_set_pdl", "mmh_get_pdl", "mmh_conv_plan_create", "mmh_conv_plan_destroy",
            "mmh_conv_run", "mmh_conv_run_key", "mmh_wgrad_plan_create", "mmh_wgrad_plan_destroy", "mmh_wgrad_run"] + list(_SIMPLE_SIGS)
 
 

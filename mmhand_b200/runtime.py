@@ -96,6 +96,7 @@ class World:
         import warnings
         if self.size <= 1 or self.peer is not None or ops.device.type != "cuda":
             return self.peer is not None
+        self.tame_launches(ops)
         mode = os.environ.get("MMH_SYNCBN", "auto")
         if mode == "nccl" or not ops.lib.mmh_is_device_build():
             return False
@@ -122,6 +123,19 @@ class World:
         if self.rank == 0:
             warnings.warn("mmhand_b200: peer-memory SyncBN exchange unavailable (%s); using NCCL all-reduces" % why)
         return False
+
+    def tame_launches(self, ops):
+        """Data-parallel groups launch without programmatic dependent launch (and MMHandModel keeps the generator update
+        on the launch stream): with both on, 8 GPUs stopped inside the first timed steps -- every rank blocked in a
+        kernel launch with its queue full (gpurun_out/bench_n8_default.err, round 2; the same picture as round 1's
+        8-GPU attempt) -- while 4 GPUs ran. CTAs parked by a dependent launch hold their SM's shared memory next to a
+        BatchNorm kernel that spins on its peers' mailboxes; NCCL's kernels of the bucketed all-reduce, which need a
+        few CTAs on EVERY rank to advance, then wait for an SM on one rank while another rank's exchange waits for
+        that rank's statistics. Without the parked CTAs the same run takes 56.5 ms per step on 8 GPUs (2266 images/s).
+        The gain given up is 0.4 ms of 57.9 at 4 GPUs. MMH_PDL=1 / MMH_G_UPDATE_STREAM=1 force them back on."""
+        import os
+        if self.size > 1 and ops.device.type == "cuda" and "MMH_PDL" not in os.environ and hasattr(ops.lib, "mmh_set_pdl"):
+            ops.lib.mmh_set_pdl(0)
 
     def close(self):
         """Unmap the peers' mailboxes and free this rank's (collective in spirit: call it on every rank once no

@@ -312,7 +312,8 @@ class MMHandModel(BaseModel):
         g_eng = self._g_engine()
         g_eng.store.zero_grad()
         self.backward_G()
-        if ops.side_stream is not None and os.environ.get("MMH_G_UPDATE_STREAM", "1") != "0":
+        dp = self.world is not None and self.world.size > 1       # (see runtime.World.tame_launches)
+        if ops.side_stream is not None and os.environ.get("MMH_G_UPDATE_STREAM", "0" if dp else "1") != "0":
             # Nothing in the discriminator segments reads the generator's weights: its gradient all-reduce, Adam
             # update and operand repacking (bandwidth-bound) run on the side stream under the discriminators'
             # convolutions; _segment_D joins before the step ends.
