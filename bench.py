@@ -463,8 +463,10 @@ def run_infer(a):
         recs.append((e0, e1, 2.0 * d.M * d.N * d.C * d.T * (d.Hv * d.Wv) / float(d.Hg * d.Wg)))
 
     ops.conv_hook = hook
-    dev_step(0)
+    chains, ops.chains = ops.chains, [None]       # serial launches on one stream: a kernel's events bracket that kernel
+    dev_step(0)                                   # alone (torch events see only torch's current stream)
     torch.cuda.synchronize()
+    ops.chains = chains
     ops.conv_hook = None
     t_conv = sum(e0.elapsed_time(e1) for e0, e1, _ in recs) / 1000.0
     f_conv = sum(f for _, _, f in recs)
