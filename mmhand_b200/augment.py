@@ -11,7 +11,7 @@ numpy / cv2 and lets ``cv2.imwrite`` round and encode it, one image at a time wi
     write (cv2.imwrite releases the GIL) to a pool of host threads, so that the GPU never waits for the disk.
 """
 import os
-import threading
+import queue
 from concurrent.futures import ThreadPoolExecutor
 
 import torch
@@ -64,36 +64,34 @@ class ImageWriter:
         import cv2
         self.cv2 = cv2
         self.pool = ThreadPoolExecutor(max_workers=max(1, workers))
-        self.depth, self.slots, self.free = depth, [], threading.Semaphore(depth)
-        self.lock, self.pending, self.next = threading.Lock(), [], 0
+        self.depth, self.slots = depth, [None] * depth
+        self.free = queue.Queue()                # indices of the pinned buffers no writer thread is reading
+        for i in range(depth):
+            self.free.put(i)
+        self.pending = []
 
     def _slot(self, shape, cuda):
-        self.free.acquire()                      # back-pressure: at most `depth` batches in flight
-        with self.lock:
-            i = self.next % self.depth
-            self.next += 1
-            while len(self.slots) <= i:
-                self.slots.append(None)
-            buf = self.slots[i]
-            if buf is None or tuple(buf.shape) != tuple(shape):
-                buf = torch.empty(shape, dtype=torch.uint8)
-                if cuda:
-                    buf = buf.pin_memory()
-                self.slots[i] = buf
-        return buf
+        i = self.free.get()                      # back-pressure: at most `depth` batches in flight; a buffer is handed
+        buf = self.slots[i]                      # out again only after ITS writer released it (completion order is
+        if buf is None or tuple(buf.shape) != tuple(shape):          # not submission order with several workers)
+            buf = torch.empty(shape, dtype=torch.uint8)
+            if cuda:
+                buf = buf.pin_memory()
+            self.slots[i] = buf
+        return i, buf
 
     def submit(self, images_bgr8, paths):
         assert images_bgr8.dtype == torch.uint8 and images_bgr8.dim() == 4 and len(paths) == images_bgr8.shape[0]
         cuda = images_bgr8.is_cuda
-        buf = self._slot(images_bgr8.shape, cuda)
+        slot, buf = self._slot(images_bgr8.shape, cuda)
         buf.copy_(images_bgr8, non_blocking=True)
         ev = None
         if cuda:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(images_bgr8.device))
-        self.pending.append(self.pool.submit(self._write, buf, ev, list(paths)))
+        self.pending.append(self.pool.submit(self._write, slot, buf, ev, list(paths)))
 
-    def _write(self, buf, ev, paths):
+    def _write(self, slot, buf, ev, paths):
         try:
             if ev is not None:
                 ev.synchronize()
@@ -105,7 +103,7 @@ class ImageWriter:
                 if not self.cv2.imwrite(p, arr[i]):
                     raise IOError("cv2.imwrite failed for %s" % p)
         finally:
-            self.free.release()
+            self.free.put(slot)
 
     def close(self):
         errs = []

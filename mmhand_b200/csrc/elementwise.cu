@@ -79,9 +79,8 @@ struct BnStatsF {
 };
 
 // ------------------------------------------------------------------------------------------------ norm + act + pad
-template <int U>
-struct NormActT {
-  static constexpr int kUnroll = U;
+struct NormActF {
+  static constexpr int kUnroll = 4;       // (2: -10 %, 8: -8 % on the step's shapes, profiles/r02_norm_act_knobs.txt)
   struct Ctx { float a[8], b[8]; };
   struct In { ActX8 x; F32x8 r; };
   const act_t* src; LayD sl; const float* coef; int relu, dropout; uint32_t key;
@@ -153,8 +152,6 @@ MMH_HD int32_t rowat(const LayD& l, const RowOff& r, int w) {
 inline bool lay_fits32(const MmhLay& l) {
   return static_cast<int64_t>(l.B) * l.Hg * l.Wg * (l.phase ? 4 : 1) * l.ld + l.c0 < (int64_t(1) << 31);
 }
-
-typedef NormActT<4> NormActF;
 
 // ------------------------------------------------------------------------------------------------ PAT gate
 struct GateFwdF {
@@ -725,16 +722,6 @@ extern "C" int mmh_norm_act(const MmhNormAct* p, void* stream) {
   MMH_CHECK(!p->dst || (p->dl.H == p->sl.H && p->dl.W == p->sl.W && p->dl.C == p->sl.C), "src/dst shape mismatch");
   MMH_CHECK(!f.reflect || (lo < f.sl.H && hi < f.sl.H && lo < f.sl.W && hi < f.sl.W), "halo too large");
   const RowGeom rg = make_rowgeom(f.sl.B, f.sl.H, f.sl.W, lo, hi);
-  // MMH_NORM_UNROLL (timing experiments): vectors in flight per thread
-  static const int unroll = [] { const char* e = getenv("MMH_NORM_UNROLL"); return e != nullptr ? atoi(e) : 4; }();
-  if (unroll == 8 || unroll == 2) {
-    NormActT<8> f8; NormActT<2> f2;
-#define MMH_CP(d) d.src = f.src; d.sl = f.sl; d.coef = f.coef; d.relu = f.relu; d.dropout = f.dropout; d.key = f.key; \
-  d.resid = f.resid; d.dst = f.dst; d.dl = f.dl; d.reflect = f.reflect; d.dst_f32 = f.dst_f32
-    MMH_CP(f8); MMH_CP(f2);
-#undef MMH_CP
-    return unroll == 8 ? launch_pg(f8, rg, p->sl.C / 8, stream) : launch_pg(f2, rg, p->sl.C / 8, stream);
-  }
   return launch_pg(f, rg, p->sl.C / 8, stream);
 }
 

@@ -420,8 +420,7 @@ int launch_pg(const F& f, const RowGeom& rg, int groups, void* stream) {
   const int threads = pg_threads(groups);
   const int ppb = threads / groups;
   const int chunks = (rg.n_cols + ppb * F::kUnroll - 1) / (ppb * F::kUnroll);
-  static const int per_sm = [] { const char* e = getenv("MMH_PG_PER_SM"); const int v = e != nullptr ? atoi(e) : 8; return v > 0 ? v : 8; }();
-  const dim3 grid = row_grid(rg, chunks, per_sm);
+  const dim3 grid = row_grid(rg, chunks, 8);       // (4 or 16 blocks per SM: no gain, profiles/r02_norm_act_knobs.txt)
   MMH_CUDA(launch_k(pg_kernel<F>, grid, dim3(threads), 0, stream, f, rg, groups, chunks));
   return 0;
 }

@@ -631,6 +631,45 @@ class GeneratorEngine(EngineBase):
         self.bwd_ready = True
         self.repack(force=True)
 
+    # ------------------------------------------------------------------------------------------ taped inference
+    def forward_taped(self, x1, x2, x3):
+        """Eval-mode forward through a recorded launch sequence (the aug.py / test() path): the ~300 launches of a
+        forward are recorded once per (input shapes, launch stream) and replayed -- a few microseconds of host time
+        per launch instead of the argument marshalling of an eager call, which made inference host-bound on slow hosts
+        (bench.py --workload infer e2e: 42 vs 20 ms per batch of 32 on two boxes of the same pool). The inputs' device
+        pointers are the only per-call arguments (the three stems' assemble launches): they are patched per replay.
+        Weights are re-packed before the replay when they changed (``repack`` compares parameter versions); eval-mode
+        BatchNorm reads the running statistics through their (stable) pointers inside the recorded launches."""
+        ops = self.ops
+        ins = (x1, x2, x3)
+        key = (tuple(tuple(t.shape) for t in ins), ops.st().value)
+        if getattr(self, "_infer_tape", None) is None or self._infer_key != key:
+            self.repack()
+            with ops.record() as tape:
+                out = self.forward(x1, x2, None, x3, None, False)
+            # where the inputs' pointers sit in the recorded argument lists
+            ptrs = {t.data_ptr(): i for i, t in enumerate(ins)}
+            assert len(ptrs) == len(ins), "the generator's three inputs must be distinct tensors"
+            slots = []
+            for ci, (fn, args, _) in enumerate(tape.cmds):
+                if fn is None:
+                    continue
+                for ai, v in enumerate(args):          # (pointers travel as plain integers, kernels._p)
+                    if isinstance(v, int) and not isinstance(v, bool) and v in ptrs:
+                        slots.append((ci, ai, ptrs[v]))
+            assert len({i for _, _, i in slots}) == len(ins), "an input is not consumed by a recorded launch"
+            self._infer_tape, self._infer_out, self._infer_key, self._infer_slots = tape, out, key, slots
+            return out
+        self.repack()
+        cmds = self._infer_tape.cmds
+        for ci, ai, i in self._infer_slots:
+            cmds[ci][1][ai] = ins[i].data_ptr()
+        self._infer_tape.keep.append(ins)            # the launches are asynchronous: keep this call's inputs alive
+        if len(self._infer_tape.keep) > 64:
+            del self._infer_tape.keep[:32]
+        self._infer_tape.replay(0)
+        return self._infer_out
+
     # ------------------------------------------------------------------------------------------ forward
     def forward(self, x1, x2a, x2b, x3a, x3b, training, step=0, net_id=0):
         """x1: image [B,3,H,W]; (x2a | x2b): pose maps; (x3a | x3b): depth maps (NCHW fp32, second halves may be

@@ -5,6 +5,7 @@ by mmhand_b200.engine.GeneratorEngine on hand-written sm_100a kernels (NHWC bf16
 Reference: models/Generator.py:8-130 (PATBlock), :133-283 (PATNModel), :286-313 (Generator).
 """
 import functools
+import os
 
 import torch
 import torch.nn as nn
@@ -98,7 +99,10 @@ class _GeneratorFn(torch.autograd.Function):
     def forward(ctx, mod, want_grad, anchor, x1, x2, x3):
         training = mod.training
         eng = mod.engine(x1.shape[0], x1.shape[2], x1.shape[3])
-        out = eng.forward(x1, x2, None, x3, None, training, step=mod._step, net_id=0)
+        if not training and not want_grad and os.environ.get("MMH_INFER_TAPE", "1") != "0":
+            out = eng.forward_taped(x1, x2, x3)          # recorded launch sequence (aug.py / test())
+        else:
+            out = eng.forward(x1, x2, None, x3, None, training, step=mod._step, net_id=0)
         if training:
             mod._step += 1
         ctx.eng = eng if want_grad else None

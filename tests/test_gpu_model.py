@@ -425,3 +425,33 @@ def test_two_stream_network_and_ssim():
     assert torch.allclose(ssim(a, b, size_average=False), O.ssim(a, b, size_average=False), atol=1e-5)
     g = torch.load(os.path.join(ROOT, "tests", "golden", "patn2_ngf4.pt"))
     assert abs(float(ssim(g["ssim_a"].to(DEV), g["ssim_b"].to(DEV))) - float(g["ssim_mean"])) < 2e-6
+
+
+def test_taped_inference_matches_eager(monkeypatch):
+    """Eval-mode Generator.forward through the recorded launch sequence (GeneratorEngine.forward_taped, layer chains on
+    three streams included): bit-identical to the eager launches, on inputs at other addresses, after new weights."""
+    from models.Generator import Generator
+    from models.network_utils import get_norm_layer, init_weights
+    torch.manual_seed(3)
+    g = Generator([3, 42, 6], 3, 32, get_norm_layer('batch'), True, 3).to(DEV)
+    init_weights(g, 'normal')
+    g.eval()
+    mk = lambda seed: [(torch.rand(4, c, 64, 64, generator=torch.Generator().manual_seed(seed)) * 2 - 1).to(DEV)
+                       for c in (3, 42, 6)]
+    xa, xb = mk(1), mk(2)
+    with torch.no_grad():
+        monkeypatch.setenv("MMH_INFER_TAPE", "0")
+        ea, eb = g(xa).clone(), g(xb).clone()
+        monkeypatch.setenv("MMH_INFER_TAPE", "1")
+        ta = g(xa).clone()
+        tb = g([t.clone() for t in xb]).clone()
+        ta2 = g(xa).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(ea, ta) and torch.equal(eb, tb) and torch.equal(ta, ta2) and not torch.equal(ta, tb)
+        sd = {k: (v * 1.5 if v.dtype.is_floating_point and v.dim() == 4 else v) for k, v in g.state_dict().items()}
+        g.load_state_dict(sd)
+        tn = g(xa).clone()
+        monkeypatch.setenv("MMH_INFER_TAPE", "0")
+        en = g(xa).clone()
+        torch.cuda.synchronize()
+    assert torch.equal(tn, en) and not torch.equal(tn, ta)

@@ -427,3 +427,36 @@ def test_l1_type_origin_fails_where_the_reference_fails(emu_bf16):
                      P2=r(1, 21, 32, 32), D2=r(1, 3, 32, 32)))
     with assert_raises:
         m.optimize_parameters()
+
+
+def test_taped_inference_matches_eager_and_follows_new_inputs_and_weights(emu_bf16, monkeypatch):
+    """Eval-mode Generator.forward replays a recorded launch sequence (GeneratorEngine.forward_taped): same result as
+    the eager path, for inputs at other addresses, and after the weights changed (load_state_dict) without re-recording
+    the wrong operands."""
+    from models.Generator import Generator
+    from models.network_utils import get_norm_layer, init_weights
+    torch.manual_seed(3)
+    g = Generator([3, 42, 6], 3, 16, get_norm_layer('batch'), True, 2)
+    init_weights(g, 'normal')
+    g.eval()
+    mk = lambda seed: [torch.rand(2, c, 32, 32, generator=torch.Generator().manual_seed(seed)) * 2 - 1 for c in (3, 42, 6)]
+    xa, xb = mk(1), mk(2)
+    with torch.no_grad():
+        monkeypatch.setenv("MMH_INFER_TAPE", "0")
+        ea, eb = g(xa).clone(), g(xb).clone()
+        monkeypatch.setenv("MMH_INFER_TAPE", "1")
+        ta = g(xa).clone()                         # records
+        tb = g([t.clone() for t in xb]).clone()    # replays on tensors at other addresses
+        ta2 = g(xa).clone()
+    assert torch.equal(ea, ta) and torch.equal(eb, tb) and torch.equal(ta, ta2)
+    assert not torch.equal(ta, tb)
+    eng = next(iter(g._engines.values()))
+    assert eng._infer_tape is not None and len(eng._infer_slots) == 3
+    # new weights: the replay must use them
+    sd = {k: (v * 1.5 if v.dtype.is_floating_point and v.dim() == 4 else v) for k, v in g.state_dict().items()}
+    g.load_state_dict(sd)
+    with torch.no_grad():
+        tn = g(xa).clone()
+        monkeypatch.setenv("MMH_INFER_TAPE", "0")
+        en = g(xa).clone()
+    assert torch.equal(tn, en) and not torch.equal(tn, ta)
