@@ -464,8 +464,11 @@ def run_infer(a):
 
     ops.conv_hook = hook
     chains, ops.chains = ops.chains, [None]       # serial launches on one stream: a kernel's events bracket that kernel
-    dev_step(0)                                   # alone (torch events see only torch's current stream)
+    os.environ["MMH_INFER_TAPE"] = "0"            # alone (torch events see only torch's current stream); eager launches
+    g._engines.clear()                            # (the hook wraps eager conv launches), on a fresh engine
+    dev_step(0)
     torch.cuda.synchronize()
+    os.environ.pop("MMH_INFER_TAPE", None)
     ops.chains = chains
     ops.conv_hook = None
     t_conv = sum(e0.elapsed_time(e1) for e0, e1, _ in recs) / 1000.0

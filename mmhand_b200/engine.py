@@ -664,9 +664,8 @@ class GeneratorEngine(EngineBase):
         cmds = self._infer_tape.cmds
         for ci, ai, i in self._infer_slots:
             cmds[ci][1][ai] = ins[i].data_ptr()
-        self._infer_tape.keep.append(ins)            # the launches are asynchronous: keep this call's inputs alive
-        if len(self._infer_tape.keep) > 64:
-            del self._infer_tape.keep[:32]
+        # (no need to keep `ins` alive past this call: the launches that read them are ordered before anything the
+        # caller enqueues later on the launch stream -- the chain streams join it inside the recorded sequence)
         self._infer_tape.replay(0)
         return self._infer_out
 
