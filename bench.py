@@ -278,15 +278,24 @@ def run_ours(a):
             fl = 2.0 * d.M * d.N_store * d.C_store * d.T
         recs[kind].append((e0, e1, fl))
 
+    ew = {}
+
+    def ew_hook(kind, nbytes, launch):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        launch()
+        e1.record()
+        ew.setdefault(kind, []).append((e0, e1, float(nbytes)))
+
     model.use_tape = False
-    ops.conv_hook = hook
+    ops.conv_hook, ops.ew_hook = hook, ew_hook
     side, ops.side_stream = ops.side_stream, None      # serial launches: a kernel's events bracket that kernel alone
     chains, ops.chains = ops.chains, [None]
     model.set_input(dev[0])
     model.optimize_parameters()
     torch.cuda.synchronize()
     ops.side_stream, ops.chains = side, chains
-    ops.conv_hook = None
+    ops.conv_hook = ops.ew_hook = None
     model.use_tape = True
     peaks = {}
     try:
@@ -314,6 +323,23 @@ def run_ours(a):
     roofline["step_tensor_util"] = GFLOP_PER_IMG * 1e9 * value / world / (peak * 1e12)
     roofline_wgrad = roof("wgrad", "wgrad2_kernel (tcgen05 weight gradient, csrc/tc_wgrad2.cu)", None,
                           "algorithmic 2*MACs over all grid rows with un-padded channel counts")
+    hbm = peaks.get("hbm_gbs", 6400.0)
+    names = {"bn_bwd": "rows_reduce_fin_kernel<BnLeanReduceF> + rows_pg_kernel<BnLeanApplyF> (BatchNorm backward: sums, "
+                       "then data gradient; csrc/elementwise.cu)",
+             "norm_act": "pg_kernel<NormActF> (BN apply + ReLU + dropout + residual + next layer's halo)"}
+    roofline_ew = []
+    for kind in ("bn_bwd", "norm_act"):
+        r = ew.get(kind, [])
+        t = sum(e0.elapsed_time(e1) for e0, e1, _ in r) / 1000.0
+        by = sum(b for _, _, b in r)
+        ach = by / t / 1e9 if t > 0 else 0.0
+        roofline_ew.append({"bound": "hbm", "kernel": names[kind], "achieved": ach, "peak": hbm, "unit": "GB/s",
+                            "frac": ach / hbm, "traffic": None, "launches_per_step": len(r),
+                            "kernel_ms_per_step": t * 1000.0,
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback",
+                            "bytes_note": "algorithmic bytes: bf16 elements read and written once (reduce 4 B, apply 6 B, "
+                                          "norm_act 2 + 2 B incl. the halo, + fp32 residual / trunk where present); "
+                                          "35-140 MB per launch"})
     chains_used = len(model.netG.engine(B, S, S, model.world)._chains())
     if world > 1:
         dist.barrier()                       # every rank is done measuring before the group goes away
@@ -340,7 +366,7 @@ def run_ours(a):
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 6 * 4,
                 "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline,
-        "rooflines_other": [roofline_wgrad],
+        "rooflines_other": [roofline_wgrad] + roofline_ew,
     }
     if world == 1 and not a.no_cpu_baseline:
         rate, n, cores = cpu_reference_rate(S, a.cpu_seconds)

@@ -106,6 +106,7 @@ class Ops:
         self.chains = [None]     # side-stream index per layer chain (one entry: no chain concurrency)
         self._ev = None
         self.conv_hook = None    # optional callable(kind, plan, launch) wrapping conv launches (bench instrumentation)
+        self.ew_hook = None      # optional callable(kernel class, algorithmic bytes, launch) for the bandwidth-bound kernels
 
     @staticmethod
     def cuda(device=None):
@@ -176,7 +177,16 @@ class Ops:
     def st(self):
         return C.c_void_p(self._stream())
 
-    def _run(self, fn, args, patch=None, keep=None):
+    def _run(self, fn, args, patch=None, keep=None, meta=None):
+        """meta = (kernel class, algorithmic bytes): lets bench.py bracket bandwidth-bound launches with CUDA events
+        (``ew_hook``; eager launches only, like ``conv_hook``)."""
+        if meta is not None and self.ew_hook is not None and self.tape is None:
+            hook, self.ew_hook = self.ew_hook, None
+            try:
+                hook(meta[0], meta[1], lambda: self._run(fn, args, patch, keep))
+            finally:
+                self.ew_hook = hook
+            return
         rc = fn(*args)
         self.launches += 1
         if rc != 0:
@@ -342,7 +352,8 @@ class Ops:
         p, patch = self._bn_bwd(dz, dz_f32, relu, dropout, key, x, xl, coef, save, sums=sums, k=k)
         args, patch = self._peer_args(world, (C.byref(p), _p(counter), float(count_global), _p(dgamma), _p(dbeta),
                                               self.st()), patch)
-        self._run(self.lib.mmh_bn_bwd_reduce_finalize, args, patch, keep=p)
+        self._run(self.lib.mmh_bn_bwd_reduce_finalize, args, patch, keep=p,
+                  meta=("bn_bwd", 2 * self.lib.act_bytes * xl.B * xl.H * xl.W * xl.C))
 
     def gate_bwd_reduce_finalize(self, world, dout, c1, x2o, x3o, sl, coef, save, sums, k, counter, count_global,
                                  dgamma, dbeta):
@@ -382,7 +393,10 @@ class Ops:
         p.dl = clay(dl) if dl is not None else clay(sl)
         p.pad_lo, p.pad_hi, p.reflect = pad_lo, pad_hi, 1 if reflect else 0
         p.dst_f32 = _p(dst_f32)
-        self._run(self.lib.mmh_norm_act, (C.byref(p), self.st()), patch, keep=p)
+        ab, n_el = self.lib.act_bytes, sl.B * sl.H * sl.W * sl.C
+        out_el = (dl.rows * dl.C if (dl is not None and dst is not None) else 0)
+        by = ab * n_el + ab * out_el + (4 * n_el if resid is not None else 0) + (4 * n_el if dst_f32 is not None else 0)
+        self._run(self.lib.mmh_norm_act, (C.byref(p), self.st()), patch, keep=p, meta=("norm_act", by))
 
     def gate_fwd(self, c1, x2o, x3o, sl, coef, trunk_in, trunk_out, d1, d1l, d2, d2l, d3, d3l, pad_lo, pad_hi, reflect):
         p = L.GateFwd()
@@ -430,7 +444,8 @@ class Ops:
 
     def bn_bwd_apply(self, dz, dz_f32, relu, dropout, key, x, xl, coef, save, k, dy, yl):
         p, patch = self._bn_bwd(dz, dz_f32, relu, dropout, key, x, xl, coef, save, k=k, dy=dy, yl=yl)
-        self._run(self.lib.mmh_bn_bwd_apply, (C.byref(p), self.st()), patch, keep=p)
+        self._run(self.lib.mmh_bn_bwd_apply, (C.byref(p), self.st()), patch, keep=p,
+                  meta=("bn_bwd", 3 * self.lib.act_bytes * xl.B * xl.H * xl.W * xl.C))
 
     def bn_bwd_finalize(self, sums_global, sums_local, count, k, dgamma, dbeta, Cc):
         self._run(self.lib.mmh_bn_bwd_finalize, (_p(sums_global), _p(sums_local), float(count), _p(k), _p(dgamma),
