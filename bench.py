@@ -321,7 +321,10 @@ def run_ours(a):
                     "algorithmic 2*MACs of the valid output positions (padded-grid rows excluded); the stems' channel "
                     "padding (3/6/24/42 -> 16/16/32/48) is included")
     roofline["step_tensor_util"] = GFLOP_PER_IMG * 1e9 * value / world / (peak * 1e12)
-    roofline_wgrad = roof("wgrad", "wgrad2_kernel (tcgen05 weight gradient, csrc/tc_wgrad2.cu)", None,
+    roofline_wgrad = roof("wgrad", "wgrad2_kernel (tcgen05 weight gradient, csrc/tc_wgrad2.cu)",
+                          # one 3x3 256->256 launch at batch 16 (ncu --set full, profiles/r02_wgrad2_ncu_full.txt): 74.3 MB read +
+                          # 4.3 MB written against 35.7 (dY) + 35.7 (activations) + 2.4 (dw) MB algorithmic
+                          {"bytes_per_launch_3x3_256": 78.5e6, "algorithmic_bytes": 73.8e6} if (B == 16 and S == 256) else None,
                           "algorithmic 2*MACs over all grid rows with un-padded channel counts")
     hbm = peaks.get("hbm_gbs", 6400.0)
     names = {"bn_bwd": "rows_reduce_fin_kernel<BnLeanReduceF> + rows_pg_kernel<BnLeanApplyF> (BatchNorm backward: sums, "
@@ -334,7 +337,11 @@ def run_ours(a):
         by = sum(b for _, _, b in r)
         ach = by / t / 1e9 if t > 0 else 0.0
         roofline_ew.append({"bound": "hbm", "kernel": names[kind], "achieved": ach, "peak": hbm, "unit": "GB/s",
-                            "frac": ach / hbm, "traffic": None, "launches_per_step": len(r),
+                            # one C = 256, 64 x 64 pair at batch 16 (profiles/r02_bn_lean_ncu_full.txt): reduce 69.4 MB read;
+                            # apply 69.3 MB read + 33.6 MB written (8.2 MB of it reach DRAM inside the launch)
+                            "traffic": ({"bytes_per_pair_c256": 69.4e6 + 69.3e6 + 33.6e6, "algorithmic_bytes": 67.1e6 * 2 + 33.6e6}
+                                        if (kind == "bn_bwd" and B == 16 and S == 256) else None),
+                            "frac": ach / hbm, "launches_per_step": len(r),
                             "kernel_ms_per_step": t * 1000.0,
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback",
                             "bytes_note": "algorithmic bytes: bf16 elements read and written once (reduce 4 B, apply 6 B, "
