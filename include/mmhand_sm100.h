@@ -284,7 +284,8 @@ int mmh_bce_logits(const float* x, int64_t n, float target, float loss_scale, fl
 /* F.l1_loss on images (losses/L1_plus_perceptualLoss.py:37): grad_acc[i] += grad_scale*sign(a-b) (may be NULL) */
 int mmh_l1_f32(const float* a, const float* b, int64_t n, float loss_scale, float grad_scale, float* loss_acc,
                float* grad_acc, void* stream);
-/* perceptual L1/MSE between two post-ReLU feature grids + gradient through the ReLU (:63-71) */
+/* perceptual L1/MSE between two feature grids + gradient (:63-71). mse: bit 0 = squared error; bit 1 = the features end
+ * on a convolution (perceptual_layers 0 / 2), else on a ReLU whose mask the gradient takes (perceptual_layers 1 / 3) */
 int mmh_perc_loss(const void* ff, const void* ft, int64_t n, int32_t mse, float loss_scale, float grad_scale,
                   float* loss_acc, void* dy, void* stream);
 /* tanh backward into the last conv's dY grid (models/Generator.py:259): dy = dfake * (1 - fake^2) */

@@ -3,8 +3,8 @@
 with n(x) = ((x + 1) / 2 - mean) / std, returning ``(loss, loss_l1, loss_perceptual)``.
 
 The VGG slice runs on the tcgen05 conv kernels (bias + ReLU in the epilogue), the two reductions and their
-gradients on the fused loss kernels. Only ``perceptual_layers == 3`` (conv1_1, ReLU, conv1_2, ReLU -- the value every
-shipped script uses) is built. Pretrained weights, in this order: ``MMH_VGG19_WEIGHTS`` (a torchvision ``vgg19``
+gradients on the fused loss kernels. ``perceptual_layers`` 0...3 are built (3 = conv1_1, ReLU, conv1_2, ReLU is the value
+every shipped script uses; deeper slices would need the max-pool stages). Pretrained weights, in this order: ``MMH_VGG19_WEIGHTS`` (a torchvision ``vgg19``
 state_dict file), torchvision's hub cache, ``torchvision.models.vgg19(weights=IMAGENET1K_V1)`` (a download, what the
 reference does, :22). If none of them works the constructor RAISES -- a training run must not silently optimise against
 random features -- unless ``MMH_VGG19_RANDOM=1`` opts into the seeded random initialisation (tests, benchmarks and the
@@ -21,14 +21,16 @@ from mmhand_b200.engine import VggEngine
 
 
 def _vgg_slice(perceptual_layers):
-    if perceptual_layers != 3:
-        raise NotImplementedError("perceptual_layers=%r: only the shipped value 3 (VGG19.features[0:4]) is built"
-                                  % (perceptual_layers,))
+    """vgg19.features[0 : perceptual_layers + 1] as the reference builds it (:22-27)."""
+    if not (0 <= perceptual_layers <= 3):
+        raise NotImplementedError("perceptual_layers=%r: the B200 path builds VGG19.features up to index 3 (conv1_1, ReLU, "
+                                  "conv1_2, ReLU; 3 is the value every shipped script uses) -- deeper slices need the "
+                                  "max-pool stages" % (perceptual_layers,))
+    layers = [("0", nn.Conv2d(3, 64, 3, padding=1)), ("1", nn.ReLU(inplace=True)), ("2", nn.Conv2d(64, 64, 3, padding=1)),
+              ("3", nn.ReLU(inplace=True))][:perceptual_layers + 1]
     seq = nn.Sequential()
-    seq.add_module("0", nn.Conv2d(3, 64, 3, padding=1))
-    seq.add_module("1", nn.ReLU(inplace=True))
-    seq.add_module("2", nn.Conv2d(64, 64, 3, padding=1))
-    seq.add_module("3", nn.ReLU(inplace=True))
+    for name, m in layers:
+        seq.add_module(name, m)
     path = os.environ.get("MMH_VGG19_WEIGHTS", "")
     sd = None
     if path and os.path.exists(path):
@@ -48,8 +50,9 @@ def _vgg_slice(perceptual_layers):
                 "state_dict (vgg19-dcbb9e9d.pth), or set MMH_VGG19_RANDOM=1 to run the perceptual loss on seeded "
                 "random features (tests / benchmarks only)." % (type(e).__name__, e)) from e
     if sd is not None:
-        seq.load_state_dict({k[len("features."):]: v for k, v in sd.items()
-                             if k in ("features.0.weight", "features.0.bias", "features.2.weight", "features.2.bias")})
+        want = ["features.0.weight", "features.0.bias"] + (["features.2.weight", "features.2.bias"]
+                                                           if perceptual_layers >= 2 else [])
+        seq.load_state_dict({k[len("features."):]: v for k, v in sd.items() if k in want})
     else:
         warnings.warn("MMH_VGG19_RANDOM=1: the perceptual loss uses random-init VGG19 features")
     return seq
@@ -86,6 +89,7 @@ class L1_plus_perceptualLoss(nn.Module):
         self.lambda_perceptual = lambda_perceptual
         self.gpu_ids = gpu_ids
         self.percep_is_l1 = percep_is_l1
+        self.perceptual_layers = perceptual_layers
         self.vgg_submodel = _vgg_slice(perceptual_layers)
         for p in self.vgg_submodel.parameters():
             p.requires_grad_(False)       # never optimised by the reference either
@@ -96,8 +100,9 @@ class L1_plus_perceptualLoss(nn.Module):
         key = (B, H, W, str(ops.device))
         if key not in self._eng:
             self._eng.clear()
-            v = self.vgg_submodel
-            self._eng[key] = VggEngine(ops, v[0].weight, v[0].bias, v[2].weight, v[2].bias, B, H, W)
+            v, two = self.vgg_submodel, self.perceptual_layers >= 2
+            self._eng[key] = VggEngine(ops, v[0].weight, v[0].bias, v[2].weight if two else None,
+                                       v[2].bias if two else None, B, H, W, layers=self.perceptual_layers)
         return self._eng[key]
 
     def forward(self, inputs, targets):

@@ -28,7 +28,7 @@ struct L1F {
 };
 
 struct PercF {
-  const act_t* ff; const act_t* ft; act_t* dy; int mse; float ls, gs;
+  const act_t* ff; const act_t* ft; act_t* dy; int mse, linear; float ls, gs;
   MMH_HD float operator()(int64_t i) const {
     float a[8], b[8], g[8];
     ld8_bf16(ff + i * 8, a);
@@ -40,7 +40,7 @@ struct PercF {
       float gr;
       if (mse) { s += d * d; gr = 2.f * d; }
       else { s += fabsf(d); gr = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); }
-      g[j] = a[j] > 0.f ? gs * gr : 0.f;   // through the ReLU that produced ff
+      g[j] = (linear || a[j] > 0.f) ? gs * gr : 0.f;   // through the ReLU that produced ff (if one did)
     }
     if (dy != nullptr) st8_bf16(dy + i * 8, g);
     return ls * s;
@@ -135,7 +135,8 @@ extern "C" int mmh_perc_loss(const void* ff, const void* ft, int64_t n, int32_t 
   MMH_CHECK((n % 8) == 0, "element count must be a multiple of 8");
   PercF f;
   f.ff = static_cast<const act_t*>(ff); f.ft = static_cast<const act_t*>(ft);
-  f.dy = static_cast<act_t*>(dy); f.mse = mse; f.ls = loss_scale; f.gs = grad_scale;
+  // mse: bit 0 = squared error instead of absolute; bit 1 = the features are a convolution's output, not a ReLU's
+  f.dy = static_cast<act_t*>(dy); f.mse = mse & 1; f.linear = (mse >> 1) & 1; f.ls = loss_scale; f.gs = grad_scale;
   return launch_reduce_scalar(f, n / 8, loss_acc, stream);
 }
 

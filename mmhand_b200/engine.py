@@ -945,25 +945,32 @@ VGG_STD = (0.229, 0.224, 0.225)
 
 
 class VggEngine:
-    """VGG19.features[0:4] on two inputs (generated image: slot 0, target: slot 1) + perceptual loss backward."""
+    """VGG19.features[0 : layers + 1] on two inputs (generated image: slot 0, target: slot 1) + perceptual loss backward.
+    layers = 3 (the shipped value): conv, ReLU, conv, ReLU; 2: without the last ReLU; 1: conv, ReLU; 0: conv."""
 
-    def __init__(self, ops: Ops, w1, b1, w2, b2, B, H, W):
-        self.ops, self.B, self.H, self.W = ops, B, H, W
+    def __init__(self, ops: Ops, w1, b1, w2, b2, B, H, W, layers=3):
+        assert 0 <= layers <= 3
+        self.ops, self.B, self.H, self.W, self.layers = ops, B, H, W, layers
         self._scratch = {}
         E = self
-        self.w = [t.detach().to(ops.device, torch.float32).contiguous() for t in (w1, b1, w2, b2)]
+        self.two = layers >= 2                      # second convolution present
+        self.linear = layers in (0, 2)              # the features end on a convolution, not on a ReLU
+        self.w = [t.detach().to(ops.device, torch.float32).contiguous() for t in ((w1, b1, w2, b2) if self.two else (w1, b1))]
         g1 = geom_s1(B, H, W, 3, 'zero', 16, 64)
         g2 = geom_s1(B, H, W, 3, 'zero', 64, 64)
         self.c1, self.c2 = [], []
         for slot in range(2):
-            c2 = ConvL(E, "vgg2.%d" % slot, g2, 64, 64, self.w[2], bias=self.w[3], act=1)
-            c1 = ConvL(E, "vgg1.%d" % slot, g1, 3, 64, self.w[0], bias=self.w[1], act=1, raw_buf=c2.x)
-            # conv1 writes straight into conv2's zero-haloed input
-            c1.fwd = convops.fwd_plans(ops.lib, g1, c1.x, c1.wp, c2.x, 16, 64, bias=c1.bias_p, act=1,
-                                       out_map=(g2.in_lay.Hg * g2.in_lay.Wg, g2.in_lay.Wg, 1, 1, 1, 1),
-                                       zero_invalid=False)
+            if self.two:
+                c2 = ConvL(E, "vgg2.%d" % slot, g2, 64, 64, self.w[2], bias=self.w[3], act=0 if self.linear else 1)
+                c1 = ConvL(E, "vgg1.%d" % slot, g1, 3, 64, self.w[0], bias=self.w[1], act=1, raw_buf=c2.x)
+                # conv1 writes straight into conv2's zero-haloed input
+                c1.fwd = convops.fwd_plans(ops.lib, g1, c1.x, c1.wp, c2.x, 16, 64, bias=c1.bias_p, act=1,
+                                           out_map=(g2.in_lay.Hg * g2.in_lay.Wg, g2.in_lay.Wg, 1, 1, 1, 1),
+                                           zero_invalid=False)
+                self.c2.append(c2)
+            else:
+                c1 = ConvL(E, "vgg1.%d" % slot, g1, 3, 64, self.w[0], bias=self.w[1], act=0 if self.linear else 1)
             self.c1.append(c1)
-            self.c2.append(c2)
         for c in self.c1 + self.c2:
             c.pack(False)
         mean = torch.tensor(VGG_MEAN, dtype=torch.float32)
@@ -983,20 +990,25 @@ class VggEngine:
         """Backward buffers, plans and data-gradient operands of the generated-image slot (once)."""
         if self.bwd_ready:
             return
-        c1, c2 = self.c1[0], self.c2[0]
-        c2.need_dx = True
-        c2.prepare_backward("v2", "v2", need_wgrad=False)
+        c1 = self.c1[0]
+        if self.two:
+            c2 = self.c2[0]
+            c2.need_dx = True
+            c2.prepare_backward("v2", "v2", need_wgrad=False)
         c1.prepare_backward("v1", "v1", need_wgrad=False)
-        c2.pack(True)
+        if self.two:
+            c2.pack(True)
         c1.pack(True)
         self.bwd_ready = True
 
     def features(self, x, slot):
-        c1, c2 = self.c1[slot], self.c2[slot]
+        c1 = self.c1[slot]
         self.ops.assemble(x, None, c1.x, c1.g.in_lay, 1, 1, False, scale=self.scale, shift=self.shift)
         c1.run_fwd()
-        c2.run_fwd()
-        return c2.raw
+        if not self.two:
+            return c1.raw
+        self.c2[slot].run_fwd()
+        return self.c2[slot].raw
 
     def loss_and_backward(self, fake, target, lambda_perc, mse, loss_acc, dfake):
         """*loss_acc += lambda * mean|f - t| ; dfake (NCHW fp32) += d loss / d fake (None: loss only)."""
@@ -1004,14 +1016,17 @@ class VggEngine:
         ff = self.features(fake, 0)
         ft = self.features(target, 1)
         n = B * 64 * H * W
-        c1, c2 = self.c1[0], self.c2[0]
+        c1 = self.c1[0]
+        last = self.c2[0] if self.two else c1
         if dfake is None:
-            ops.perc_loss(ff, ft, mse, lambda_perc / n, 0.0, loss_acc, None)
+            ops.perc_loss(ff, ft, mse, lambda_perc / n, 0.0, loss_acc, None, linear=self.linear)
             return
         self.prepare_training()
-        ops.perc_loss(ff, ft, mse, lambda_perc / n, lambda_perc / n, loss_acc, c2.dy)
-        c2.run_bwd(False)
-        # through the ReLU of conv1 (its output lives in conv2's input buffer)
-        ops.grad_gather([c2.dx_source()], B, H, W, 64, c1.dy, c1.g.out_lay, False, mask=c2.x, ml=c2.g.in_lay)
+        ops.perc_loss(ff, ft, mse, lambda_perc / n, lambda_perc / n, loss_acc, last.dy, linear=self.linear)
+        if self.two:
+            c2 = self.c2[0]
+            c2.run_bwd(False)
+            # through the ReLU of conv1 (its output lives in conv2's input buffer)
+            ops.grad_gather([c2.dx_source()], B, H, W, 64, c1.dy, c1.g.out_lay, False, mask=c2.x, ml=c2.g.in_lay)
         c1.run_bwd(False)
         ops.input_grad_nchw(c1.dx_source(), self.scale, dfake, B, 3, H, W, True)

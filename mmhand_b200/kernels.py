@@ -481,8 +481,9 @@ class Ops:
         self._run(self.lib.mmh_l1_f32, (_p(a), _p(b), a.numel(), loss_scale, grad_scale, _p(loss_acc), _p(grad_acc),
                                         self.st()), keep=(a, b, loss_acc, grad_acc))
 
-    def perc_loss(self, ff, ft, mse, loss_scale, grad_scale, loss_acc, dy=None):
-        self._run(self.lib.mmh_perc_loss, (_p(ff), _p(ft), ff.numel(), 1 if mse else 0, loss_scale, grad_scale,
+    def perc_loss(self, ff, ft, mse, loss_scale, grad_scale, loss_acc, dy=None, linear=False):
+        """linear: the features end on a convolution (no ReLU mask in the gradient)."""
+        self._run(self.lib.mmh_perc_loss, (_p(ff), _p(ft), ff.numel(), (1 if mse else 0) | (2 if linear else 0), loss_scale, grad_scale,
                                            _p(loss_acc), _p(dy), self.st()), keep=(loss_acc,))
 
     def tanh_bwd(self, dfake, fake, dy, yl: Lay, Cc):

@@ -227,18 +227,26 @@ VGG_MEAN = (0.485, 0.456, 0.406)
 VGG_STD = (0.229, 0.224, 0.225)
 
 
-def vgg_features(vgg_sd, x):
-    """VGG19.features[0:4] = conv3-64, ReLU, conv64-64, ReLU (perceptual_layers=3)."""
-    h = F.relu(F.conv2d(x, vgg_sd["0.weight"], vgg_sd["0.bias"], padding=1))
-    return F.relu(F.conv2d(h, vgg_sd["2.weight"], vgg_sd["2.bias"], padding=1))
+def vgg_features(vgg_sd, x, perceptual_layers=3):
+    """VGG19.features[0 : perceptual_layers + 1] (L1_plus_perceptualLoss.py:22-27): conv3-64 (0), ReLU (1), conv64-64 (2),
+    ReLU (3) -- the shipped value 3 gives all four; 0 / 2 end on a convolution, without its ReLU."""
+    h = F.conv2d(x, vgg_sd["0.weight"], vgg_sd["0.bias"], padding=1)
+    if perceptual_layers >= 1:
+        h = F.relu(h)
+    if perceptual_layers >= 2:
+        h = F.conv2d(h, vgg_sd["2.weight"], vgg_sd["2.bias"], padding=1)
+    if perceptual_layers >= 3:
+        h = F.relu(h)
+    assert perceptual_layers <= 3, "deeper slices (max-pool onwards) are not restated"
+    return h
 
 
-def l1_plus_perceptual(vgg_sd, inputs, targets, lambda_l1, lambda_perc, percep_is_l1=1):
+def l1_plus_perceptual(vgg_sd, inputs, targets, lambda_l1, lambda_perc, percep_is_l1=1, perceptual_layers=3):
     loss_l1 = F.l1_loss(inputs, targets) * lambda_l1
     mean = torch.tensor(VGG_MEAN, device=inputs.device).view(1, 3, 1, 1)
     std = torch.tensor(VGG_STD, device=inputs.device).view(1, 3, 1, 1)
-    f = vgg_features(vgg_sd, ((inputs + 1) / 2 - mean) / std)
-    t = vgg_features(vgg_sd, ((targets + 1) / 2 - mean) / std).detach()
+    f = vgg_features(vgg_sd, ((inputs + 1) / 2 - mean) / std, perceptual_layers)
+    t = vgg_features(vgg_sd, ((targets + 1) / 2 - mean) / std, perceptual_layers).detach()
     if percep_is_l1 == 1:
         loss_p = F.l1_loss(f, t) * lambda_perc
     else:

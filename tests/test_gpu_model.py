@@ -455,3 +455,26 @@ def test_taped_inference_matches_eager(monkeypatch):
         en = g(xa).clone()
         torch.cuda.synchronize()
     assert torch.equal(tn, en) and not torch.equal(tn, ta)
+
+
+@pytest.mark.parametrize("p", [0, 2, 3])
+def test_perceptual_layers_variants(p):
+    """L1_plus_perceptualLoss with perceptual_layers = 0 / 2 (features end on a convolution: no ReLU mask) and 3, at
+    256 x 256 against the oracle: loss values to 1e-2 relative, gradient direction."""
+    from losses.L1_plus_perceptualLoss import L1_plus_perceptualLoss
+    from oracle import patn_ref as O
+    torch.manual_seed(8)
+    L = L1_plus_perceptualLoss(10.0, 10.0, p, [0], 1).to(DEV)
+    g = torch.Generator().manual_seed(5)
+    fake = (torch.rand(2, 3, 256, 256, generator=g) * 2 - 1).to(DEV).requires_grad_(True)
+    tgt = (torch.rand(2, 3, 256, 256, generator=g) * 2 - 1).to(DEV)
+    out = L(fake, tgt)
+    out[0].backward()
+    vsd = {k: v.detach().clone() for k, v in L.vgg_submodel.state_dict().items()}
+    fo = fake.detach().clone().requires_grad_(True)
+    oo = O.l1_plus_perceptual(vsd, fo, tgt, 10.0, 10.0, 1, perceptual_layers=p)
+    oo[0].backward()
+    for a, b in zip(out, oo):
+        assert abs(a.item() - b.item()) <= 1e-2 * abs(b.item()), (p, a.item(), b.item())
+    cos = torch.nn.functional.cosine_similarity(fake.grad.flatten(), fo.grad.flatten(), dim=0).item()
+    assert cos > 0.98, (p, cos)

@@ -460,3 +460,26 @@ def test_taped_inference_matches_eager_and_follows_new_inputs_and_weights(emu_bf
         monkeypatch.setenv("MMH_INFER_TAPE", "0")
         en = g(xa).clone()
     assert torch.equal(tn, en) and not torch.equal(tn, ta)
+
+
+@pytest.mark.parametrize("p", [0, 1, 2])
+@pytest.mark.parametrize("is_l1", [1, 0])
+def test_perceptual_layers_variants(emu_f32, p, is_l1):
+    """perceptual_layers != 3 (reference L1_plus_perceptualLoss.py:22-27 cuts vgg19.features after that index): loss
+    values and the gradient w.r.t. the generated image against the oracle (pinned to the reference class by
+    tests/golden/perc_layers.pt)."""
+    from losses.L1_plus_perceptualLoss import L1_plus_perceptualLoss
+    torch.manual_seed(8)
+    L = L1_plus_perceptualLoss(10.0, 10.0, p, [0], is_l1)
+    assert len(L.vgg_submodel) == p + 1
+    fake = (torch.rand(2, 3, 32, 32) * 2 - 1).requires_grad_(True)
+    tgt = torch.rand(2, 3, 32, 32) * 2 - 1
+    out = L(fake, tgt)
+    out[0].backward()
+    vsd = {k: v.detach().clone() for k, v in L.vgg_submodel.state_dict().items()}
+    fo = fake.detach().clone().requires_grad_(True)
+    oo = O.l1_plus_perceptual(vsd, fo, tgt, 10.0, 10.0, is_l1, perceptual_layers=p)
+    oo[0].backward()
+    for a, b in zip(out, oo):
+        assert abs(a.item() - b.item()) <= 2e-5 * abs(b.item())
+    assert (fake.grad - fo.grad).abs().max() <= 2e-5 * fo.grad.abs().max()

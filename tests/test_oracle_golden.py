@@ -89,3 +89,20 @@ def test_discriminator_variants_match_reference_class():
         y = O.discriminator_forward(c["sd"], c["x"], train=False, use_dropout=True, n_blocks=2, n_downsampling=nd)
         assert y.shape == c["y"].shape
         assert torch.allclose(y, c["y"], atol=1e-6), (nd, (y - c["y"]).abs().max())
+
+
+def test_perceptual_layer_variants_match_reference_class():
+    """oracle.l1_plus_perceptual(perceptual_layers = 0..3, L1 and MSE) reproduces the reference L1_plus_perceptualLoss
+    (values and input gradient) recorded by oracle/make_golden_perc.py."""
+    import os
+    import torch
+    from oracle import patn_ref as O
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "perc_layers.pt"))
+    for p in (0, 1, 2, 3):
+        for is_l1 in (1, 0):
+            c = g["p%d_l1%d" % (p, is_l1)]
+            x = g["x"].clone().requires_grad_(True)
+            loss, l1, lp = O.l1_plus_perceptual(c["sd"], x, g["t"], 10.0, 10.0, is_l1, perceptual_layers=p)
+            loss.backward()
+            assert abs(float(l1) - float(c["l1"])) < 1e-5 and abs(float(lp) - float(c["lp"])) < 1e-5 * max(1, float(c["lp"]))
+            assert torch.allclose(x.grad, c["grad"], atol=1e-7, rtol=1e-4), (p, is_l1)
