@@ -483,3 +483,28 @@ def test_perceptual_layers_variants(emu_f32, p, is_l1):
     for a, b in zip(out, oo):
         assert abs(a.item() - b.item()) <= 2e-5 * abs(b.item())
     assert (fake.grad - fo.grad).abs().max() <= 2e-5 * fo.grad.abs().max()
+
+
+def test_dropin_modules_reproduce_reference_outputs_mid_size(emu_f32):
+    """The drop-in Generator / Discriminator (host-emulated kernels, fp32 storage) against the outputs the REFERENCE
+    modules produced for the same weights and inputs (tests/golden/mid_outputs.pt: ngf = ndf = 16, 64 x 64, 9 PAT blocks
+    / 3 residual blocks, eval and train mode) -- no oracle in between."""
+    from models.Discriminator import Discriminator
+    from models.Generator import Generator
+    from models.network_utils import get_norm_layer
+    from oracle.golden_weights import fill
+    from oracle.make_golden_mid import inputs
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "mid_outputs.pt"))
+    x, xd = inputs(gold["input_seed"])
+    norm = get_norm_layer('batch')
+    g = Generator([3, 42, 6], 3, 16, norm, False, 9)
+    g.load_state_dict(fill(g.state_dict(), 1))
+    d = Discriminator(24, 16, norm, False, 3, [], 'reflect', False, 2)
+    d.load_state_dict(fill(d.state_dict(), 2))
+    with torch.no_grad():
+        g.eval(); d.eval()
+        assert torch.allclose(g(x), gold["g_eval"], atol=5e-5)
+        assert torch.allclose(d(xd), gold["d_eval"], atol=5e-4, rtol=1e-4)
+        g.train(); d.train()
+        assert torch.allclose(g(x), gold["g_train"], atol=5e-5)
+        assert torch.allclose(d(xd), gold["d_train"], atol=5e-4, rtol=1e-4)

@@ -106,3 +106,29 @@ def test_perceptual_layer_variants_match_reference_class():
             loss.backward()
             assert abs(float(l1) - float(c["l1"])) < 1e-5 and abs(float(lp) - float(c["lp"])) < 1e-5 * max(1, float(c["lp"]))
             assert torch.allclose(x.grad, c["grad"], atol=1e-7, rtol=1e-4), (p, is_l1)
+
+
+def test_mid_size_outputs_match_reference_modules():
+    """ngf = ndf = 16, 64 x 64, 9 PAT blocks / 3 residual blocks: the oracle reproduces the reference Generator /
+    Discriminator outputs (eval and train mode) stored by oracle/make_golden_mid.py. Weights come from
+    oracle/golden_weights.fill over the state_dict keys of THIS repository's drop-in modules (the reference's key set --
+    tests/test_state_dict_compat.py), inputs from the recorded seed."""
+    import os
+    import torch
+    from models.Discriminator import Discriminator
+    from models.Generator import Generator
+    from models.network_utils import get_norm_layer
+    from oracle import patn_ref as O
+    from oracle.golden_weights import fill
+    from oracle.make_golden_mid import inputs
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "mid_outputs.pt"))
+    x, xd = inputs(g["input_seed"])
+    norm = get_norm_layer('batch')
+    sd_g = fill(Generator([3, 42, 6], 3, 16, norm, False, 9).state_dict(), 1)
+    sd_d = fill(Discriminator(24, 16, norm, False, 3, [], 'reflect', False, 2).state_dict(), 2)
+    with torch.no_grad():
+        for mode, train in (("eval", False), ("train", True)):
+            yg = O.generator_forward({k: v.clone() for k, v in sd_g.items()}, x, train=train, use_dropout=False)
+            yd = O.discriminator_forward({k: v.clone() for k, v in sd_d.items()}, xd, train, False)
+            assert torch.allclose(yg, g["g_" + mode], atol=2e-5), (mode, (yg - g["g_" + mode]).abs().max())
+            assert torch.allclose(yd, g["d_" + mode], atol=2e-4, rtol=1e-4), (mode, (yd - g["d_" + mode]).abs().max())
